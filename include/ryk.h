@@ -1,0 +1,142 @@
+/*
+ * ryk.h -- C ABI of libryk.so: the B200-native per-chunk hot path of realtime-yukarin
+ *          (encode -> stage 1 -> stage 2 -> vocode).  Plain pointers and sizes only.
+ *
+ * Every entry point replaces one call the reference makes into an un-vendored third-party library
+ * (file:line are paths under the reference checkout, realtime_voice_conversion/ abbreviated rvc/):
+ *
+ *   ryk_world_analyze          <- yukarin.AcousticFeature.extract (pyworld dio/stonemask/cheaptrick/d4c + pysptk.sp2mc)
+ *                                 rvc/yukarin_wrapper/vocoder.py:26-48, rvc/yukarin_wrapper/acoustic_feature_wrapper.py:28-33
+ *   ryk_world_f0               <- yukarin.AcousticFeature.extract_f0 (override hook at acoustic_feature_wrapper.py:66-80)
+ *   ryk_silence_mask           <- AcousticConverter.separate_effective (librosa _signal_to_frame_nonsilent)  rvc/yukarin_wrapper/voice_changer.py:27-31
+ *   ryk_stage1_load/_convert   <- yukarin.AcousticConverter(...)/.convert (Chainer forward)                   voice_changer.py:33, converter/yukarin_converter.py:40-46
+ *   ryk_mc2sp                  <- AcousticConverter.decode_spectrogram (pysptk.mc2sp)                           voice_changer.py:38
+ *   ryk_stage2_load/_convert   <- become_yukarin.SuperResolution(...)/.convert (Chainer forward)               voice_changer.py:41, converter/yukarin_converter.py:50-55
+ *   ryk_convert_window         <- VoiceChanger.convert_from_acoustic_feature, fused on device                   voice_changer.py:24-42
+ *   ryk_synth_create           <- world4py apidefinitions._InitializeSynthesizer                                rvc/yukarin_wrapper/vocoder.py:79-87
+ *   ryk_synth_add_parameters   <- world4py apidefinitions._AddParameters                                        vocoder.py:99
+ *   ryk_synth_synthesis2       <- world4py apidefinitions._Synthesis2 (+ the per-sample buffer read-out)        vocoder.py:102-104
+ *   ryk_synth_decode           <- RealtimeVocoder.decode as one call (add + drain)                              vocoder.py:89-120
+ *   ryk_session_*              <- the encode/convert/decode StreamWrapper chain of one audio stream kept on
+ *                                 device                                                                       rvc/worker/*.py, rvc/stream/*.py
+ *
+ * Conventions: all functions return 0 on success and a negative value on error unless stated otherwise
+ * (ryk_last_error() describes the failure); "host" pointers are ordinary process memory, "dev"
+ * pointers are CUDA device memory of the engine's GPU.  One engine per process per GPU; an engine is
+ * NOT thread-safe (the reference drives each stage from a single thread as well).
+ */
+#ifndef RYK_H_
+#define RYK_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ryk_engine ryk_engine;
+
+int ryk_abi_version(void);
+const char* ryk_last_error(void);
+
+/* ---- engine ---------------------------------------------------------------------------- */
+int ryk_engine_create(int device, ryk_engine** out);
+int ryk_engine_destroy(ryk_engine* e);
+/* 0: FP32 CUDA-core convolutions everywhere (bisecting / numerics reference)
+ * 1: FP16 operands + FP32 accumulate on tcgen05 tensor cores for the stage-2 k4 layers (default) */
+int ryk_engine_set_precision(ryk_engine* e, int mode);
+int ryk_engine_get_precision(ryk_engine* e);
+long long ryk_engine_launch_count(ryk_engine* e);        /* kernels launched by this engine so far */
+int ryk_engine_synchronize(ryk_engine* e);
+
+/* ---- WORLD analysis (encode) -------------------------------------------------------------- */
+/* wave_host: n float32 samples.  Outputs are n_frames = n / hop rows (hop = fs * frame_period / 1000):
+ * f0 [n_frames], sp/ap [n_frames][fft_length/2+1], mc [n_frames][order+1], voiced [n_frames] (0/1).
+ * f0_override (nullable, double[n_frames_world = n/hop + 1]) replaces DIO+StoneMask. Any output may be NULL. */
+int ryk_world_analyze(ryk_engine* e, const float* wave_host, int n, int fs, double frame_period_ms,
+                      double f0_floor, double f0_ceil, int fft_length, int order, double alpha,
+                      const double* f0_override, float* f0, float* sp, float* ap, float* mc, uint8_t* voiced);
+/* DIO + StoneMask only; f0/t are double[n / hop + 1] (WORLD's own frame count). */
+int ryk_world_f0(ryk_engine* e, const float* wave_host, int n, int fs, double frame_period_ms,
+                 double f0_floor, double f0_ceil, double* f0, double* t);
+int ryk_world_num_frames(int n, int fs, double frame_period_ms);
+
+/* ---- silence gate --------------------------------------------------------------------------- */
+/* mask[n_frames] (0/1); threshold_db < 0 disables the gate (all frames effective). */
+int ryk_silence_mask(ryk_engine* e, const float* wave_host, int n, int frame_length, int hop,
+                     double threshold_db, int n_frames, uint8_t* mask);
+
+/* ---- networks ------------------------------------------------------------------------------- */
+/* stage: 1 (1-D, yukarin) or 2 (2-D, become-yukarin).  Layers 0..7 = encoder c0..c7, 8..15 = decoder c0..c7.
+ * W is the model file's (Chainer) layout: conv (Cout, Cin, k[, k]), transposed conv (Cin, Cout, k[, k]);
+ * scale/shift [Cout] are the bias and eval-mode BatchNorm folded together (y = conv(x) * scale + shift). */
+int ryk_model_create(ryk_engine* e, int stage, int in_channels, int out_channels, int base_channels);
+int ryk_model_set_layer(ryk_engine* e, int stage, int layer, const float* W, const float* scale, const float* shift);
+int ryk_model_layer_shape(ryk_engine* e, int stage, int layer, int* transposed, int* cin, int* cout, int* k);
+/* per-channel normalisation of the stage-1 input/output features and the log-f0 statistics */
+int ryk_stage1_set_stats(ryk_engine* e, int channels, const float* in_mean, const float* in_std,
+                         const float* out_mean, const float* out_std);
+int ryk_f0_set_stats(ryk_engine* e, double in_mean, double in_std, double target_mean, double target_std);
+/* x, y: [T][channels] float32 (T >= 1; internally padded to the next multiple of 128 with the per-channel minimum) */
+int ryk_stage1_convert(ryk_engine* e, const float* x, int T, float* y);
+/* f0_out[i] = voiced[i] ? exp((ln f0[i] - mu_in) / sd_in * sd_tgt + mu_tgt) : 0 */
+int ryk_f0_convert(ryk_engine* e, const float* f0, const uint8_t* voiced, int T, float* f0_out);
+/* mc [T][order+1] float32 -> sp [T][fftlen/2+1] float64 = exp(H mc) (pysptk.mc2sp) */
+int ryk_mc2sp(ryk_engine* e, const float* mc, int T, int order, double alpha, int fftlen, double* sp);
+/* sp, out: [T][513] float32 */
+int ryk_stage2_convert(ryk_engine* e, const float* sp, int T, float* out);
+
+/* The whole VoiceChanger.convert_from_acoustic_feature on device: one upload, one download.
+ * in : wave [n_wave], f0 [T], ap [T][nb], mc [T][order+1], voiced [T]
+ * out: f0 [T], ap [T][nb], sp [T][nb], voiced [T], mc [T][order+1] (nullable)      nb = fftlen/2+1 */
+int ryk_convert_window(ryk_engine* e, const float* wave, int n_wave, int fs, int frame_length, int hop, double threshold_db,
+                       const float* f0, const float* ap, const float* mc, const uint8_t* voiced, int T,
+                       int order, double alpha, int fftlen,
+                       float* f0_out, float* ap_out, float* sp_out, uint8_t* voiced_out, float* mc_out);
+
+/* ---- WORLD realtime synthesizer (vocode) ------------------------------------------------------ */
+int ryk_synth_create(ryk_engine* e, int fs, double frame_period_ms, int fft_size, int buffer_size,
+                     int number_of_pointers, int* synth_id);
+int ryk_synth_destroy(ryk_engine* e, int synth_id);
+/* returns 1 when the frames were queued, 0 when the ring is full (world4py semantics), < 0 on error */
+int ryk_synth_add_parameters(ryk_engine* e, int synth_id, const double* f0, int n, const float* sp, const float* ap);
+/* returns 1 and writes buffer_size doubles when a block was produced, 0 when not enough pulses are queued */
+int ryk_synth_synthesis2(ryk_engine* e, int synth_id, double* buffer);
+/* add + drain in one call: out receives *n_blocks * buffer_size doubles (at most max_blocks blocks) */
+int ryk_synth_decode(ryk_engine* e, int synth_id, const double* f0, int n, const float* sp, const float* ap,
+                     double* out, int max_blocks, int* n_blocks);
+
+/* ---- device-resident streaming session (one audio stream) -------------------------------------- */
+typedef struct {
+  int fs;                       /* 24000 */
+  double frame_period_ms;       /* 5 */
+  double f0_floor, f0_ceil;     /* 71, 800 */
+  int fft_length, order;        /* 1024, 8 */
+  double alpha;                 /* 0.466 */
+  double buffer_time;           /* seconds of audio per pushed chunk (0.3) */
+  double encode_extra_time, convert_extra_time, decode_extra_time;   /* 0, 0.5, 0 */
+  double threshold_db;          /* silence gate, < 0 disables */
+  int vocoder_buffer_size;      /* 1024 */
+} ryk_session_config;
+
+int ryk_session_create(ryk_engine* e, const ryk_session_config* cfg, int* session_id);
+int ryk_session_destroy(ryk_engine* e, int session_id);
+/* One chunk through encode -> convert -> decode with host buffers (H2D + kernels + D2H inside).
+ * wave: round(fs * buffer_time) float32 samples; out: up to out_capacity float64 samples; *n_out is a
+ * multiple of vocoder_buffer_size (the remainder stays in the synthesizer, as in the reference). */
+int ryk_session_push(ryk_engine* e, int session_id, const float* wave, int n, double* out, int out_capacity, int* n_out);
+/* Same chunk step with the input already resident in HBM and the output left there (throughput measurement). */
+int ryk_session_push_device(ryk_engine* e, int session_id, const float* wave_dev, int n, double* out_dev, int out_capacity,
+                            int* n_out_dev);
+
+/* ---- diagnostics -------------------------------------------------------------------------------------- */
+/* One conv (transposed = 0) or transposed-conv layer of the U-Nets in isolation, host fp32 NHWC tensors in and
+ * out, weights in the Chainer layout; use_tc selects the FP16 tcgen05 kernel (1) or the FP32 CUDA-core kernel (0).
+ * `repeat` extra timed runs report the mean device time per run (ms) -- used by the unit parity tests and ncu. */
+int ryk_test_conv_layer(ryk_engine* e, int transposed, int k, int stride, int pad, int B, int Hin, int Win, int C0, int C1, int Cout,
+                        const float* in0, const float* in1, const float* W, const float* scale, const float* shift, int act,
+                        int use_tc, int repeat, float* out, float* ms_per_run);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* RYK_H_ */

@@ -1,0 +1,208 @@
+"""ctypes front-end of oracle/world_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+CPU restatement of the WORLD / SPTK arithmetic reached from
+realtime_voice_conversion/yukarin_wrapper/vocoder.py:26-48 (analysis), voice_changer.py:38 (mc2sp)
+and vocoder.py:72-120 (realtime synthesis).  PARITY UNPINNED (see world_oracle.c header).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+import ctypes
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_SO = _HERE / '_build' / 'libworld_oracle.so'
+_SRC = _HERE / 'world_oracle.c'
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_float_p = ctypes.POINTER(ctypes.c_float)
+c_int_p = ctypes.POINTER(ctypes.c_int)
+c_ll_p = ctypes.POINTER(ctypes.c_longlong)
+
+
+def build(force: bool = False) -> Path:
+    """gcc -O2 the C restatement into oracle/_build/ (a few hundred ms)."""
+    if force or not _SO.exists() or _SO.stat().st_mtime < _SRC.stat().st_mtime:
+        _SO.parent.mkdir(exist_ok=True)
+        subprocess.check_call(['gcc', '-O2', '-fPIC', '-shared', '-std=c99', '-o', str(_SO), str(_SRC), '-lm'])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(str(_SO))
+        _lib.wo_synth_create.restype = ctypes.c_void_p
+        _lib.wo_synth_create.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        _lib.wo_synth_add.argtypes = [ctypes.c_void_p, c_double_p, ctypes.c_int, c_float_p, c_float_p]
+        _lib.wo_synth_synthesis2.argtypes = [ctypes.c_void_p, c_double_p]
+        _lib.wo_synth_destroy.argtypes = [ctypes.c_void_p]
+        _lib.wo_synth_pulse_count.argtypes = [ctypes.c_void_p]
+        _lib.wo_synth_pulse_count.restype = ctypes.c_longlong
+        _lib.wo_synth_get_pulses.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, c_ll_p, c_double_p, c_int_p]
+        _lib.wo_randn_stream.argtypes = [ctypes.c_longlong, ctypes.c_int, c_double_p]
+        _lib.wo_cheaptrick_fft_size.argtypes = [ctypes.c_int, ctypes.c_double]
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_double_p)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def cheaptrick_fft_size(fs: int, f0_floor: float = 71.0) -> int:
+    return lib().wo_cheaptrick_fft_size(int(fs), float(f0_floor))
+
+
+def fft(x: np.ndarray, sign: int = -1) -> np.ndarray:
+    re = _f64(x.real).copy()
+    im = _f64(x.imag).copy() if np.iscomplexobj(x) else np.zeros_like(re)
+    lib().wo_fft(_dp(re), _dp(im), ctypes.c_int(len(re)), ctypes.c_int(sign))
+    return re + 1j * im
+
+
+def interp1(x, y, xi):
+    x, y, xi = _f64(x), _f64(y), _f64(xi)
+    out = np.empty_like(xi)
+    lib().wo_interp1(_dp(x), _dp(y), ctypes.c_int(len(x)), _dp(xi), ctypes.c_int(len(xi)), _dp(out))
+    return out
+
+
+def randn_stream(start: int, n: int) -> np.ndarray:
+    out = np.empty(n)
+    lib().wo_randn_stream(start, n, _dp(out))
+    return out
+
+
+def dio(x, fs, frame_period=5.0, f0_floor=71.0, f0_ceil=800.0, debug=False):
+    x = _f64(x)
+    n = lib().wo_dio_num_frames(int(fs), len(x), ctypes.c_double(frame_period))
+    t = np.empty(n)
+    f0 = np.empty(n)
+    nb = 1 + int(np.log(f0_ceil / f0_floor) / 0.69314718055994529 * 2.0)
+    cand = np.empty((nb, n))
+    score = np.empty((nb, n))
+    lib().wo_dio(_dp(x), ctypes.c_int(len(x)), ctypes.c_int(int(fs)), ctypes.c_double(frame_period),
+                 ctypes.c_double(f0_floor), ctypes.c_double(f0_ceil), _dp(t), _dp(f0), _dp(cand), _dp(score))
+    if debug:
+        return f0, t, cand, score
+    return f0, t
+
+
+def stonemask(x, fs, t, f0):
+    x, t, f0 = _f64(x), _f64(t), _f64(f0)
+    out = np.empty_like(f0)
+    lib().wo_stonemask(_dp(x), ctypes.c_int(len(x)), ctypes.c_int(int(fs)), _dp(t), _dp(f0), ctypes.c_int(len(f0)), _dp(out))
+    return out
+
+
+def cheaptrick(x, fs, t, f0, fft_size=None, q1=-0.15):
+    x, t, f0 = _f64(x), _f64(t), _f64(f0)
+    if fft_size is None:
+        fft_size = cheaptrick_fft_size(fs)
+    sp = np.empty((len(f0), fft_size // 2 + 1))
+    lib().wo_cheaptrick(_dp(x), ctypes.c_int(len(x)), ctypes.c_int(int(fs)), _dp(t), _dp(f0), ctypes.c_int(len(f0)),
+                        ctypes.c_int(fft_size), ctypes.c_double(q1), _dp(sp))
+    return sp
+
+
+def d4c(x, fs, t, f0, fft_size=None, threshold=0.85, debug=False):
+    x, t, f0 = _f64(x), _f64(t), _f64(f0)
+    if fft_size is None:
+        fft_size = cheaptrick_fft_size(fs)
+    ap = np.empty((len(f0), fft_size // 2 + 1))
+    ap0 = np.empty(len(f0))
+    lib().wo_d4c(_dp(x), ctypes.c_int(len(x)), ctypes.c_int(int(fs)), _dp(t), _dp(f0), ctypes.c_int(len(f0)),
+                 ctypes.c_int(fft_size), ctypes.c_double(threshold), _dp(ap), _dp(ap0))
+    if debug:
+        return ap, ap0
+    return ap
+
+
+def freqt(c, order, alpha):
+    c = _f64(c)
+    out = np.empty(order + 1)
+    lib().wo_freqt(_dp(c), ctypes.c_int(len(c) - 1), _dp(out), ctypes.c_int(order), ctypes.c_double(alpha))
+    return out
+
+
+def sp2mc(sp, order, alpha):
+    sp = _f64(sp)
+    T, nb = sp.shape
+    mc = np.empty((T, order + 1))
+    lib().wo_sp2mc(_dp(sp), ctypes.c_int(T), ctypes.c_int((nb - 1) * 2), ctypes.c_int(order), ctypes.c_double(alpha), _dp(mc))
+    return mc
+
+
+def mc2sp(mc, alpha, fftlen):
+    mc = _f64(mc)
+    T, d = mc.shape
+    sp = np.empty((T, fftlen // 2 + 1))
+    lib().wo_mc2sp(_dp(mc), ctypes.c_int(T), ctypes.c_int(d - 1), ctypes.c_double(alpha), ctypes.c_int(fftlen), _dp(sp))
+    return sp
+
+
+def frame_mse(wave, frame_length, hop, n_frames=None):
+    w = np.ascontiguousarray(wave, dtype=np.float32)
+    if n_frames is None:
+        n_frames = 1 + len(w) // hop
+    out = np.empty(n_frames)
+    lib().wo_frame_mse(w.ctypes.data_as(c_float_p), ctypes.c_int(len(w)), ctypes.c_int(frame_length), ctypes.c_int(hop),
+                       _dp(out), ctypes.c_int(n_frames))
+    return out
+
+
+class RealtimeSynthesizer:
+    """Restatement of world4py's WorldSynthesizer + _InitializeSynthesizer/_AddParameters/_Synthesis2
+    (call sites: realtime_voice_conversion/yukarin_wrapper/vocoder.py:79-103)."""
+
+    def __init__(self, fs, frame_period, fft_size, buffer_size, ring_frames=4096):
+        self.buffer_size = buffer_size
+        self.fft_size = fft_size
+        self._h = lib().wo_synth_create(int(fs), float(frame_period), int(fft_size), int(buffer_size), int(ring_frames))
+
+    def add_parameters(self, f0, sp, ap) -> int:
+        f0 = _f64(np.asarray(f0).ravel())
+        sp = np.ascontiguousarray(sp, dtype=np.float32)
+        ap = np.ascontiguousarray(ap, dtype=np.float32)
+        return lib().wo_synth_add(self._h, _dp(f0), ctypes.c_int(len(f0)), sp.ctypes.data_as(c_float_p), ap.ctypes.data_as(c_float_p))
+
+    def synthesis2(self):
+        out = np.empty(self.buffer_size)
+        ok = lib().wo_synth_synthesis2(self._h, _dp(out))
+        return out if ok else None
+
+    def pulses(self):
+        n = lib().wo_synth_pulse_count(self._h)
+        idx = np.empty(n, dtype=np.int64)
+        tm = np.empty(n)
+        vuv = np.empty(n, dtype=np.int32)
+        if n:
+            lib().wo_synth_get_pulses(self._h, 0, int(n), idx.ctypes.data_as(c_ll_p), _dp(tm), vuv.ctypes.data_as(c_int_p))
+        return idx, tm, vuv
+
+    def decode(self, f0, sp, ap) -> np.ndarray:
+        """RealtimeVocoder.decode (vocoder.py:89-120): add, then drain whole blocks."""
+        self.add_parameters(f0, sp, ap)
+        ys = []
+        while True:
+            y = self.synthesis2()
+            if y is None:
+                break
+            ys.append(y)
+        return np.concatenate(ys) if ys else np.empty(0)
+
+    def __del__(self):
+        try:
+            lib().wo_synth_destroy(self._h)
+        except Exception:
+            pass

@@ -1,0 +1,600 @@
+// api.cu -- the C ABI of libryk.so (include/ryk.h).  Host pointers in, host pointers out; every
+// entry point uploads its arguments, runs the CUDA path on the engine's stream and downloads the
+// result.  The device-resident streaming session lives in session.cu.
+#include <math.h>
+#include <stddef.h>
+#include <string.h>
+#include <mutex>
+#include <vector>
+
+#include "../../include/ryk.h"
+#include "conv.h"
+#include "engine.h"
+#include "fft.cuh"
+#include "features.h"
+#include "synth.h"
+#include "unet.h"
+
+namespace ryk {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+
+void fft_fill_twiddles(double2* t) {
+  for (int k = 0; k < kTwiddleN / 2; ++k) t[k] = make_double2(cos(2.0 * kPi * k / kTwiddleN), -sin(2.0 * kPi * k / kTwiddleN));
+}
+
+int engine_scratch(Engine* e, size_t bytes, void** out) {
+  if (bytes > e->scratch_bytes) {
+    RYK_CUDA(cudaStreamSynchronize(e->stream));
+    if (e->d_scratch) RYK_CUDA(cudaFree(e->d_scratch));
+    size_t cap = bytes + bytes / 4 + (1 << 20);
+    RYK_CUDA(cudaMalloc(&e->d_scratch, cap));
+    e->scratch_bytes = cap;
+  }
+  *out = e->d_scratch;
+  return 0;
+}
+
+int engine_pinned(Engine* e, size_t bytes, void** out) {
+  if (bytes > e->pinned_bytes) {
+    RYK_CUDA(cudaStreamSynchronize(e->stream));
+    if (e->h_pinned) RYK_CUDA(cudaFreeHost(e->h_pinned));
+    size_t cap = bytes + bytes / 4 + (1 << 16);
+    RYK_CUDA(cudaMallocHost(&e->h_pinned, cap));
+    e->pinned_bytes = cap;
+  }
+  *out = e->h_pinned;
+  return 0;
+}
+
+struct Arena {
+  char* base; size_t off = 0;
+  explicit Arena(void* b) : base((char*)b) {}
+  template <typename T> T* take(size_t count) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = (T*)(base + off);
+    off += count * sizeof(T);
+    return p;
+  }
+};
+static size_t arena_need(std::initializer_list<size_t> sizes) {
+  size_t t = 0;
+  for (size_t s : sizes) t = ((t + 255) & ~(size_t)255) + s;
+  return t + 256;
+}
+
+int dio_get_plan(Engine* e, int n, int fs, double frame_period, double f0_floor, double f0_ceil, DioPlan** out) {
+  auto key = std::make_tuple(n, fs, (int)lround(frame_period * 1000), (int)lround(f0_floor * 1000), (int)lround(f0_ceil * 1000));
+  auto it = e->dio_plans.find(key);
+  if (it != e->dio_plans.end()) { *out = it->second; return 0; }
+  DioPlan* p = nullptr;
+  if (dio_plan_create(e, n, fs, frame_period, f0_floor, f0_ceil, &p)) return -1;
+  e->dio_plans[key] = p;
+  *out = p;
+  return 0;
+}
+
+static UNet*& stage_net(Engine* e, int stage) { return stage == 1 ? e->stage1 : e->stage2; }
+
+static int upload_vec(float** d, const float* h, int n) {
+  if (*d) cudaFree(*d);
+  RYK_CUDA(cudaMalloc(d, sizeof(float) * n));
+  RYK_CUDA(cudaMemcpy(*d, h, sizeof(float) * n, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static int ensure_stage1_stats(Engine* e, int C) {
+  if (e->d_s1_in_mean && (int)e->s1_in_mean.size() == C) return 0;
+  std::vector<float> zero(C, 0.f), one(C, 1.f);
+  e->s1_in_mean = zero; e->s1_in_std = one; e->s1_out_mean = zero; e->s1_out_std = one;
+  if (upload_vec(&e->d_s1_in_mean, zero.data(), C)) return -1;
+  if (upload_vec(&e->d_s1_in_std, one.data(), C)) return -1;
+  if (upload_vec(&e->d_s1_out_mean, zero.data(), C)) return -1;
+  if (upload_vec(&e->d_s1_out_std, one.data(), C)) return -1;
+  return 0;
+}
+
+__global__ void k_affine_rows(const float* __restrict__ y, int T, int C, const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < T * C) out[i] = __fadd_rn(__fmul_rn(y[i], scale[i % C]), shift[i % C]);
+}
+
+__global__ void k_f32_to_f16(const float* __restrict__ a, __half* __restrict__ b, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) b[i] = __float2half_rn(a[i]);
+}
+__global__ void k_f16_to_f32(const __half* __restrict__ a, float* __restrict__ b, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) b[i] = __half2float(a[i]);
+}
+
+__global__ void k_f0_convert(const float* __restrict__ f0, const uint8_t* __restrict__ voiced, int T, double mu_i, double sd_i,
+                             double mu_t, double sd_t, int has_stats, float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T) return;
+  float v = 0.f;
+  if (voiced[i]) v = has_stats ? (float)exp((log((double)f0[i]) - mu_i) / sd_i * sd_t + mu_t) : f0[i];
+  out[i] = v;
+}
+
+// stage-1 forward on device buffers: x already normalised+padded in plan->d_in; returns plan
+static int stage1_plan_for(Engine* e, int Tp, UNetPlan** plan) {
+  RYK_CHECK(e->stage1 != nullptr, "stage-1 model not loaded");
+  return unet_get_plan(e, e->stage1, 1, 1, Tp, 0, plan);
+}
+static int stage2_plan_for(Engine* e, int Tp, UNetPlan** plan) {
+  RYK_CHECK(e->stage2 != nullptr, "stage-2 model not loaded");
+  return unet_get_plan(e, e->stage2, 1, Tp, 512, e->precision, plan);
+}
+
+}  // namespace ryk
+
+using namespace ryk;
+
+struct ryk_engine { Engine impl; };
+static Engine* E(ryk_engine* e) { return &e->impl; }
+
+extern "C" {
+
+int ryk_abi_version(void) { return 1; }
+const char* ryk_last_error(void) { return g_err.c_str(); }
+
+int ryk_engine_create(int device, ryk_engine** out) {
+  RYK_CHECK(out != nullptr, "null out pointer");
+  int count = 0;
+  RYK_CUDA(cudaGetDeviceCount(&count));
+  RYK_CHECK(count > 0 && device < count, "no such CUDA device (libryk has no CPU fallback)");
+  RYK_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  RYK_CUDA(cudaGetDeviceProperties(&prop, device));
+  RYK_CHECK(prop.major == 10, "libryk is built for sm_100a (B200) only");
+  ryk_engine* h = new ryk_engine();
+  Engine* e = &h->impl;
+  e->device = device;
+  RYK_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  std::vector<double2> tw(kTwiddleN / 2);
+  fft_fill_twiddles(tw.data());
+  RYK_CUDA(cudaMalloc(&e->d_twiddle, sizeof(double2) * tw.size()));
+  RYK_CUDA(cudaMemcpy(e->d_twiddle, tw.data(), sizeof(double2) * tw.size(), cudaMemcpyHostToDevice));
+  if (analysis_kernels_init()) return -1;
+  if (tc_init()) return -1;
+  *out = h;
+  return 0;
+}
+
+int ryk_engine_destroy(ryk_engine* h) {
+  if (!h) return 0;
+  Engine* e = E(h);
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  for (auto& kv : e->dio_plans) dio_plan_free(kv.second);
+  unet_destroy(e->stage1); unet_destroy(e->stage2);
+  for (Synth* s : e->synths) synth_destroy(s);
+  session_destroy_all(e);
+  void* ptrs[] = {e->d_twiddle, e->d_jump, e->d_G, e->d_H, e->d_s1_in_mean, e->d_s1_in_std, e->d_s1_out_mean, e->d_s1_out_std, e->d_scratch};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (e->h_pinned) cudaFreeHost(e->h_pinned);
+  cudaStreamDestroy(e->stream);
+  delete h;
+  return 0;
+}
+
+int ryk_engine_set_precision(ryk_engine* h, int mode) {
+  RYK_CHECK(mode == 0 || mode == 1, "precision mode must be 0 (fp32) or 1 (fp16 tensor core)");
+  E(h)->precision = mode;
+  return 0;
+}
+int ryk_engine_get_precision(ryk_engine* h) { return E(h)->precision; }
+long long ryk_engine_launch_count(ryk_engine* h) { return E(h)->launches; }
+int ryk_engine_synchronize(ryk_engine* h) { RYK_CUDA(cudaStreamSynchronize(E(h)->stream)); return 0; }
+
+int ryk_world_num_frames(int n, int fs, double frame_period_ms) { return (int)(1000.0 * n / fs / frame_period_ms) + 1; }
+
+int ryk_world_f0(ryk_engine* h, const float* wave, int n, int fs, double fp, double f0_floor, double f0_ceil, double* f0, double* t) {
+  Engine* e = E(h);
+  RYK_CUDA(cudaSetDevice(e->device));
+  RYK_CHECK(n > 0, "empty wave");
+  DioPlan* plan = nullptr;
+  if (dio_get_plan(e, n, fs, fp, f0_floor, f0_ceil, &plan)) return -1;
+  void* scratch = nullptr;
+  if (engine_scratch(e, sizeof(float) * n + 256, &scratch)) return -1;
+  float* d_x = (float*)scratch;
+  RYK_CUDA(cudaMemcpyAsync(d_x, wave, sizeof(float) * n, cudaMemcpyHostToDevice, e->stream));
+  if (dio_stonemask_run(e, plan, d_x, e->stream)) return -1;
+  e->launches += 9;
+  int nf = dio_plan_frames(plan);
+  RYK_CUDA(cudaMemcpyAsync(f0, dio_plan_f0(plan), sizeof(double) * nf, cudaMemcpyDeviceToHost, e->stream));
+  RYK_CUDA(cudaStreamSynchronize(e->stream));
+  if (t) for (int i = 0; i < nf; ++i) t[i] = i * fp / 1000.0;
+  return 0;
+}
+
+int ryk_world_analyze(ryk_engine* h, const float* wave, int n, int fs, double fp, double f0_floor, double f0_ceil, int fft_length,
+                      int order, double alpha, const double* f0_override, float* f0, float* sp, float* ap, float* mc, uint8_t* voiced) {
+  Engine* e = E(h);
+  RYK_CUDA(cudaSetDevice(e->device));
+  int hop = (int)(fs * fp / 1000.0);
+  RYK_CHECK(hop > 0, "bad frame period");
+  int n_out = n / hop;
+  if (n_out <= 0) return 0;
+  int nb = fft_length / 2 + 1;
+  if (sptk_prepare(e, order, alpha, fft_length)) return -1;
+  DioPlan* plan = nullptr;
+  if (dio_get_plan(e, n, fs, fp, f0_floor, f0_ceil, &plan)) return -1;
+  void* scratch = nullptr;
+  size_t need = arena_need({sizeof(float) * n, sizeof(float) * n_out, sizeof(float) * n_out * nb, sizeof(float) * n_out * nb,
+                            sizeof(float) * n_out * (order + 1), (size_t)n_out});
+  if (engine_scratch(e, need, &scratch)) return -1;
+  Arena A(scratch);
+  float* d_x = A.take<float>(n);
+  float* d_f0 = A.take<float>(n_out);
+  float* d_sp = A.take<float>((size_t)n_out * nb);
+  float* d_ap = A.take<float>((size_t)n_out * nb);
+  float* d_mc = A.take<float>((size_t)n_out * (order + 1));
+  uint8_t* d_v = A.take<uint8_t>(n_out);
+  RYK_CUDA(cudaMemcpyAsync(d_x, wave, sizeof(float) * n, cudaMemcpyHostToDevice, e->stream));
+  if (f0_override) {
+    RYK_CUDA(cudaMemcpyAsync(dio_plan_f0_mut(plan), f0_override, sizeof(double) * dio_plan_frames(plan), cudaMemcpyHostToDevice, e->stream));
+  } else {
+    if (dio_stonemask_run(e, plan, d_x, e->stream)) return -1;
+    e->launches += 9;
+  }
+  if (spectral_analysis_run(e, d_x, n, fs, fp, dio_plan_f0(plan), n_out, fft_length, order, d_sp, d_ap, d_mc, d_f0, d_v, e->stream)) return -1;
+  e->launches += 3;
+  if (f0) RYK_CUDA(cudaMemcpyAsync(f0, d_f0, sizeof(float) * n_out, cudaMemcpyDeviceToHost, e->stream));
+  if (sp) RYK_CUDA(cudaMemcpyAsync(sp, d_sp, sizeof(float) * n_out * nb, cudaMemcpyDeviceToHost, e->stream));
+  if (ap) RYK_CUDA(cudaMemcpyAsync(ap, d_ap, sizeof(float) * n_out * nb, cudaMemcpyDeviceToHost, e->stream));
+  if (mc) RYK_CUDA(cudaMemcpyAsync(mc, d_mc, sizeof(float) * n_out * (order + 1), cudaMemcpyDeviceToHost, e->stream));
+  if (voiced) RYK_CUDA(cudaMemcpyAsync(voiced, d_v, n_out, cudaMemcpyDeviceToHost, e->stream));
+  RYK_CUDA(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int ryk_silence_mask(ryk_engine* h, const float* wave, int n, int frame_length, int hop, double threshold_db, int n_frames, uint8_t* mask) {
+  Engine* e = E(h);
+  RYK_CUDA(cudaSetDevice(e->device));
+  if (n_frames <= 0) return 0;
+  void* scratch = nullptr;
+  size_t need = arena_need({sizeof(float) * (size_t)(n > 0 ? n : 1), sizeof(double) * n_frames, (size_t)n_frames, sizeof(int) * n_frames, sizeof(int) * 2});
+  if (engine_scratch(e, need, &scratch)) return -1;
+  Arena A(scratch);
+  float* d_x = A.take<float>(n > 0 ? n : 1);
+  double* d_mse = A.take<double>(n_frames);
+  uint8_t* d_mask = A.take<uint8_t>(n_frames);
+  int* d_index = A.take<int>(n_frames);
+  int* d_count = A.take<int>(2);
+  if (n > 0) RYK_CUDA(cudaMemcpyAsync(d_x, wave, sizeof(float) * n, cudaMemcpyHostToDevice, e->stream));
+  if (gate_mask_run(e, d_x, n, frame_length, hop, threshold_db, n_frames, d_mse, d_mask, d_index, d_count, e->stream)) return -1;
+  RYK_CUDA(cudaMemcpyAsync(mask, d_mask, n_frames, cudaMemcpyDeviceToHost, e->stream));
+  RYK_CUDA(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int ryk_model_create(ryk_engine* h, int stage, int in_ch, int out_ch, int base) {
+  Engine* e = E(h);
+  RYK_CUDA(cudaSetDevice(e->device));
+  RYK_CHECK(stage == 1 || stage == 2, "stage must be 1 or 2");
+  UNet*& net = stage_net(e, stage);
+  if (net) { RYK_CUDA(cudaStreamSynchronize(e->stream)); unet_destroy(net); net = nullptr; }
+  net = unet_create(stage == 1 ? 1 : 2, in_ch, out_ch, base);
+  return 0;
+}
+
+int ryk_model_set_layer(ryk_engine* h, int stage, int layer, const float* W, const float* scale, const float* shift) {
+  Engine* e = E(h);
+  RYK_CUDA(cudaSetDevice(e->device));
+  UNet* net = stage_net(e, stage);
+  RYK_CHECK(net != nullptr, "ryk_model_create was not called for this stage");
+  return unet_set_layer(e, net, layer, W, scale, shift);
+}
+
+int ryk_model_layer_shape(ryk_engine* h, int stage, int layer, int* transposed, int* cin, int* cout, int* k) {
+  UNet* net = stage_net(E(h), stage);
+  RYK_CHECK(net != nullptr && layer >= 0 && layer < 16, "no such layer");
+  const UNetLayerW& L = net->layers[layer];
+  *transposed = L.transposed; *cin = L.cin; *cout = L.cout; *k = L.k;
+  return 0;
+}
+
+int ryk_stage1_set_stats(ryk_engine* h, int C, const float* in_mean, const float* in_std, const float* out_mean, const float* out_std) {
+  Engine* e = E(h);
+  RYK_CUDA(cudaSetDevice(e->device));
+  RYK_CUDA(cudaStreamSynchronize(e->stream));
+  e->s1_in_mean.assign(in_mean, in_mean + C); e->s1_in_std.assign(in_std, in_std + C);
+  e->s1_out_mean.assign(out_mean, out_mean + C); e->s1_out_std.assign(out_std, out_std + C);
+  if (upload_vec(&e->d_s1_in_mean, in_mean, C)) return -1;
+  if (upload_vec(&e->d_s1_in_std, in_std, C)) return -1;
+  if (upload_vec(&e->d_s1_out_mean, out_mean, C)) return -1;
+  if (upload_vec(&e->d_s1_out_std, out_std, C)) return -1;
+  return 0;
+}
+
+int ryk_f0_set_stats(ryk_engine* h, double in_mean, double in_std, double target_mean, double target_std) {
+  Engine* e = E(h);
+  e->f0_in_mean = in_mean; e->f0_in_std = in_std; e->f0_tgt_mean = target_mean; e->f0_tgt_std = target_std;
+  e->has_f0_stats = true;
+  return 0;
+}
+
+int ryk_stage1_convert(ryk_engine* h, const float* x, int T, float* y) {
+  Engine* e = E(h);
+  RYK_CUDA(cudaSetDevice(e->device));
+  RYK_CHECK(e->stage1 != nullptr, "stage-1 model not loaded");
+  RYK_CHECK(T > 0, "empty input");
+  const int C = e->stage1->in_ch, Co = e->stage1->out_ch;
+  if (ensure_stage1_stats(e, C)) return -1;
+  const int Tp = T + (128 - T % 128);
+  UNetPlan* plan = nullptr;
+  if (stage1_plan_for(e, Tp, &plan)) return -1;
+  void* scratch = nullptr;
+  if (engine_scratch(e, arena_need({sizeof(float) * T * C, sizeof(float) * T * Co, sizeof(int) * 2}), &scratch)) return -1;
+  Arena A(scratch);
+  float* d_x = A.take<float>((size_t)T * C);
+  float* d_y = A.take<float>((size_t)T * Co);
+  int* d_count = A.take<int>(2);
+  int cnt[2] = {T, Tp};
+  RYK_CUDA(cudaMemcpyAsync(d_x, x, sizeof(float) * T * C, cudaMemcpyHostToDevice, e->stream));
+  RYK_CUDA(cudaMemcpyAsync(d_count, cnt, sizeof(cnt), cudaMemcpyHostToDevice, e->stream));
+  if (stage1_prologue_run(e, d_x, nullptr, d_count, C, (float*)plan->d_in, Tp, e->stream)) return -1;
+  if (unet_forward(e, plan, e->stream)) return -1;
+  k_affine_rows<<<(T * Co + 255) / 256, 256, 0, e->stream>>>((const float*)plan->d_out, T, Co, e->d_s1_out_std, e->d_s1_out_mean, d_y);
+  e->launches++;
+  RYK_CUDA(cudaMemcpyAsync(y, d_y, sizeof(float) * T * Co, cudaMemcpyDeviceToHost, e->stream));
+  RYK_CUDA(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int ryk_f0_convert(ryk_engine* h, const float* f0, const uint8_t* voiced, int T, float* out) {
+  Engine* e = E(h);
+  RYK_CUDA(cudaSetDevice(e->device));
+  if (T <= 0) return 0;
+  void* scratch = nullptr;
+  if (engine_scratch(e, arena_need({sizeof(float) * T, (size_t)T, sizeof(float) * T}), &scratch)) return -1;
+  Arena A(scratch);
+  float* d_f0 = A.take<float>(T); uint8_t* d_v = A.take<uint8_t>(T); float* d_o = A.take<float>(T);
+  RYK_CUDA(cudaMemcpyAsync(d_f0, f0, sizeof(float) * T, cudaMemcpyHostToDevice, e->stream));
+  RYK_CUDA(cudaMemcpyAsync(d_v, voiced, T, cudaMemcpyHostToDevice, e->stream));
+  k_f0_convert<<<(T + 127) / 128, 128, 0, e->stream>>>(d_f0, d_v, T, e->f0_in_mean, e->f0_in_std, e->f0_tgt_mean, e->f0_tgt_std,
+                                                      e->has_f0_stats ? 1 : 0, d_o);
+  e->launches++;
+  RYK_CUDA(cudaMemcpyAsync(out, d_o, sizeof(float) * T, cudaMemcpyDeviceToHost, e->stream));
+  RYK_CUDA(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int ryk_mc2sp(ryk_engine* h, const float* mc, int T, int order, double alpha, int fftlen, double* sp) {
+  Engine* e = E(h);
+  RYK_CUDA(cudaSetDevice(e->device));
+  if (T <= 0) return 0;
+  if (sptk_prepare(e, order, alpha, fftlen)) return -1;
+  int nb = fftlen / 2 + 1;
+  void* scratch = nullptr;
+  if (engine_scratch(e, arena_need({sizeof(float) * T * (order + 1), sizeof(double) * T * nb}), &scratch)) return -1;
+  Arena A(scratch);
+  float* d_mc = A.take<float>((size_t)T * (order + 1));
+  double* d_sp = A.take<double>((size_t)T * nb);
+  RYK_CUDA(cudaMemcpyAsync(d_mc, mc, sizeof(float) * T * (order + 1), cudaMemcpyHostToDevice, e->stream));
+  if (mc2sp_run(e, d_mc, T, order, fftlen, 0.0, nullptr, d_sp, e->stream)) return -1;
+  RYK_CUDA(cudaMemcpyAsync(sp, d_sp, sizeof(double) * T * nb, cudaMemcpyDeviceToHost, e->stream));
+  RYK_CUDA(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int ryk_stage2_convert(ryk_engine* h, const float* sp, int T, float* out) {
+  Engine* e = E(h);
+  RYK_CUDA(cudaSetDevice(e->device));
+  RYK_CHECK(T > 0, "empty input");
+  const int nb = 513;
+  const int Tp = T + (128 - T % 128);
+  UNetPlan* plan = nullptr;
+  if (stage2_plan_for(e, Tp, &plan)) return -1;
+  void* scratch = nullptr;
+  if (engine_scratch(e, arena_need({sizeof(float) * T * nb, sizeof(float) * T * nb}), &scratch)) return -1;
+  Arena A(scratch);
+  float* d_sp = A.take<float>((size_t)T * nb);
+  float* d_out = A.take<float>((size_t)T * nb);
+  RYK_CUDA(cudaMemcpyAsync(d_sp, sp, sizeof(float) * T * nb, cudaMemcpyHostToDevice, e->stream));
+  if (sr_prologue_run(e, d_sp, T, Tp, nb, (float*)plan->d_in, e->stream)) return -1;
+  if (unet_forward(e, plan, e->stream)) return -1;
+  if (sr_epilogue_run(e, (const float*)plan->d_out, T, nb, d_out, e->stream)) return -1;
+  RYK_CUDA(cudaMemcpyAsync(out, d_out, sizeof(float) * T * nb, cudaMemcpyDeviceToHost, e->stream));
+  RYK_CUDA(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int ryk_convert_window(ryk_engine* h, const float* wave, int n_wave, int fs, int frame_length, int hop, double threshold_db,
+                       const float* f0, const float* ap, const float* mc, const uint8_t* voiced, int T, int order, double alpha,
+                       int fftlen, float* f0_out, float* ap_out, float* sp_out, uint8_t* voiced_out, float* mc_out) {
+  Engine* e = E(h);
+  RYK_CUDA(cudaSetDevice(e->device));
+  RYK_CHECK(T > 0, "empty window");
+  RYK_CHECK(e->stage1 && e->stage2, "models not loaded");
+  const int nb = fftlen / 2 + 1, C = order + 1;
+  RYK_CHECK(nb == 513, "stage 2 expects 513-bin spectra");
+  RYK_CHECK(e->stage1->in_ch == C && e->stage1->out_ch == C, "stage-1 channel count does not match order + 1");
+  if (sptk_prepare(e, order, alpha, fftlen)) return -1;
+  if (ensure_stage1_stats(e, C)) return -1;
+  ConvertBuffers cb;
+  if (convert_buffers_get(e, T, n_wave, nb, C, &cb)) return -1;
+  cudaStream_t st = e->stream;
+  RYK_CUDA(cudaMemcpyAsync(cb.d_wave, wave, sizeof(float) * n_wave, cudaMemcpyHostToDevice, st));
+  RYK_CUDA(cudaMemcpyAsync(cb.d_f0, f0, sizeof(float) * T, cudaMemcpyHostToDevice, st));
+  RYK_CUDA(cudaMemcpyAsync(cb.d_ap, ap, sizeof(float) * T * nb, cudaMemcpyHostToDevice, st));
+  RYK_CUDA(cudaMemcpyAsync(cb.d_mc, mc, sizeof(float) * T * C, cudaMemcpyHostToDevice, st));
+  RYK_CUDA(cudaMemcpyAsync(cb.d_voiced, voiced, T, cudaMemcpyHostToDevice, st));
+  if (convert_window_device(e, cb, T, n_wave, frame_length, hop, threshold_db, order, fftlen, st)) return -1;
+  RYK_CUDA(cudaMemcpyAsync(f0_out, cb.d_f0_out, sizeof(float) * T, cudaMemcpyDeviceToHost, st));
+  RYK_CUDA(cudaMemcpyAsync(ap_out, cb.d_ap_out, sizeof(float) * T * nb, cudaMemcpyDeviceToHost, st));
+  RYK_CUDA(cudaMemcpyAsync(sp_out, cb.d_sp_out, sizeof(float) * T * nb, cudaMemcpyDeviceToHost, st));
+  RYK_CUDA(cudaMemcpyAsync(voiced_out, cb.d_voiced_out, T, cudaMemcpyDeviceToHost, st));
+  if (mc_out) RYK_CUDA(cudaMemcpyAsync(mc_out, cb.d_mc_out, sizeof(float) * T * C, cudaMemcpyDeviceToHost, st));
+  RYK_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ---- synthesizer -------------------------------------------------------------------------------
+static Synth* get_synth(Engine* e, int id) { return (id >= 0 && id < (int)e->synths.size()) ? e->synths[id] : nullptr; }
+
+int ryk_synth_create(ryk_engine* h, int fs, double fp, int fft_size, int buffer_size, int number_of_pointers, int* synth_id) {
+  Engine* e = E(h);
+  RYK_CUDA(cudaSetDevice(e->device));
+  (void)number_of_pointers;     // world4py's pointer ring is replaced by a frame ring owned by the library
+  Synth* s = nullptr;
+  if (synth_create(e, fs, fp, fft_size, buffer_size, 4096, &s)) return -1;
+  e->synths.push_back(s);
+  *synth_id = (int)e->synths.size() - 1;
+  return 0;
+}
+
+int ryk_synth_destroy(ryk_engine* h, int id) {
+  Engine* e = E(h);
+  Synth* s = get_synth(e, id);
+  RYK_CHECK(s != nullptr, "no such synthesizer");
+  RYK_CUDA(cudaStreamSynchronize(e->stream));
+  synth_destroy(s);
+  e->synths[id] = nullptr;
+  return 0;
+}
+
+static int synth_upload(Engine* e, Synth* s, const double* f0, int n, const float* sp, const float* ap, double** d_f0, float** d_sp, float** d_ap,
+                        double** d_out, int max_blocks) {
+  int nb = s->dev.fft_size / 2 + 1;
+  void* scratch = nullptr;
+  size_t need = arena_need({sizeof(double) * n, sizeof(float) * n * nb, sizeof(float) * n * nb, sizeof(double) * (size_t)max_blocks * s->dev.buffer_size});
+  if (engine_scratch(e, need, &scratch)) return -1;
+  Arena A(scratch);
+  *d_f0 = A.take<double>(n); *d_sp = A.take<float>((size_t)n * nb); *d_ap = A.take<float>((size_t)n * nb);
+  *d_out = A.take<double>((size_t)max_blocks * s->dev.buffer_size);
+  if (n > 0) {
+    RYK_CUDA(cudaMemcpyAsync(*d_f0, f0, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
+    RYK_CUDA(cudaMemcpyAsync(*d_sp, sp, sizeof(float) * n * nb, cudaMemcpyHostToDevice, e->stream));
+    RYK_CUDA(cudaMemcpyAsync(*d_ap, ap, sizeof(float) * n * nb, cudaMemcpyHostToDevice, e->stream));
+  }
+  return 0;
+}
+
+int ryk_synth_add_parameters(ryk_engine* h, int id, const double* f0, int n, const float* sp, const float* ap) {
+  Engine* e = E(h);
+  RYK_CUDA(cudaSetDevice(e->device));
+  Synth* s = get_synth(e, id);
+  RYK_CHECK(s != nullptr, "no such synthesizer");
+  if (n <= 0) return 1;
+  double* d_f0; float *d_sp, *d_ap; double* d_out;
+  if (synth_upload(e, s, f0, n, sp, ap, &d_f0, &d_sp, &d_ap, &d_out, 1)) return -1;
+  long long before = s->host_cum_frames;
+  if (synth_add_async(e, s, d_f0, n, d_sp, d_ap, e->stream)) return -1;
+  int status = 0;
+  RYK_CUDA(cudaMemcpyAsync(&status, (char*)s->dev.state + offsetof(SynthState, last_add_status), sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  RYK_CUDA(cudaStreamSynchronize(e->stream));
+  if (!status) s->host_cum_frames = before;
+  return status;
+}
+
+int ryk_synth_synthesis2(ryk_engine* h, int id, double* buffer) {
+  Engine* e = E(h);
+  RYK_CUDA(cudaSetDevice(e->device));
+  Synth* s = get_synth(e, id);
+  RYK_CHECK(s != nullptr, "no such synthesizer");
+  void* scratch = nullptr;
+  if (engine_scratch(e, sizeof(double) * s->dev.buffer_size + 256, &scratch)) return -1;
+  double* d_out = (double*)scratch;
+  if (synth_drain_async(e, s, d_out, 1, e->stream)) return -1;
+  int blocks = 0;
+  RYK_CUDA(cudaMemcpyAsync(&blocks, (char*)s->dev.state + offsetof(SynthState, blocks_out), sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  RYK_CUDA(cudaMemcpyAsync(buffer, d_out, sizeof(double) * s->dev.buffer_size, cudaMemcpyDeviceToHost, e->stream));
+  RYK_CUDA(cudaStreamSynchronize(e->stream));
+  return blocks > 0 ? 1 : 0;
+}
+
+int ryk_synth_decode(ryk_engine* h, int id, const double* f0, int n, const float* sp, const float* ap, double* out, int max_blocks, int* n_blocks) {
+  Engine* e = E(h);
+  RYK_CUDA(cudaSetDevice(e->device));
+  Synth* s = get_synth(e, id);
+  RYK_CHECK(s != nullptr, "no such synthesizer");
+  RYK_CHECK(max_blocks > 0, "max_blocks must be positive");
+  double* d_f0; float *d_sp, *d_ap; double* d_out;
+  if (synth_upload(e, s, f0, n, sp, ap, &d_f0, &d_sp, &d_ap, &d_out, max_blocks)) return -1;
+  if (n > 0 && synth_add_async(e, s, d_f0, n, d_sp, d_ap, e->stream)) return -1;
+  if (synth_drain_async(e, s, d_out, max_blocks, e->stream)) return -1;
+  int blocks = 0;
+  RYK_CUDA(cudaMemcpyAsync(&blocks, (char*)s->dev.state + offsetof(SynthState, blocks_out), sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  RYK_CUDA(cudaStreamSynchronize(e->stream));
+  if (blocks > 0) {
+    RYK_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)blocks * s->dev.buffer_size, cudaMemcpyDeviceToHost, e->stream));
+    RYK_CUDA(cudaStreamSynchronize(e->stream));
+  }
+  *n_blocks = blocks;
+  return 0;
+}
+
+
+// ---- diagnostics: one conv / transposed-conv layer in isolation (unit parity + profiling) -------
+// in0/in1: host fp32 NHWC [B][Hin][Win][C0|C1]; W: Chainer layout; out: host fp32 NHWC [B][Hout][Wout][Cout].
+// use_tc = 1 runs the FP16 tcgen05 kernel (activations rounded to fp16), 0 the FP32 CUDA-core kernel.
+int ryk_test_conv_layer(ryk_engine* h, int transposed, int k, int stride, int pad, int B, int Hin, int Win, int C0, int C1, int Cout,
+                        const float* in0, const float* in1, const float* W, const float* scale, const float* shift, int act,
+                        int use_tc, int repeat, float* out, float* ms_per_run) {
+  Engine* e = E(h);
+  RYK_CUDA(cudaSetDevice(e->device));
+  cudaStream_t st = e->stream;
+  ConvLayer L;
+  L.transposed = transposed; L.B = B; L.Hin = Hin; L.Win = Win; L.C0 = C0; L.C1 = C1; L.Cout = Cout;
+  L.KH = L.KW = k; L.SH = L.SW = stride; L.PH = L.PW = pad; L.act = act;
+  if (transposed) { L.Hout = (Hin - 1) * stride + k - 2 * pad; L.Wout = (Win - 1) * stride + k - 2 * pad; }
+  else { L.Hout = (Hin + 2 * pad - k) / stride + 1; L.Wout = (Win + 2 * pad - k) / stride + 1; }
+  const int Cin = C0 + C1;
+  size_t n0 = (size_t)B * Hin * Win * C0, n1 = (size_t)B * Hin * Win * C1, no = (size_t)B * L.Hout * L.Wout * Cout;
+  size_t nw = (size_t)Cin * Cout * k * k;
+  std::vector<void*> frees;
+  auto A = [&](size_t bytes) -> void* { void* p = nullptr; if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) return nullptr; frees.push_back(p); return p; };
+  float* d_in0 = (float*)A(n0 * 4); float* d_in1 = (float*)A(n1 * 4); float* d_w = (float*)A(nw * 4);
+  float* d_wd = (float*)A(nw * 4); __half* d_wt = (__half*)A(nw * 2);
+  float* d_scale = (float*)A(Cout * 4); float* d_shift = (float*)A(Cout * 4);
+  __half* d_h0 = (__half*)A(n0 * 2); __half* d_h1 = (__half*)A(n1 * 2); __half* d_ho = (__half*)A(no * 2); float* d_out = (float*)A(no * 4);
+  RYK_CHECK(d_out != nullptr, "cudaMalloc failed in ryk_test_conv_layer");
+  RYK_CUDA(cudaMemcpyAsync(d_in0, in0, n0 * 4, cudaMemcpyHostToDevice, st));
+  if (n1) RYK_CUDA(cudaMemcpyAsync(d_in1, in1, n1 * 4, cudaMemcpyHostToDevice, st));
+  RYK_CUDA(cudaMemcpyAsync(d_w, W, nw * 4, cudaMemcpyHostToDevice, st));
+  RYK_CUDA(cudaMemcpyAsync(d_scale, scale, Cout * 4, cudaMemcpyHostToDevice, st));
+  RYK_CUDA(cudaMemcpyAsync(d_shift, shift, Cout * 4, cudaMemcpyHostToDevice, st));
+  if (pack_weights_direct(d_w, transposed, Cin, Cout, k, k, d_wd, st)) return -1;
+  L.w_direct = d_wd; L.scale = d_scale; L.shift = d_shift;
+  int rc = 0;
+  cudaEvent_t ev0, ev1;
+  RYK_CUDA(cudaEventCreate(&ev0)); RYK_CUDA(cudaEventCreate(&ev1));
+  if (use_tc) {
+    if (pack_weights_tc(d_w, transposed, Cin, Cout, k, k, d_wt, st)) return -1;
+    k_f32_to_f16<<<1184, 256, 0, st>>>(d_in0, d_h0, n0);
+    if (n1) k_f32_to_f16<<<1184, 256, 0, st>>>(d_in1, d_h1, n1);
+    L.in0 = d_h0; L.in1 = n1 ? d_h1 : nullptr; L.in_dtype = DT_F16; L.out = d_ho; L.out_dtype = DT_F16; L.w_tc = d_wt;
+    RYK_CHECK(tc_layer_eligible(L), "layer shape is not eligible for the tensor-core kernel");
+    int num_sms = 148;
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, e->device);
+    size_t ws = tc_splitk_ws_bytes(L, num_sms);
+    if (ws) L.splitk_ws = (float*)A(ws);
+    if (tc_layer_prepare(L, num_sms)) return -1;
+    rc = conv_tc_run(L, st);
+    RYK_CUDA(cudaEventRecord(ev0, st));
+    for (int i = 0; i < repeat && !rc; ++i) rc = conv_tc_run(L, st);
+    RYK_CUDA(cudaEventRecord(ev1, st));
+    k_f16_to_f32<<<1184, 256, 0, st>>>(d_ho, d_out, no);
+  } else {
+    L.in0 = d_in0; L.in1 = n1 ? d_in1 : nullptr; L.in_dtype = DT_F32; L.out = d_out; L.out_dtype = DT_F32;
+    rc = conv_direct_run(L, st);
+    RYK_CUDA(cudaEventRecord(ev0, st));
+    for (int i = 0; i < repeat && !rc; ++i) rc = conv_direct_run(L, st);
+    RYK_CUDA(cudaEventRecord(ev1, st));
+  }
+  if (!rc) {
+    cudaError_t err = cudaMemcpyAsync(out, d_out, no * 4, cudaMemcpyDeviceToHost, st);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+    if (err != cudaSuccess) { set_error(std::string("conv layer test failed: ") + cudaGetErrorString(err)); rc = -1; }
+  }
+  float ms = 0.f;
+  if (!rc && repeat > 0) { cudaEventElapsedTime(&ms, ev0, ev1); ms /= repeat; }
+  if (ms_per_run) *ms_per_run = ms;
+  cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+  for (void* p : frees) cudaFree(p);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,19 @@
+#!/bin/bash
+# Builds libryk.so for sm_100a (B200) in-tree.  Usage: ./build.sh [-j N]
+set -e
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -Wno-unused-variable --expt-relaxed-constexpr"
+mkdir -p _obj
+SRCS="api conv_direct conv_tc unet world_analysis world_synth features convert session"
+pids=""
+for s in $SRCS; do
+  if [ ! -f _obj/$s.o ] || [ $s.cu -nt _obj/$s.o ] || [ -n "$(find . -maxdepth 1 \( -name '*.h' -o -name '*.cuh' \) -newer _obj/$s.o 2>/dev/null)" ] || [ ../../include/ryk.h -nt _obj/$s.o ]; then
+    $NVCC $FLAGS -c $s.cu -o _obj/$s.o &
+    pids="$pids $!"
+  fi
+done
+for p in $pids; do wait $p; done
+OBJS=""; for s in $SRCS; do OBJS="$OBJS _obj/$s.o"; done
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libryk.so $OBJS -L/usr/local/cuda/lib64 -lcufft -Xlinker -rpath -Xlinker /usr/local/cuda/lib64
+echo "built $(pwd)/libryk.so"

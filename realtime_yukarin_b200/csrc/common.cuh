@@ -1,0 +1,118 @@
+// common.cuh -- shared declarations for libryk (B200 / sm_100a hot path of realtime-yukarin).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+namespace ryk {
+
+constexpr double kPi = 3.1415926535897932384;
+constexpr double kLog2 = 0.69314718055994529;
+constexpr double kSafeMin = 0.000000000001;
+constexpr double kEps = 0.00000000000000022204460492503131;
+constexpr double kDefaultF0 = 500.0;
+constexpr double kMaxValue = 100000.0;
+
+void set_error(const std::string& msg);
+
+#define RYK_CUDA(call)                                                                       \
+  do {                                                                                       \
+    cudaError_t _e = (call);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      ryk::set_error(std::string(#call) + " failed: " + cudaGetErrorString(_e) + " at " +    \
+                     __FILE__ + ":" + std::to_string(__LINE__));                             \
+      return -1;                                                                             \
+    }                                                                                        \
+  } while (0)
+
+#define RYK_CHECK(cond, msg)                                                                 \
+  do {                                                                                       \
+    if (!(cond)) {                                                                           \
+      ryk::set_error(std::string(msg) + " (" #cond ") at " + __FILE__ + ":" +                \
+                     std::to_string(__LINE__));                                              \
+      return -2;                                                                             \
+    }                                                                                        \
+  } while (0)
+
+__host__ __device__ inline int matlab_round(double x) { return x > 0 ? (int)(x + 0.5) : (int)(x - 0.5); }
+__host__ __device__ inline int imin(int a, int b) { return a < b ? a : b; }
+__host__ __device__ inline int imax(int a, int b) { return a > b ? a : b; }
+
+inline int suitable_fft_size(int sample) {
+  return (int)pow(2.0, (int)(log((double)sample) / kLog2) + 1.0);
+}
+inline int cheaptrick_fft_size(int fs, double f0_floor) {
+  return (int)pow(2.0, 1.0 + (int)(log(3.0 * fs / f0_floor + 1) / kLog2));
+}
+
+// ---- block-wide helpers (all threads of the CTA must call) ------------------------------------
+__device__ inline double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// scratch: >= 32 doubles of shared memory. Result broadcast to every thread.
+__device__ inline double block_sum(double v, double* scratch) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) scratch[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (w == 0) {
+    r = lane < nw ? scratch[lane] : 0.0;
+    r = warp_sum(r);
+    if (lane == 0) scratch[0] = r;
+  }
+  __syncthreads();
+  r = scratch[0];
+  __syncthreads();
+  return r;
+}
+
+// In-place inclusive prefix sum over smem array a[0..n) (doubles). scratch >= blockDim.x doubles.
+__device__ inline void block_inclusive_scan(double* a, int n, double* scratch) {
+  int T = blockDim.x;
+  int per = (n + T - 1) / T;
+  int lo = threadIdx.x * per, hi = min(lo + per, n);
+  double s = 0.0;
+  for (int i = lo; i < hi; ++i) { s += a[i]; a[i] = s; }
+  scratch[threadIdx.x] = s;
+  __syncthreads();
+  // exclusive scan of partial sums (T <= 1024): simple Hillis-Steele on scratch
+  for (int off = 1; off < T; off <<= 1) {
+    double v = threadIdx.x >= off ? scratch[threadIdx.x - off] : 0.0;
+    __syncthreads();
+    scratch[threadIdx.x] += v;
+    __syncthreads();
+  }
+  double base = threadIdx.x > 0 ? scratch[threadIdx.x - 1] : 0.0;
+  for (int i = lo; i < hi; ++i) a[i] += base;
+  __syncthreads();
+}
+
+// interp1Q on an equally spaced grid (origin x0, spacing dx), y has n points (delta_y[n-1] = 0).
+__device__ inline double interp1q(double x0, double dx, const double* y, int n, double xi) {
+  double pos = (xi - x0) / dx;
+  int base = (int)pos;
+  double frac = pos - base;
+  double dy = base + 1 < n ? y[base + 1] - y[base] : 0.0;
+  return y[base] + dy * frac;
+}
+
+// matlab interp1 (histc + linear, extrapolating): k = clamp(#{x[j] <= xi}, 1, n-1)
+__device__ inline double interp1_at(const double* x, const double* y, int n, double xi) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (x[mid] <= xi) lo = mid + 1; else hi = mid;
+  }
+  int k = lo < 1 ? 1 : (lo > n - 1 ? n - 1 : lo);
+  double s = (xi - x[k - 1]) / (x[k] - x[k - 1]);
+  return y[k - 1] + s * (y[k] - y[k - 1]);
+}
+
+}  // namespace ryk

@@ -1,0 +1,50 @@
+// conv.h -- convolution layer descriptors shared by the FP32 CUDA-core path (conv_direct.cu), the
+// FP16 tcgen05 tensor-core path (conv_tc.cu) and the U-Net scheduler (unet.cu).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace ryk {
+
+enum Act { ACT_NONE = 0, ACT_LEAKY = 1, ACT_RELU = 2 };
+enum DType { DT_F32 = 0, DT_F16 = 1 };
+
+// One conv / transposed-conv layer over NHWC activations (1-D nets use H = 1, KH = 1).
+// The input is the channel-concatenation of up to two tensors (U-Net skip "concat by pointer").
+struct ConvLayer {
+  int transposed = 0;
+  int B = 1, Hin = 1, Win = 1, Hout = 1, Wout = 1;
+  int C0 = 0, C1 = 0, Cout = 0;           // Cin = C0 + C1
+  int KH = 1, KW = 1, SH = 1, SW = 1, PH = 0, PW = 0;
+  int act = ACT_NONE;
+  // device pointers
+  const void* in0 = nullptr; const void* in1 = nullptr; int in_dtype = DT_F32;
+  void* out = nullptr; int out_dtype = DT_F32;
+  const float* w_direct = nullptr;        // [KH][KW][Cin][Cout] fp32
+  const float* scale = nullptr;           // [Cout] folded BN scale (1 when no BN)
+  const float* shift = nullptr;           // [Cout] folded bias / BN shift
+  // tensor-core path (filled by tc_layer_prepare)
+  const __half* w_tc = nullptr;           // conv: [Cout][KH*KW*Cin]; deconv: [4 classes][Cout][4*Cin]
+  float* splitk_ws = nullptr;             // [pixels][Cout] fp32 when ksplit > 1
+  int ksplit = 1;
+  CUtensorMap tmA0, tmA1, tmB;
+  int tile_w = 0, tile_h = 0;             // pixel tile = tile_w x tile_h = 128
+  int block_n = 0;
+  bool tc_ready = false;
+};
+
+// Weight repacking from the Chainer layouts the model files use:
+//   conv   W: (Cout, Cin, KH, KW)      deconv W: (Cin, Cout, KH, KW)
+int pack_weights_direct(const float* d_w_chainer, int transposed, int Cin, int Cout, int KH, int KW, float* d_out, cudaStream_t st);
+int pack_weights_tc(const float* d_w_chainer, int transposed, int Cin, int Cout, int KH, int KW, __half* d_out, cudaStream_t st);
+
+int conv_direct_run(const ConvLayer& L, cudaStream_t st);
+
+bool tc_layer_eligible(const ConvLayer& L);
+int tc_init();                                           // resolves cuTensorMapEncodeTiled, sets smem attributes
+int tc_layer_prepare(ConvLayer& L, int num_sms);         // builds tensor maps, picks tiles / split-K (needs final pointers)
+int conv_tc_run(const ConvLayer& L, cudaStream_t st);
+size_t tc_splitk_ws_bytes(const ConvLayer& L, int num_sms);
+
+}  // namespace ryk

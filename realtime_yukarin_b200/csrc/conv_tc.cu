@@ -1,0 +1,383 @@
+// conv_tc.cu -- tcgen05 (5th-gen tensor core) implicit-GEMM convolution for the stage-2
+// "Become-Yukarin" 2-D U-Net (component I: > 99 % of the hot path's FLOPs).
+//
+//   D[pixels, Cout] = sum over taps t, channels c of  A_t[pixels, c] * W[t, c, Cout]
+//
+// * Operands are FP16, accumulation FP32 in TMEM (kind::f16, UMMA 128 x BLOCK_N x 16).
+// * A tiles (128 output pixels x 64 input channels of ONE tap) are fetched by TMA straight from the
+//   NHWC activation tensor: a 4-D box (64 ch, tile_w, tile_h, 1) whose W/H traversal stride is the
+//   conv stride (elementStrides = 2 for the k4 s2 p1 encoder convs) and whose out-of-bounds part is
+//   zero-filled by the TMA unit -- that IS the zero padding; no im2col buffer ever exists.
+//   Transposed convs (decoder) are run per output-parity class, each a dense 2x2-tap conv.
+// * The U-Net skip concat is "by pointer": the K loop walks the channels of tensor 0, then tensor 1.
+// * B tiles (BLOCK_N output channels x 64 K) come from a K-major packed weight matrix, also by TMA.
+// * Both tiles land in the canonical 128-byte-swizzled K-major layout that UMMA smem descriptors
+//   address; a ring of kStages stages is handed between three warp roles through mbarriers:
+//     warp 4 lane 0 : TMA producer        (waits empty[s], arms full[s] with expect_tx, issues 2 loads)
+//     warp 5 lane 0 : MMA issuer          (waits full[s], 4 x tcgen05.mma, tcgen05.commit -> empty[s])
+//     warps 0-3     : epilogue            (wait tmem_full, tcgen05.ld 32 lanes x 32 columns at a time,
+//                                          folded BN scale/shift + LeakyReLU/ReLU, FP16 NHWC store)
+// * Small-M bottleneck layers are weight-bandwidth bound: split-K over blockIdx.z spreads the weight
+//   stream over all SMs, partial sums meet in an FP32 workspace (red.global.add) and a finalize
+//   kernel applies the epilogue.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "conv.h"
+
+namespace ryk {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;          // fp16 elements = 128 bytes = one swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kTcThreads = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, 128B-swizzled operand: 8-row atoms of 1024 B (SBO), LBO unused, descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((1024u >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+struct TcParams {
+  int transposed, B, Hout, Wout, Cout;
+  int Hc, Wc;                    // class-local output grid (== Hout, Wout for convs)
+  int tile_w, tile_h, tiles_w, tiles_h;
+  int chunks0, chunks1;          // 64-channel chunks of source 0 / 1
+  int taps_w, ntaps;             // taps_w = KW (conv: 4) or 2 (deconv class)
+  int stride;                    // 2 for convs, 1 for deconv classes
+  int ksplit, chunks_per_split;
+  int act;
+  const float* scale; const float* shift;
+  __half* out;
+  float* ws;                     // split-K workspace or nullptr
+};
+
+template <int BLOCK_N, int kStages>
+__global__ void __launch_bounds__(kTcThreads, 1)
+k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+          const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
+  constexpr uint32_t kBBytes = BLOCK_N * kBlockK * 2;
+  // carve: 1024-aligned stage buffers first, barriers after
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * kABytes;
+  uint64_t* full_bar = (uint64_t*)(smem_b + kStages * kBBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint32_t* tmem_ptr_smem = (uint32_t*)(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // tile coordinates
+  int mt = blockIdx.x;
+  const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+  const int th = mt % p.tiles_h; mt /= p.tiles_h;
+  const int b = mt;
+  const int n0 = blockIdx.y * BLOCK_N;
+  const int cls = blockIdx.z / p.ksplit, split = blockIdx.z % p.ksplit;
+  const int py = cls >> 1, px = cls & 1;
+  const int oy0 = th * p.tile_h, ox0 = tw * p.tile_w;       // class-local output origin of the tile
+  const int chunks_per_tap = p.chunks0 + p.chunks1;
+  const int total_chunks = p.ntaps * chunks_per_tap;
+  const int kc_begin = split * p.chunks_per_split;
+  const int kc_end = min(total_chunks, kc_begin + p.chunks_per_split);
+  const int my_chunks = kc_end - kc_begin;
+
+  if (threadIdx.x == 128) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    if (p.chunks1 > 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
+  }
+  if (threadIdx.x == 160) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {   // TMEM allocation (whole warp), BLOCK_N fp32 accumulator columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)BLOCK_N) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 4 && lane == 0) {
+    // ===== TMA producer =====
+    for (int i = 0; i < my_chunks; ++i) {
+      const int s = i % kStages;
+      const uint32_t ph = (i / kStages) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      const int kc = kc_begin + i;
+      const int tap = kc / chunks_per_tap;
+      const int cc = kc - tap * chunks_per_tap;
+      const int ty = tap / p.taps_w, tx = tap - ty * p.taps_w;
+      int ix, iy;
+      if (!p.transposed) { ix = ox0 * 2 + tx - 1; iy = oy0 * 2 + ty - 1; }
+      else { ix = ox0 + tx - 1 + px; iy = oy0 + ty - 1 + py; }
+      mbar_expect_tx(&full_bar[s], kABytes + kBBytes);
+      if (cc < p.chunks0) tma_load_4d(smem_a + s * kABytes, &tmA0, &full_bar[s], cc * kBlockK, ix, iy, b);
+      else tma_load_4d(smem_a + s * kABytes, &tmA1, &full_bar[s], (cc - p.chunks0) * kBlockK, ix, iy, b);
+      tma_load_2d(smem_b + s * kBBytes, &tmB, &full_bar[s], kc * kBlockK, cls * p.Cout + n0);
+    }
+  } else if (warp == 5 && lane == 0) {
+    // ===== MMA issuer =====
+    // instruction descriptor: D=F32, A=B=F16, both K-major, N = BLOCK_N, M = 128
+    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+    for (int i = 0; i < my_chunks; ++i) {
+      const int s = i % kStages;
+      const uint32_t ph = (i / kStages) & 1;
+      mbar_wait(&full_bar[s], ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint64_t adesc = make_sw128_desc(smem_u32(smem_a + s * kABytes));
+      const uint64_t bdesc = make_sw128_desc(smem_u32(smem_b + s * kBBytes));
+#pragma unroll
+      for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+        // advance 32 bytes (16 fp16) inside the swizzle atom: +2 in the (addr >> 4) field
+        umma_f16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (i > 0 || k > 0) ? 1u : 0u);
+      }
+      umma_commit(&empty_bar[s]);
+    }
+    umma_commit(tmem_full_bar);
+  } else if (warp < 4) {
+    // ===== epilogue =====
+    mbar_wait(tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int row = warp * 32 + lane;                 // accumulator row == TMEM lane == pixel of the tile
+    const int hl = row / p.tile_w, wl = row - hl * p.tile_w;
+    const int my = oy0 + hl, mx = ox0 + wl;            // class-local output coordinate
+    const bool valid = (my < p.Hc) && (mx < p.Wc) && my_chunks > 0;
+    int oy = my, ox = mx;
+    if (p.transposed) { oy = my * 2 + py; ox = mx * 2 + px; }
+    const size_t pix = ((size_t)(b * p.Hout + oy) * p.Wout + ox);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t r[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+            "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+            "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (valid) {
+        const int n = n0 + c0;
+        if (p.ws) {
+          float* w = p.ws + pix * p.Cout + n;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(w + j, __uint_as_float(r[j]));
+        } else {
+          __half* o = p.out + pix * p.Cout + n;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float v0 = __uint_as_float(r[j + 2 * q]) * __ldg(p.scale + n + j + 2 * q) + __ldg(p.shift + n + j + 2 * q);
+              float v1 = __uint_as_float(r[j + 2 * q + 1]) * __ldg(p.scale + n + j + 2 * q + 1) + __ldg(p.shift + n + j + 2 * q + 1);
+              if (p.act == ACT_LEAKY) { v0 = v0 > 0.f ? v0 : 0.2f * v0; v1 = v1 > 0.f ? v1 : 0.2f * v1; }
+              else if (p.act == ACT_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+              __half2 h = __floats2half2_rn(v0, v1);
+              pk[q] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(o + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BLOCK_N) : "memory");
+  }
+}
+
+// split-K finalize: out = act(ws * scale + shift) as fp16
+__global__ void k_splitk_finalize(const float* __restrict__ ws, size_t total, int Cout, const float* __restrict__ scale,
+                                  const float* __restrict__ shift, int act, __half* __restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int n = i % Cout;
+    float v = ws[i] * scale[n] + shift[n];
+    if (act == ACT_LEAKY) v = v > 0.f ? v : 0.2f * v;
+    else if (act == ACT_RELU) v = fmaxf(v, 0.f);
+    out[i] = __float2half_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+template <int BN, int ST> static constexpr size_t tc_smem_bytes() {
+  return (size_t)ST * (kBlockM * kBlockK * 2 + BN * kBlockK * 2) + (2 * ST + 1) * 8 + 16 + 1024;
+}
+
+int tc_init() {
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    RYK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    RYK_CHECK(qres == cudaDriverEntryPointSuccess && fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+    g_encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+  }
+  RYK_CUDA(cudaFuncSetAttribute(k_conv_tc<64, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<64, 6>()));
+  RYK_CUDA(cudaFuncSetAttribute(k_conv_tc<128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<128, 6>()));
+  RYK_CUDA(cudaFuncSetAttribute(k_conv_tc<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<256, 4>()));
+  return 0;
+}
+
+bool tc_layer_eligible(const ConvLayer& L) {
+  if (L.KH != 4 || L.KW != 4 || L.SH != 2 || L.SW != 2 || L.PH != 1 || L.PW != 1) return false;
+  if (L.C0 % kBlockK != 0 || L.C1 % kBlockK != 0 || L.C0 == 0) return false;
+  if (L.Cout % 64 != 0) return false;
+  if (L.in_dtype != DT_F16 || L.out_dtype != DT_F16) return false;
+  return true;
+}
+
+static int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
+
+static int make_act_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int B, int box_w, int box_h, int stride) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(box_w * stride), (cuuint32_t)(box_h * stride), 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activation) failed: " + std::to_string((int)r)); return -1; }
+  return 0;
+}
+
+static int make_weight_map(CUtensorMap* m, const void* ptr, size_t K, size_t rows, int block_n) {
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)block_n};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r)); return -1; }
+  return 0;
+}
+
+static void tc_geometry(const ConvLayer& L, int num_sms, int* tile_w, int* tile_h, int* block_n, int* ksplit) {
+  int Wc = L.transposed ? L.Win : L.Wout;
+  int Hc = L.transposed ? L.Hin : L.Hout;
+  int tw = pow2_floor(Wc < kBlockM ? Wc : kBlockM);
+  int th = kBlockM / tw;
+  int bn = L.Cout >= 256 ? 256 : (L.Cout >= 128 ? 128 : 64);
+  int tiles = L.B * ((Wc + tw - 1) / tw) * ((Hc + th - 1) / th) * (L.Cout / bn) * (L.transposed ? 4 : 1);
+  int ntaps = L.transposed ? 4 : 16;
+  int total_chunks = ntaps * (L.C0 + L.C1) / kBlockK;
+  int ks = 1;
+  if (tiles < num_sms) {
+    ks = num_sms / tiles;
+    if (ks > total_chunks / 2) ks = total_chunks / 2;   // at least 2 chunks per split
+    if (ks < 1) ks = 1;
+  }
+  *tile_w = tw; *tile_h = th; *block_n = bn; *ksplit = ks;
+}
+
+size_t tc_splitk_ws_bytes(const ConvLayer& L, int num_sms) {
+  int tw, th, bn, ks;
+  tc_geometry(L, num_sms, &tw, &th, &bn, &ks);
+  return ks > 1 ? (size_t)L.B * L.Hout * L.Wout * L.Cout * sizeof(float) : 0;
+}
+
+int tc_layer_prepare(ConvLayer& L, int num_sms) {
+  RYK_CHECK(g_encode != nullptr, "tc_init() was not called");
+  RYK_CHECK(tc_layer_eligible(L), "layer is not eligible for the tensor-core path");
+  tc_geometry(L, num_sms, &L.tile_w, &L.tile_h, &L.block_n, &L.ksplit);
+  int stride = L.transposed ? 1 : 2;
+  if (make_act_map(&L.tmA0, L.in0, L.C0, L.Win, L.Hin, L.B, L.tile_w, L.tile_h, stride)) return -1;
+  if (L.C1 > 0) { if (make_act_map(&L.tmA1, L.in1, L.C1, L.Win, L.Hin, L.B, L.tile_w, L.tile_h, stride)) return -1; }
+  else L.tmA1 = L.tmA0;
+  size_t K = (size_t)(L.transposed ? 4 : 16) * (L.C0 + L.C1);
+  size_t rows = (size_t)(L.transposed ? 4 : 1) * L.Cout;
+  if (make_weight_map(&L.tmB, L.w_tc, K, rows, L.block_n)) return -1;
+  RYK_CHECK(L.ksplit == 1 || L.splitk_ws != nullptr, "split-K layer without a workspace");
+  L.tc_ready = true;
+  return 0;
+}
+
+int conv_tc_run(const ConvLayer& L, cudaStream_t st) {
+  RYK_CHECK(L.tc_ready, "tc layer not prepared");
+  TcParams p;
+  p.transposed = L.transposed; p.B = L.B; p.Hout = L.Hout; p.Wout = L.Wout; p.Cout = L.Cout;
+  p.Hc = L.transposed ? L.Hin : L.Hout; p.Wc = L.transposed ? L.Win : L.Wout;
+  p.tile_w = L.tile_w; p.tile_h = L.tile_h;
+  p.tiles_w = (p.Wc + L.tile_w - 1) / L.tile_w; p.tiles_h = (p.Hc + L.tile_h - 1) / L.tile_h;
+  p.chunks0 = L.C0 / kBlockK; p.chunks1 = L.C1 / kBlockK;
+  p.taps_w = L.transposed ? 2 : 4; p.ntaps = L.transposed ? 4 : 16;
+  p.stride = L.transposed ? 1 : 2;
+  p.ksplit = L.ksplit;
+  int total_chunks = p.ntaps * (p.chunks0 + p.chunks1);
+  p.chunks_per_split = (total_chunks + L.ksplit - 1) / L.ksplit;
+  p.act = L.act; p.scale = L.scale; p.shift = L.shift; p.out = (__half*)L.out;
+  p.ws = L.ksplit > 1 ? L.splitk_ws : nullptr;
+  size_t out_elems = (size_t)L.B * L.Hout * L.Wout * L.Cout;
+  if (p.ws) RYK_CUDA(cudaMemsetAsync(p.ws, 0, out_elems * sizeof(float), st));
+  dim3 grid(L.B * p.tiles_w * p.tiles_h, L.Cout / L.block_n, (L.transposed ? 4 : 1) * L.ksplit);
+  if (L.block_n == 256) k_conv_tc<256, 4><<<grid, kTcThreads, tc_smem_bytes<256, 4>(), st>>>(L.tmA0, L.tmA1, L.tmB, p);
+  else if (L.block_n == 128) k_conv_tc<128, 6><<<grid, kTcThreads, tc_smem_bytes<128, 6>(), st>>>(L.tmA0, L.tmA1, L.tmB, p);
+  else k_conv_tc<64, 6><<<grid, kTcThreads, tc_smem_bytes<64, 6>(), st>>>(L.tmA0, L.tmA1, L.tmB, p);
+  RYK_CUDA(cudaGetLastError());
+  if (p.ws) {
+    int blocks = (int)((out_elems + 255) / 256); if (blocks > 1184) blocks = 1184;
+    k_splitk_finalize<<<blocks, 256, 0, st>>>(p.ws, out_elems, L.Cout, L.scale, L.shift, L.act, (__half*)L.out);
+    RYK_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // namespace ryk

@@ -1,0 +1,73 @@
+// engine.h -- internal state of one libryk engine (one per process / GPU).
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "common.cuh"
+#include "unet.h"
+#include "synth.h"
+
+namespace ryk {
+
+struct DioPlan;
+struct Session;
+
+struct Engine {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int precision = 1;                 // 0: FP32 CUDA-core convs everywhere, 1: FP16 tcgen05 tensor-core convs where eligible
+  // FFT twiddles
+  double2* d_twiddle = nullptr;
+  // xorshift128 jump-ahead matrices (synthesis noise stream)
+  uint32_t* d_jump = nullptr;
+  // SPTK matrices
+  double* d_G = nullptr; int G_order = -1, G_fft = 0; double G_alpha = 0;     // sp2mc: (order+1) x nb
+  double* d_H = nullptr; int H_order = -1, H_fft = 0; double H_alpha = 0;     // mc2sp: nb x (order+1)
+  // DIO plans keyed by (n, fs, frame_period*1000, floor*1000, ceil*1000)
+  std::map<std::tuple<int, int, int, int, int>, DioPlan*> dio_plans;
+  // networks
+  UNet* stage1 = nullptr;
+  UNet* stage2 = nullptr;
+  // stage-1 statistics
+  std::vector<float> s1_in_mean, s1_in_std, s1_out_mean, s1_out_std;
+  float *d_s1_in_mean = nullptr, *d_s1_in_std = nullptr, *d_s1_out_mean = nullptr, *d_s1_out_std = nullptr;
+  double f0_in_mean = 0, f0_in_std = 1, f0_tgt_mean = 0, f0_tgt_std = 1;
+  bool has_f0_stats = false;
+  // synthesizers
+  std::vector<Synth*> synths;
+  std::vector<Session*> sessions;
+  // scratch arena for the per-op host-pointer API (grown on demand)
+  void* d_scratch = nullptr; size_t scratch_bytes = 0;
+  void* h_pinned = nullptr; size_t pinned_bytes = 0;
+  // counters
+  long long launches = 0;
+};
+
+int engine_scratch(Engine* e, size_t bytes, void** out);
+int engine_pinned(Engine* e, size_t bytes, void** out);
+
+// world_analysis.cu
+int analysis_kernels_init();
+int dio_plan_create(Engine* e, int n, int fs, double frame_period, double f0_floor, double f0_ceil, DioPlan** out);
+void dio_plan_free(DioPlan* p);
+int dio_get_plan(Engine* e, int n, int fs, double frame_period, double f0_floor, double f0_ceil, DioPlan** out);
+int dio_stonemask_run(Engine* e, DioPlan* p, const float* d_x, cudaStream_t st);
+const double* dio_plan_f0(DioPlan* p);      // refined f0 (double) after dio_stonemask_run
+double* dio_plan_f0_mut(DioPlan* p);
+int dio_plan_frames(DioPlan* p);
+int spectral_analysis_run(Engine* e, const float* d_x, int n, int fs, double frame_period, const double* d_f0, int n_out,
+                          int fft_size, int order, float* d_sp, float* d_ap, float* d_mc, float* d_f0_out, uint8_t* d_voiced,
+                          cudaStream_t st);
+
+// sptk.cu
+int sptk_prepare(Engine* e, int order, double alpha, int fft_size);                 // builds G and H on the device
+int mc2sp_run(Engine* e, const float* d_mc, int T, int order, int fft_size, double add, float* d_sp_f32, double* d_sp_f64, cudaStream_t st);
+
+// gate.cu
+int gate_mask_run(Engine* e, const float* d_wave, int n, int frame_length, int hop, double threshold_db, int n_frames,
+                  double* d_mse_scratch, uint8_t* d_mask, int* d_index /*compacted frame ids*/, int* d_count, cudaStream_t st);
+
+}  // namespace ryk

@@ -1,0 +1,42 @@
+// unet.h -- U-Net containers (weights + per-shape plans).
+#pragma once
+#include <map>
+#include <tuple>
+#include <vector>
+
+#include "conv.h"
+
+namespace ryk {
+
+struct Engine;
+
+struct UNetLayerW {
+  int transposed = 0, cin = 0, cout = 0, k = 3, s = 1, p = 1, act = 0;
+  float* d_w_direct = nullptr;
+  __half* d_w_tc = nullptr;
+  float* d_scale = nullptr;
+  float* d_shift = nullptr;
+  bool loaded = false;
+};
+
+struct UNetPlan {
+  int B = 1, H = 1, W = 0, precision = 0;
+  std::vector<ConvLayer> layers;
+  std::vector<void*> buffers;
+  void* d_in = nullptr;     // fp32 NHWC input  [B][H][W][in_ch]
+  void* d_out = nullptr;    // fp32 NHWC output [B][H][W][out_ch]
+};
+
+struct UNet {
+  int ndim = 2, in_ch = 1, out_ch = 1, base = 64;
+  std::vector<UNetLayerW> layers;                                  // 0..7 encoder, 8..15 decoder
+  std::map<std::tuple<int, int, int, int>, UNetPlan*> plans;       // (B, H, W, precision)
+};
+
+UNet* unet_create(int ndim, int in_ch, int out_ch, int base);
+void unet_destroy(UNet* n);
+int unet_set_layer(Engine* e, UNet* n, int idx, const float* W, const float* scale, const float* shift);
+int unet_get_plan(Engine* e, UNet* n, int B, int H, int W, int precision, UNetPlan** out);
+int unet_forward(Engine* e, UNetPlan* p, cudaStream_t st, int first_layer = 0, int last_layer = 15);
+
+}  // namespace ryk

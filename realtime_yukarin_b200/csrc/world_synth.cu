@@ -1,0 +1,476 @@
+// world_synth.cu -- WORLD realtime synthesizer on the B200 (component J).
+// Replaces world4py's _InitializeSynthesizer / _AddParameters / _Synthesis2 (call sites:
+// realtime_voice_conversion/yukarin_wrapper/vocoder.py:79-103) with a device-resident state machine:
+//   k_synth_add     one CTA : append frames to the device ring, sample-rate f0/vuv interpolation,
+//                             total-phase prefix scan (FP64 block scan), ordered pulse compaction
+//   k_synth_noise   one CTA : xorshift128 randn stream, addressed by absolute sample position,
+//                             generated in 8192-position tiles with GF(2) jump-ahead matrices
+//   k_synth_plan    one warp: how many 1024-sample blocks may be emitted + which pulses they need
+//   k_synth_pulse   one CTA per pulse: spectral/aperiodic interpolation, 2 minimum-phase
+//                             reconstructions + noise FFT + 2 inverse FFTs, all in shared memory
+//   k_synth_ola     gather-style overlap-add in pulse order (deterministic), emits blocks + new carry
+// The state (frame ring, pulse ring, noise ring, OLA carry, hand-off phase/f0) never leaves HBM.
+#include <math.h>
+#include <string.h>
+#include <vector>
+
+#include "engine.h"
+#include "fft.cuh"
+#include "synth.h"
+
+namespace ryk {
+
+__device__ inline double safe_ap(double x) { return fmax(0.001, fmin(0.999999999999, x)); }
+
+// ------------------------------------------------------------------------------------ add parameters
+__global__ void __launch_bounds__(1024) k_synth_add(SynthDev S, const double* __restrict__ f0, int n,
+                                                   const float* __restrict__ sp, const float* __restrict__ ap) {
+  SynthState* st = S.state;
+  __shared__ double scan_scratch[1024];
+  __shared__ long long sh_first_frame, sh_start, sh_np;
+  __shared__ int sh_ns, sh_hf, sh_ok;
+  __shared__ double sh_handoff_f0, sh_tp0;
+  __shared__ int wsum[32];
+  __shared__ int sh_total;
+  const int nb = S.fft_size / 2 + 1;
+  const double fp = S.frame_period, fs = (double)S.fs;
+  if (threadIdx.x == 0) {
+    long long oldest = (long long)(st->synthesized_sample / (fp * fs)) - 1;
+    if (oldest < 0) oldest = 0;
+    sh_ok = (st->cumulative_frame + n - oldest + 1 > S.cap_frames) ? 0 : 1;
+    st->last_add_status = sh_ok;
+  }
+  __syncthreads();
+  if (!sh_ok || n <= 0) return;
+  const long long cum_before = st->cumulative_frame;
+  // a. frames into the ring
+  for (int i = threadIdx.x; i < n; i += blockDim.x) S.f0[(cum_before + 1 + i) % S.cap_frames] = f0[i];
+  for (size_t i = threadIdx.x; i < (size_t)n * nb; i += blockDim.x) {
+    int fr = i / nb, k = i % nb;
+    size_t slot = (size_t)((cum_before + 1 + fr) % S.cap_frames) * nb + k;
+    S.sp[slot] = sp[i];
+    S.ap[slot] = ap[i];
+  }
+  __syncthreads();
+  const long long cum = cum_before + n;
+  if (cum < 1) {   // first-ever single frame: only the hand-off f0 is recorded
+    if (threadIdx.x == 0) { st->cumulative_frame = cum; st->handoff_f0 = f0[n - 1]; st->handoff = 1; }
+    return;
+  }
+  if (threadIdx.x == 0) {
+    long long first_frame = cum - n;
+    long long start = (long long)ceil((double)first_frame * fp * fs);
+    if (start < 0) start = 0;
+    long long end = (long long)ceil((double)cum * fp * fs);
+    sh_first_frame = first_frame; sh_start = start; sh_ns = (int)(end - start); sh_hf = st->handoff;
+    sh_handoff_f0 = st->handoff_f0;
+  }
+  __syncthreads();
+  const int ns = sh_ns, hf = sh_hf;
+  const long long start = sh_start;
+  const long long cum0 = sh_first_frame < 0 ? 0 : sh_first_frame;
+  const int nc = n + hf;
+  const double hf0 = sh_handoff_f0;
+  // c. sample-rate f0 / vuv (coarse axis evaluated on the fly)
+  auto ct = [&](int j) { return j == 0 ? (double)cum0 * fp : (double)(j - hf + cum0 + hf) * fp; };
+  auto cf = [&](int j) { return (hf && j == 0) ? hf0 : f0[j - hf]; };
+  for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+    double t = (double)(i + start) / fs;
+    int lo = 0, hi = nc;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (ct(mid) <= t) lo = mid + 1; else hi = mid; }
+    int k = lo < 1 ? 1 : (lo > nc - 1 ? nc - 1 : lo);
+    double x0 = ct(k - 1), x1 = ct(k);
+    double s = (t - x0) / (x1 - x0);
+    double fa = cf(k - 1), fb = cf(k);
+    double va = fa == 0.0 ? 0.0 : 1.0, vb = fb == 0.0 ? 0.0 : 1.0;
+    double fi = fa + s * (fb - fa);
+    double vi = va + s * (vb - va);
+    vi = vi > 0.5 ? 1.0 : 0.0;
+    S.if0[i] = vi == 0.0 ? kDefaultF0 : fi;
+    S.ivuv[i] = vi;
+  }
+  __syncthreads();
+  // d. total phase: tp[0] given, tp[i] = tp[i-1] + 2 pi if0[i - hf] / fs
+  const int np_ = ns + hf;
+  if (threadIdx.x == 0) sh_tp0 = hf == 1 ? st->handoff_phase : 2.0 * kPi * S.if0[0] / fs;
+  for (int i = threadIdx.x; i < np_; i += blockDim.x) S.tp[i] = i == 0 ? 0.0 : 2.0 * kPi * S.if0[i - hf] / fs;
+  __syncthreads();
+  block_inclusive_scan(S.tp, np_, scan_scratch);
+  const double tp0 = sh_tp0;
+  for (int i = threadIdx.x; i < np_; i += blockDim.x) S.tp[i] = tp0 + S.tp[i];
+  __syncthreads();
+  // e. ordered pulse compaction
+  int per = (np_ - 1 + blockDim.x - 1) / blockDim.x;
+  int lo = threadIdx.x * per, hi = min(lo + per, np_ - 1);
+  int cnt = 0;
+  for (int i = lo; i < hi; ++i) {
+    double a = fmod(S.tp[i], 2.0 * kPi), b = fmod(S.tp[i + 1], 2.0 * kPi);
+    cnt += fabs(b - a) > kPi ? 1 : 0;
+  }
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = cnt;
+  for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int v = wsum[lane], iv = v;
+    for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += u; }
+    wsum[lane] = iv - v;
+    if (lane == 31) sh_total = iv;
+  }
+  __syncthreads();
+  const long long base_pulse = st->n_pulses;
+  int pos = wsum[w] + inc - cnt;
+  for (int i = lo; i < hi; ++i) {
+    double a = fmod(S.tp[i], 2.0 * kPi), b = fmod(S.tp[i + 1], 2.0 * kPi);
+    if (fabs(b - a) > kPi) {
+      double t = (double)(i + start) / fs - (double)hf / fs;
+      long long idx = matlab_round(t * fs);
+      long long li = idx - start;
+      if (li < 0) li = 0;
+      if (li >= ns) li = ns - 1;
+      int slot = (int)((base_pulse + pos) % S.cap_pulses);
+      S.p_time[slot] = t; S.p_index[slot] = idx; S.p_vuv[slot] = S.ivuv[li] > 0.5 ? 1 : 0;
+      ++pos;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int total = sh_total;
+    if (total > 0) st->last_location = S.p_index[(base_pulse + total - 1) % S.cap_pulses];
+    st->n_pulses = base_pulse + total;
+    st->handoff_phase = S.tp[np_ - 1];
+    st->handoff_f0 = f0[n - 1];
+    st->handoff = 1;
+    st->cumulative_frame = cum;
+  }
+}
+
+// ------------------------------------------------------------------------------------ noise stream
+__device__ inline void xs_step(uint32_t& x, uint32_t& y, uint32_t& z, uint32_t& w) {
+  uint32_t t = x ^ (x << 11);
+  x = y; y = z; z = w;
+  w = (w ^ (w >> 19)) ^ (t ^ (t >> 8));
+}
+
+// state <- M * state over GF(2); M: 128 rows x 4 words, row r = output bit r (word r/32, bit r%32)
+__device__ inline void gf2_apply(const uint32_t* __restrict__ M, uint32_t s[4]) {
+  uint32_t o[4] = {0, 0, 0, 0};
+  for (int r = 0; r < 128; ++r) {
+    const uint32_t* row = M + r * 4;
+    uint32_t v = (row[0] & s[0]) ^ (row[1] & s[1]) ^ (row[2] & s[2]) ^ (row[3] & s[3]);
+    o[r >> 5] |= (uint32_t)(__popc(v) & 1) << (r & 31);
+  }
+  s[0] = o[0]; s[1] = o[1]; s[2] = o[2]; s[3] = o[3];
+}
+
+// Generates `tiles` tiles of kNoiseTile positions starting at state->rng_generated. 256 threads, 32 positions each.
+__global__ void __launch_bounds__(256) k_synth_noise(SynthDev S, const uint32_t* __restrict__ jump /*[8][128][4]*/, int tiles) {
+  SynthState* st = S.state;
+  __shared__ uint32_t base[4];
+  for (int tile = 0; tile < tiles; ++tile) {
+    __syncthreads();
+    if (threadIdx.x == 0) { base[0] = st->rng_state[0]; base[1] = st->rng_state[1]; base[2] = st->rng_state[2]; base[3] = st->rng_state[3]; }
+    __syncthreads();
+    uint32_t s[4] = {base[0], base[1], base[2], base[3]};
+    for (int j = 0; j < 8; ++j) if (threadIdx.x & (1 << j)) gf2_apply(jump + j * 512, s);
+    long long pos0 = st->rng_generated + (long long)threadIdx.x * 32;
+    for (int i = 0; i < 32; ++i) {
+      uint32_t tmp = 0;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) { xs_step(s[0], s[1], s[2], s[3]); tmp += s[3] >> 4; }
+      S.noise[(pos0 + i) % S.cap_noise] = tmp;
+    }
+    __syncthreads();
+    if (threadIdx.x == 255) {
+      st->rng_state[0] = s[0]; st->rng_state[1] = s[1]; st->rng_state[2] = s[2]; st->rng_state[3] = s[3];
+      st->rng_generated += kNoiseTile;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ plan
+__global__ void k_synth_plan(SynthDev S, int max_blocks) {
+  if (threadIdx.x != 0) return;
+  SynthState* st = S.state;
+  const int B = S.buffer_size;
+  long long s0 = st->synthesized_sample;
+  long long nblocks = 0;
+  if (st->n_pulses > 0 && st->last_location - s0 - 1 >= 0) nblocks = (st->last_location - s0 - 1) / B;
+  if (nblocks > max_blocks) nblocks = max_blocks;
+  long long first = st->next_pulse, count = 0;
+  while (true) {
+    long long limit = s0 + nblocks * B;
+    // pulses [first, first+count) with index < limit (indices ascending)
+    long long lo = first, hi = st->n_pulses;
+    while (lo < hi) { long long mid = (lo + hi) >> 1; if (S.p_index[mid % S.cap_pulses] < limit) lo = mid + 1; else hi = mid; }
+    count = lo - first;
+    if (count <= S.max_pulses || nblocks == 0) break;
+    --nblocks;
+  }
+  if (nblocks == 0) count = 0;
+  st->plan_blocks = (int)nblocks;
+  st->plan_first = first;
+  st->plan_count = (int)count;
+}
+
+// ------------------------------------------------------------------------------------ per-pulse response
+__global__ void __launch_bounds__(256) k_synth_pulse(SynthDev S, const double2* __restrict__ tw) {
+  extern __shared__ double2 sm2[];
+  SynthState* st = S.state;
+  if ((int)blockIdx.x >= st->plan_count) return;
+  const int n = S.fft_size, nb = n / 2 + 1, lg = ilog2(n);
+  double2* A = sm2;
+  double2* Nz = sm2 + n;
+  double* spec = (double*)(sm2 + 2 * n);
+  double* apr = spec + nb + 1;
+  double* periodic = apr + nb + 1;
+  double* scratch = periodic + n;
+  const long long p = st->plan_first + blockIdx.x;
+  const int slot = (int)(p % S.cap_pulses);
+  const double t = S.p_time[slot];
+  const int vuv = S.p_vuv[slot];
+  const long long idx = S.p_index[slot];
+  long long nxt = S.p_index[(p + 1) % S.cap_pulses];
+  int noise_size = (int)(nxt - idx);
+  if (noise_size < 1) noise_size = 1;
+  if (noise_size > n) noise_size = n;
+  const long long qpos = idx < 0 ? 0 : idx;
+  long long fl = (long long)(t / S.frame_period);
+  long long ce = (long long)ceil(t / S.frame_period);
+  const double interp = t / S.frame_period - fl;
+  const long long cum = st->cumulative_frame;
+  if (fl > cum) fl = cum;
+  if (ce > cum) ce = cum;
+  const float* sp0 = S.sp + (size_t)(fl % S.cap_frames) * nb; const float* sp1 = S.sp + (size_t)(ce % S.cap_frames) * nb;
+  const float* ap0 = S.ap + (size_t)(fl % S.cap_frames) * nb; const float* ap1 = S.ap + (size_t)(ce % S.cap_frames) * nb;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+    double sv, av;
+    if (fl == ce) { sv = fabs((double)sp0[i]); av = safe_ap((double)ap0[i]); }
+    else {
+      sv = (1.0 - interp) * fabs((double)sp0[i]) + interp * fabs((double)sp1[i]);
+      av = (1.0 - interp) * safe_ap((double)ap0[i]) + interp * safe_ap((double)ap1[i]);
+    }
+    spec[i] = sv; apr[i] = av * av;
+  }
+  __syncthreads();
+  // periodic response
+  const bool has_periodic = !(vuv == 0 || apr[0] > 0.999);
+  if (!has_periodic) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) periodic[i] = 0.0;
+  } else {
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) A[i] = make_double2(log(spec[i] * (1.0 - apr[i]) + kSafeMin) / 2.0, 0.0);
+    min_phase_smem(A, n, lg, tw);
+    irfft_smem(A, n, lg, tw);
+    double part = 0.0;
+    for (int i = n / 2 + threadIdx.x; i < n; i += blockDim.x) part += A[i - n / 2].x;      // periodic[i] = tmp[i - n/2]
+    double dc = block_sum(part, scratch);
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+      periodic[i] = i < n / 2 ? 0.0 : A[i - n / 2].x - dc * S.dc_remover[i - n / 2];
+  }
+  __syncthreads();
+  // aperiodic response: zero-mean noise of length noise_size
+  double part = 0.0;
+  for (int i = threadIdx.x; i < noise_size; i += blockDim.x)
+    part += (double)S.noise[(qpos + i) % S.cap_noise] / 268435456.0 - 6.0;
+  double avg = block_sum(part, scratch) / noise_size;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double v = 0.0;
+    if (i < noise_size) v = ((double)S.noise[(qpos + i) % S.cap_noise] / 268435456.0 - 6.0) - avg;
+    Nz[i] = make_double2(v, 0.0);
+  }
+  fft_smem(Nz, n, lg, -1, tw);
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+    double v = vuv != 0 ? log(spec[i] * apr[i]) / 2.0 : log(spec[i]) / 2.0;
+    A[i] = make_double2(v, 0.0);
+  }
+  min_phase_smem(A, n, lg, tw);
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+    double2 m = A[i], z = Nz[i];
+    A[i] = make_double2(m.x * z.x - m.y * z.y, m.x * z.y + m.y * z.x);
+  }
+  irfft_smem(A, n, lg, tw);
+  const double sq = sqrt((double)noise_size);
+  double* resp = S.resp + (size_t)blockIdx.x * n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double aper = i < n / 2 ? A[i + n / 2].x : A[i - n / 2].x;
+    resp[i] = (periodic[i] * sq + aper) / n;
+  }
+}
+
+// ------------------------------------------------------------------------------------ overlap-add
+// absolute sample a = s0 + j for j in [0, nblocks*B + carry_len): carry_in + pulses (in pulse order).
+__global__ void __launch_bounds__(256) k_synth_ola(SynthDev S, double* __restrict__ out, int out_cap_samples, int phase) {
+  SynthState* st = S.state;
+  const int B = S.buffer_size, n = S.fft_size;
+  const int nblocks = st->plan_blocks, count = st->plan_count;
+  const long long s0 = st->synthesized_sample;
+  const long long first = st->plan_first;
+  const int total = nblocks * B + S.carry_len;
+  const double* cin = S.carry[st->carry_sel];
+  double* cout = S.carry[st->carry_sel ^ 1];
+  if (phase == 0) {
+    if (nblocks == 0) return;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gridDim.x * blockDim.x) {
+      long long a = s0 + j;
+      double v = j < S.carry_len ? cin[j] : 0.0;
+      // pulses with idx in [a - n/2, a + n/2 - 1]
+      long long lo = 0, hi = count;
+      long long want = a - n / 2;
+      while (lo < hi) { long long mid = (lo + hi) >> 1; if (S.p_index[(first + mid) % S.cap_pulses] < want) lo = mid + 1; else hi = mid; }
+      for (long long q = lo; q < count; ++q) {
+        long long idx = S.p_index[(first + q) % S.cap_pulses];
+        if (idx > a + n / 2 - 1) break;
+        long long blockstart = idx < s0 ? s0 : s0 + ((idx - s0) / B) * B;
+        if (a < blockstart) continue;
+        long long off = idx - n / 2 + 1;     // absolute sample of response[0]
+        v += S.resp[(size_t)q * n + (a - off)];
+      }
+      if (j < nblocks * B) { if (j < out_cap_samples) out[j] = v; }
+      else cout[j - nblocks * B] = v;
+    }
+  } else {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && nblocks > 0) {
+      st->synthesized_sample = s0 + (long long)nblocks * B;
+      st->next_pulse = first + count;
+      st->carry_sel ^= 1;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->blocks_out = nblocks;
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+static void gf2_mul(const uint32_t* A, const uint32_t* Bm, uint32_t* C) {   // C = A * B (apply B first), 128x128 bit rows
+  // column extraction of B is awkward; use C row r = XOR over set bits k of A row r of B row k
+  for (int r = 0; r < 128; ++r) {
+    uint32_t acc[4] = {0, 0, 0, 0};
+    for (int k = 0; k < 128; ++k)
+      if (A[r * 4 + (k >> 5)] >> (k & 31) & 1) for (int w = 0; w < 4; ++w) acc[w] ^= Bm[k * 4 + w];
+    for (int w = 0; w < 4; ++w) C[r * 4 + w] = acc[w];
+  }
+}
+
+// jump[j] = T^(12*32*2^j), T = one xorshift128 step on the 128-bit state (x,y,z,w) = words 0..3
+static void build_jump_matrices(std::vector<uint32_t>& jump) {
+  std::vector<uint32_t> T(512, 0), P(512), Q(512);
+  // build T column by column: apply one step to each basis state
+  for (int c = 0; c < 128; ++c) {
+    uint32_t s[4] = {0, 0, 0, 0};
+    s[c >> 5] = 1u << (c & 31);
+    uint32_t t = s[0] ^ (s[0] << 11);
+    uint32_t nx = s[1], ny = s[2], nz = s[3];
+    uint32_t nw = (s[3] ^ (s[3] >> 19)) ^ (t ^ (t >> 8));
+    uint32_t o[4] = {nx, ny, nz, nw};
+    for (int r = 0; r < 128; ++r) if (o[r >> 5] >> (r & 31) & 1) T[r * 4 + (c >> 5)] |= 1u << (c & 31);
+  }
+  // P = T^384 by square-and-multiply (384 = 256 + 128)
+  std::vector<uint32_t> pw = T;          // T^(2^k)
+  std::vector<uint32_t> acc; bool have = false;
+  for (int bit = 0; bit < 9; ++bit) {
+    if ((384 >> bit) & 1) {
+      if (!have) { acc = pw; have = true; } else { gf2_mul(pw.data(), acc.data(), Q.data()); acc = Q; }
+    }
+    gf2_mul(pw.data(), pw.data(), Q.data()); pw = Q;
+  }
+  jump.resize(8 * 512);
+  P = acc;
+  for (int j = 0; j < 8; ++j) {
+    memcpy(&jump[j * 512], P.data(), 512 * sizeof(uint32_t));
+    gf2_mul(P.data(), P.data(), Q.data()); P = Q;
+  }
+}
+
+int synth_module_init(Engine* e) {
+  if (e->d_jump) return 0;
+  std::vector<uint32_t> jump;
+  build_jump_matrices(jump);
+  RYK_CUDA(cudaMalloc(&e->d_jump, jump.size() * sizeof(uint32_t)));
+  RYK_CUDA(cudaMemcpy(e->d_jump, jump.data(), jump.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  RYK_CUDA(cudaFuncSetAttribute(k_synth_pulse, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  return 0;
+}
+
+static size_t pulse_smem_bytes(int n) {
+  int nb = n / 2 + 1;
+  return sizeof(double2) * 2 * n + sizeof(double) * (2 * (nb + 1) + n + 64);
+}
+
+int synth_create(Engine* e, int fs, double frame_period_ms, int fft_size, int buffer_size, int ring_frames, Synth** out) {
+  if (synth_module_init(e)) return -1;
+  RYK_CHECK(fft_size >= 64 && fft_size <= kTwiddleN && (fft_size & (fft_size - 1)) == 0, "unsupported synthesis fft size");
+  Synth* s = new Synth();
+  SynthDev& D = s->dev;
+  D.fs = fs; D.fft_size = fft_size; D.buffer_size = buffer_size; D.frame_period = frame_period_ms / 1000.0;
+  D.cap_frames = ring_frames; D.cap_pulses = 1 << 15; D.cap_noise = 1 << 18; D.max_pulses = 2048;
+  D.carry_len = buffer_size + fft_size;
+  D.max_samples_per_add = 1 << 17;
+  int nb = fft_size / 2 + 1;
+  auto A = [&](void** p, size_t bytes) -> int { RYK_CUDA(cudaMalloc(p, bytes)); RYK_CUDA(cudaMemset(*p, 0, bytes)); s->allocs.push_back(*p); return 0; };
+  if (A((void**)&D.state, sizeof(SynthState))) return -1;
+  if (A((void**)&D.f0, sizeof(double) * ring_frames)) return -1;
+  if (A((void**)&D.sp, sizeof(float) * (size_t)ring_frames * nb)) return -1;
+  if (A((void**)&D.ap, sizeof(float) * (size_t)ring_frames * nb)) return -1;
+  if (A((void**)&D.p_index, sizeof(long long) * D.cap_pulses)) return -1;
+  if (A((void**)&D.p_time, sizeof(double) * D.cap_pulses)) return -1;
+  if (A((void**)&D.p_vuv, sizeof(int) * D.cap_pulses)) return -1;
+  if (A((void**)&D.noise, sizeof(uint32_t) * D.cap_noise)) return -1;
+  if (A((void**)&D.if0, sizeof(double) * D.max_samples_per_add)) return -1;
+  if (A((void**)&D.ivuv, sizeof(double) * D.max_samples_per_add)) return -1;
+  if (A((void**)&D.tp, sizeof(double) * (D.max_samples_per_add + 2))) return -1;
+  if (A((void**)&D.resp, sizeof(double) * (size_t)D.max_pulses * fft_size)) return -1;
+  if (A((void**)&D.carry[0], sizeof(double) * D.carry_len)) return -1;
+  if (A((void**)&D.carry[1], sizeof(double) * D.carry_len)) return -1;
+  if (A((void**)&D.dc_remover, sizeof(double) * (fft_size / 2))) return -1;
+  std::vector<double> dc(fft_size / 2);
+  double sum = 0.0;
+  for (int i = 0; i < fft_size / 2; ++i) { dc[i] = 0.5 - 0.5 * cos(2.0 * kPi * (i + 1.0) / (1.0 + fft_size / 2)); sum += dc[i]; }
+  for (auto& v : dc) v /= sum;
+  RYK_CUDA(cudaMemcpy(D.dc_remover, dc.data(), sizeof(double) * dc.size(), cudaMemcpyHostToDevice));
+  SynthState init;
+  memset(&init, 0, sizeof(init));
+  init.cumulative_frame = -1;
+  init.rng_state[0] = 123456789u; init.rng_state[1] = 362436069u; init.rng_state[2] = 521288629u; init.rng_state[3] = 88675123u;
+  RYK_CUDA(cudaMemcpy(D.state, &init, sizeof(init), cudaMemcpyHostToDevice));
+  s->host_cum_frames = -1; s->host_noise_generated = 0;
+  *out = s;
+  return 0;
+}
+
+void synth_destroy(Synth* s) {
+  if (!s) return;
+  for (void* p : s->allocs) cudaFree(p);
+  delete s;
+}
+
+// Stream-ordered: append n frames (device pointers). Also tops up the noise ring to the new end sample.
+int synth_add_async(Engine* e, Synth* s, const double* d_f0, int n, const float* d_sp, const float* d_ap, cudaStream_t st) {
+  SynthDev& D = s->dev;
+  RYK_CHECK((long long)n * D.frame_period * D.fs + 2 < D.max_samples_per_add, "too many frames in one AddParameters call");
+  k_synth_add<<<1, 1024, 0, st>>>(D, d_f0, n, d_sp, d_ap);
+  s->host_cum_frames += n;
+  long long need = (long long)ceil((double)(s->host_cum_frames < 0 ? 0 : s->host_cum_frames) * D.frame_period * D.fs) + D.fft_size + 2;
+  if (need > s->host_noise_generated) {
+    int tiles = (int)((need - s->host_noise_generated + kNoiseTile - 1) / kNoiseTile);
+    k_synth_noise<<<1, 256, 0, st>>>(D, e->d_jump, tiles);
+    s->host_noise_generated += (long long)tiles * kNoiseTile;
+    e->launches++;
+  }
+  e->launches++;
+  RYK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Stream-ordered: emit up to max_blocks blocks into d_out (doubles); the count lands in state->blocks_out.
+int synth_drain_async(Engine* e, Synth* s, double* d_out, int max_blocks, cudaStream_t st) {
+  SynthDev& D = s->dev;
+  k_synth_plan<<<1, 32, 0, st>>>(D, max_blocks);
+  k_synth_pulse<<<D.max_pulses, 256, pulse_smem_bytes(D.fft_size), st>>>(D, e->d_twiddle);
+  int total = max_blocks * D.buffer_size + D.carry_len;
+  k_synth_ola<<<(total + 255) / 256, 256, 0, st>>>(D, d_out, max_blocks * D.buffer_size, 0);
+  k_synth_ola<<<1, 32, 0, st>>>(D, d_out, 0, 1);
+  e->launches += 4;
+  RYK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace ryk

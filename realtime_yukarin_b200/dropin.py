@@ -1,0 +1,62 @@
+"""Import aliases that make this package answer to the names the reference's drivers import:
+
+    realtime_voice_conversion.{config, stream[.base_stream|...], segment.*, yukarin_wrapper.*, converter.*}
+    yukarin[.acoustic_feature|.wave|.param|.config|.f0_converter],  become_yukarin[.param|.config.sr_config]
+
+Nothing is copied: each alias module is a thin namespace whose attributes are this package's objects
+(import sites: check.py:7-17, tests/test_*.py of the reference).
+"""
+import sys
+import types
+
+
+def _module(name: str, **attrs) -> types.ModuleType:
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    m.__path__ = []          # behave like a package so that submodule imports resolve through sys.modules
+    sys.modules[name] = m
+    parent, _, child = name.rpartition('.')
+    if parent and parent in sys.modules:
+        setattr(sys.modules[parent], child, m)
+    return m
+
+
+def install() -> None:
+    from . import config, converter, feature, models, params, segment, stream, vocoder, voice_changer
+
+    rvc = 'realtime_voice_conversion'
+    _module(rvc)
+    _module(f'{rvc}.config', Config=config.Config, VocodeMode=config.VocodeMode)
+    st = dict(BaseStream=stream.BaseStream, EncodeStream=stream.EncodeStream, ConvertStream=stream.ConvertStream,
+              DecodeStream=stream.DecodeStream, StreamWrapper=stream.StreamWrapper)
+    _module(f'{rvc}.stream', **st)
+    _module(f'{rvc}.stream.base_stream', BaseStream=stream.BaseStream)
+    _module(f'{rvc}.stream.encode_stream', EncodeStream=stream.EncodeStream)
+    _module(f'{rvc}.stream.convert_stream', ConvertStream=stream.ConvertStream)
+    _module(f'{rvc}.stream.decode_stream', DecodeStream=stream.DecodeStream)
+    _module(f'{rvc}.stream.stream_wrapper', StreamWrapper=stream.StreamWrapper)
+    _module(f'{rvc}.segment')
+    _module(f'{rvc}.segment.segment', BaseSegmentMethod=segment.BaseSegmentMethod, Segment=segment.Segment)
+    _module(f'{rvc}.segment.wave_segment', WaveSegmentMethod=segment.WaveSegmentMethod)
+    _module(f'{rvc}.segment.feature_segment', FeatureSegmentMethod=segment.FeatureSegmentMethod)
+    _module(f'{rvc}.segment.feature_wrapper_segment', FeatureWrapperSegmentMethod=segment.FeatureWrapperSegmentMethod)
+    _module(f'{rvc}.yukarin_wrapper')
+    _module(f'{rvc}.yukarin_wrapper.vocoder', Vocoder=vocoder.Vocoder, RealtimeVocoder=vocoder.RealtimeVocoder)
+    _module(f'{rvc}.yukarin_wrapper.voice_changer', VoiceChanger=voice_changer.VoiceChanger,
+            AcousticFeatureWrapper=feature.AcousticFeatureWrapper)
+    _module(f'{rvc}.yukarin_wrapper.acoustic_feature_wrapper', AcousticFeatureWrapper=feature.AcousticFeatureWrapper,
+            CrepeAcousticFeatureWrapper=vocoder.CrepeAcousticFeatureWrapper)
+    _module(f'{rvc}.converter')
+    _module(f'{rvc}.converter.yukarin_converter', YukarinConverter=converter.YukarinConverter)
+
+    _module('yukarin', AcousticConverter=models.AcousticConverter, AcousticFeature=feature.AcousticFeature, Wave=feature.Wave)
+    _module('yukarin.acoustic_feature', AcousticFeature=feature.AcousticFeature)
+    _module('yukarin.wave', Wave=feature.Wave)
+    _module('yukarin.param', AcousticParam=params.AcousticParam)
+    _module('yukarin.config', create_from_json=params.create_from_json, Config=params.Config)
+    _module('yukarin.f0_converter', F0Converter=models.F0Converter)
+    _module('become_yukarin', SuperResolution=models.SuperResolution)
+    _module('become_yukarin.param', Param=params.Param, VoiceParam=params.VoiceParam,
+            AcousticFeatureParam=params.AcousticFeatureParam)
+    _module('become_yukarin.config')
+    _module('become_yukarin.config.sr_config', create_from_json=params.create_sr_from_json, SRConfig=params.SRConfig)

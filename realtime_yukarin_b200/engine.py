@@ -1,0 +1,318 @@
+"""ctypes binding of libryk.so (include/ryk.h): the only door between the Python host layer and
+the CUDA hot path.  There is NO CPU fallback: if the shared object is missing, cannot be loaded, or
+no B200 is visible, every call raises.
+"""
+import ctypes
+import os
+import threading
+from pathlib import Path
+from typing import Dict, Optional
+
+import numpy
+
+from .world_consts import cheaptrick_fft_size, dio_num_frames  # noqa: F401  (re-exported)
+
+_CSRC = Path(__file__).resolve().parent / 'csrc'
+_LIB_PATH = _CSRC / 'libryk.so'
+
+c_int_p = ctypes.POINTER(ctypes.c_int)
+c_float_p = ctypes.POINTER(ctypes.c_float)
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_u8_p = ctypes.POINTER(ctypes.c_uint8)
+
+
+class RykError(RuntimeError):
+    pass
+
+
+class SessionConfig(ctypes.Structure):
+    _fields_ = [
+        ('fs', ctypes.c_int), ('frame_period_ms', ctypes.c_double), ('f0_floor', ctypes.c_double),
+        ('f0_ceil', ctypes.c_double), ('fft_length', ctypes.c_int), ('order', ctypes.c_int),
+        ('alpha', ctypes.c_double), ('buffer_time', ctypes.c_double), ('encode_extra_time', ctypes.c_double),
+        ('convert_extra_time', ctypes.c_double), ('decode_extra_time', ctypes.c_double),
+        ('threshold_db', ctypes.c_double), ('vocoder_buffer_size', ctypes.c_int),
+    ]
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+# every symbol include/ryk.h declares (tests check that the library exports all of them)
+EXPORTED_SYMBOLS = [
+    'ryk_abi_version', 'ryk_last_error', 'ryk_engine_create', 'ryk_engine_destroy', 'ryk_engine_set_precision',
+    'ryk_engine_get_precision', 'ryk_engine_launch_count', 'ryk_engine_synchronize', 'ryk_world_analyze', 'ryk_world_f0',
+    'ryk_world_num_frames', 'ryk_silence_mask', 'ryk_model_create', 'ryk_model_set_layer', 'ryk_model_layer_shape',
+    'ryk_stage1_set_stats', 'ryk_f0_set_stats', 'ryk_stage1_convert', 'ryk_f0_convert', 'ryk_mc2sp',
+    'ryk_stage2_convert', 'ryk_convert_window', 'ryk_synth_create', 'ryk_synth_destroy', 'ryk_synth_add_parameters',
+    'ryk_synth_synthesis2', 'ryk_synth_decode', 'ryk_session_create', 'ryk_session_destroy', 'ryk_session_push',
+    'ryk_session_push_device', 'ryk_test_conv_layer',
+]
+
+
+def load_library() -> ctypes.CDLL:
+    """dlopen csrc/libryk.so (built by __graft_entry__.build() / csrc/build.sh)."""
+    global _lib
+    with _lib_lock:
+        if _lib is None:
+            if not _LIB_PATH.exists():
+                raise RykError(f'{_LIB_PATH} is missing: run `python -c "import __graft_entry__ as g; g.build()"` '
+                               f'(the hot path has no CPU fallback)')
+            lib = ctypes.CDLL(str(_LIB_PATH))
+            lib.ryk_last_error.restype = ctypes.c_char_p
+            lib.ryk_engine_launch_count.restype = ctypes.c_longlong
+            _lib = lib
+    return _lib
+
+
+def _f32(a) -> numpy.ndarray:
+    return numpy.ascontiguousarray(a, dtype=numpy.float32)
+
+
+def _fp(a: numpy.ndarray):
+    return a.ctypes.data_as(c_float_p)
+
+
+def _dp(a: numpy.ndarray):
+    return a.ctypes.data_as(c_double_p)
+
+
+def _bp(a: numpy.ndarray):
+    return a.ctypes.data_as(c_u8_p)
+
+
+class Engine(object):
+    """One per process per GPU (not thread-safe, like the reference's single-threaded stages)."""
+
+    def __init__(self, device: Optional[int] = None):
+        self.lib = load_library()
+        if device is None:
+            device = int(os.environ.get('LOCAL_RANK', '0'))
+        self.device = device
+        h = ctypes.c_void_p()
+        self._check(self.lib.ryk_engine_create(ctypes.c_int(device), ctypes.byref(h)))
+        self._h = h
+        self._synth_block = {}
+
+    # ---- plumbing ----
+    def _check(self, rc: int):
+        if rc < 0:
+            raise RykError(self.lib.ryk_last_error().decode('utf-8', 'replace'))
+        return rc
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self.lib.ryk_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_precision(self, mode: str):
+        self._check(self.lib.ryk_engine_set_precision(self._h, {'fp32': 0, 'fp16': 1}[mode]))
+
+    @property
+    def precision(self) -> str:
+        return ['fp32', 'fp16'][self.lib.ryk_engine_get_precision(self._h)]
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.ryk_engine_launch_count(self._h))
+
+    def synchronize(self):
+        self._check(self.lib.ryk_engine_synchronize(self._h))
+
+    # ---- WORLD analysis ----
+    def world_f0(self, x, fs, frame_period, f0_floor, f0_ceil):
+        x = _f32(x)
+        n = dio_num_frames(fs, len(x), frame_period)
+        f0 = numpy.empty(n, dtype=numpy.float64)
+        t = numpy.empty(n, dtype=numpy.float64)
+        self._check(self.lib.ryk_world_f0(self._h, _fp(x), len(x), int(fs), ctypes.c_double(frame_period),
+                                          ctypes.c_double(f0_floor), ctypes.c_double(f0_ceil), _dp(f0), _dp(t)))
+        return f0, t
+
+    def world_analyze(self, x, fs, frame_period, f0_floor, f0_ceil, fft_length, order, alpha, f0=None) -> Dict[str, numpy.ndarray]:
+        x = _f32(x)
+        hop = int(fs * frame_period / 1000)
+        T = len(x) // hop
+        nb = fft_length // 2 + 1
+        out = dict(
+            f0=numpy.zeros(T, dtype=numpy.float32), sp=numpy.zeros((T, nb), dtype=numpy.float32),
+            ap=numpy.zeros((T, nb), dtype=numpy.float32), mc=numpy.zeros((T, order + 1), dtype=numpy.float32),
+            voiced=numpy.zeros(T, dtype=numpy.uint8))
+        f0_arg = None
+        if f0 is not None:
+            nw = dio_num_frames(fs, len(x), frame_period)
+            f0_full = numpy.zeros(nw, dtype=numpy.float64)
+            f0_full[:min(nw, len(f0))] = numpy.asarray(f0, dtype=numpy.float64).ravel()[:nw]
+            f0_arg = _dp(f0_full)
+        if T > 0:
+            self._check(self.lib.ryk_world_analyze(
+                self._h, _fp(x), len(x), int(fs), ctypes.c_double(frame_period), ctypes.c_double(f0_floor),
+                ctypes.c_double(f0_ceil), int(fft_length), int(order), ctypes.c_double(alpha), f0_arg,
+                _fp(out['f0']), _fp(out['sp']), _fp(out['ap']), _fp(out['mc']), _bp(out['voiced'])))
+        out['voiced'] = out['voiced'].astype(bool)
+        return out
+
+    # ---- silence gate ----
+    def silence_mask(self, wave, frame_length, hop, threshold_db, n_frames) -> numpy.ndarray:
+        w = _f32(wave)
+        mask = numpy.zeros(n_frames, dtype=numpy.uint8)
+        thr = -1.0 if threshold_db is None else float(threshold_db)
+        self._check(self.lib.ryk_silence_mask(self._h, _fp(w), len(w), int(frame_length), int(hop), ctypes.c_double(thr),
+                                              int(n_frames), _bp(mask)))
+        return mask.astype(bool)
+
+    # ---- models ----
+    def model_create(self, stage: int, in_channels: int, out_channels: int, base_channels: int):
+        self._check(self.lib.ryk_model_create(self._h, stage, in_channels, out_channels, base_channels))
+
+    def model_layer_shape(self, stage: int, layer: int):
+        tr, cin, cout, k = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        self._check(self.lib.ryk_model_layer_shape(self._h, stage, layer, ctypes.byref(tr), ctypes.byref(cin),
+                                                   ctypes.byref(cout), ctypes.byref(k)))
+        return bool(tr.value), cin.value, cout.value, k.value
+
+    def model_set_layer(self, stage: int, layer: int, W, scale, shift):
+        W, scale, shift = _f32(W), _f32(scale), _f32(shift)
+        self._check(self.lib.ryk_model_set_layer(self._h, stage, layer, _fp(W), _fp(scale), _fp(shift)))
+
+    def stage1_set_stats(self, in_mean, in_std, out_mean, out_std):
+        a, b, c, d = _f32(in_mean), _f32(in_std), _f32(out_mean), _f32(out_std)
+        self._check(self.lib.ryk_stage1_set_stats(self._h, len(a), _fp(a), _fp(b), _fp(c), _fp(d)))
+
+    def f0_set_stats(self, in_mean, in_std, target_mean, target_std):
+        self._check(self.lib.ryk_f0_set_stats(self._h, ctypes.c_double(in_mean), ctypes.c_double(in_std),
+                                              ctypes.c_double(target_mean), ctypes.c_double(target_std)))
+
+    def stage1_convert(self, x) -> numpy.ndarray:
+        x = _f32(x)
+        y = numpy.empty_like(x)
+        self._check(self.lib.ryk_stage1_convert(self._h, _fp(x), x.shape[0], _fp(y)))
+        return y
+
+    def f0_convert(self, f0, voiced) -> numpy.ndarray:
+        f = _f32(numpy.asarray(f0).ravel())
+        v = numpy.ascontiguousarray(numpy.asarray(voiced).ravel(), dtype=numpy.uint8)
+        out = numpy.empty_like(f)
+        self._check(self.lib.ryk_f0_convert(self._h, _fp(f), _bp(v), len(f), _fp(out)))
+        return out
+
+    def mc2sp(self, mc, alpha, fftlen) -> numpy.ndarray:
+        mc = _f32(mc)
+        sp = numpy.empty((mc.shape[0], fftlen // 2 + 1), dtype=numpy.float64)
+        if mc.shape[0]:
+            self._check(self.lib.ryk_mc2sp(self._h, _fp(mc), mc.shape[0], mc.shape[1] - 1, ctypes.c_double(alpha), int(fftlen), _dp(sp)))
+        return sp
+
+    def stage2_convert(self, sp) -> numpy.ndarray:
+        sp = _f32(sp)
+        out = numpy.empty_like(sp)
+        self._check(self.lib.ryk_stage2_convert(self._h, _fp(sp), sp.shape[0], _fp(out)))
+        return out
+
+    def convert_window(self, wave, fs, frame_length, hop, threshold_db, f0, ap, mc, voiced, order, alpha, fftlen):
+        wave, f0, ap, mc = _f32(wave), _f32(numpy.asarray(f0).ravel()), _f32(ap), _f32(mc)
+        v = numpy.ascontiguousarray(numpy.asarray(voiced).ravel(), dtype=numpy.uint8)
+        T, nb = len(f0), fftlen // 2 + 1
+        out = dict(f0=numpy.empty(T, numpy.float32), ap=numpy.empty((T, nb), numpy.float32), sp=numpy.empty((T, nb), numpy.float32),
+                   voiced=numpy.empty(T, numpy.uint8), mc=numpy.empty((T, order + 1), numpy.float32))
+        thr = -1.0 if threshold_db is None else float(threshold_db)
+        self._check(self.lib.ryk_convert_window(
+            self._h, _fp(wave), len(wave), int(fs), int(frame_length), int(hop), ctypes.c_double(thr),
+            _fp(f0), _fp(ap), _fp(mc), _bp(v), T, int(order), ctypes.c_double(alpha), int(fftlen),
+            _fp(out['f0']), _fp(out['ap']), _fp(out['sp']), _bp(out['voiced']), _fp(out['mc'])))
+        out['voiced'] = out['voiced'].astype(bool)
+        return out
+
+    # ---- synthesizer ----
+    def synth_create(self, fs, frame_period, fft_size, buffer_size, number_of_pointers=16) -> int:
+        sid = ctypes.c_int()
+        self._check(self.lib.ryk_synth_create(self._h, int(fs), ctypes.c_double(frame_period), int(fft_size), int(buffer_size),
+                                              int(number_of_pointers), ctypes.byref(sid)))
+        self._synth_block[sid.value] = (int(buffer_size), int(fft_size))
+        return sid.value
+
+    def synth_destroy(self, sid: int):
+        self._check(self.lib.ryk_synth_destroy(self._h, sid))
+
+    def synth_add_parameters(self, sid, f0, sp, ap) -> int:
+        f0 = numpy.ascontiguousarray(numpy.asarray(f0).ravel(), dtype=numpy.float64)
+        sp, ap = _f32(sp), _f32(ap)
+        return self._check(self.lib.ryk_synth_add_parameters(self._h, sid, _dp(f0), len(f0), _fp(sp), _fp(ap)))
+
+    def synth_synthesis2(self, sid):
+        B = self._synth_block[sid][0]
+        buf = numpy.empty(B, dtype=numpy.float64)
+        ok = self._check(self.lib.ryk_synth_synthesis2(self._h, sid, _dp(buf)))
+        return buf if ok else None
+
+    def synth_decode(self, sid, f0, sp, ap, max_blocks=None) -> numpy.ndarray:
+        f0 = numpy.ascontiguousarray(numpy.asarray(f0).ravel(), dtype=numpy.float64)
+        sp, ap = _f32(sp), _f32(ap)
+        B = self._synth_block[sid][0]
+        if max_blocks is None:
+            max_blocks = max(4, len(f0) * 240 // B + 4)
+        out = numpy.empty(max_blocks * B, dtype=numpy.float64)
+        nblk = ctypes.c_int()
+        self._check(self.lib.ryk_synth_decode(self._h, sid, _dp(f0), len(f0), _fp(sp), _fp(ap), _dp(out), int(max_blocks), ctypes.byref(nblk)))
+        return out[:nblk.value * B].copy()
+
+    # ---- diagnostics ----
+    def test_conv_layer(self, in0, in1, W, scale, shift, transposed, k, stride, pad, act, use_tc, repeat=0):
+        """One conv layer in isolation; in0/in1 NHWC float32, W in the Chainer layout. Returns (out NHWC, ms per run)."""
+        in0 = _f32(in0)
+        B, H, Wd, C0 = in0.shape
+        C1 = 0 if in1 is None else in1.shape[3]
+        in1a = _f32(in1) if in1 is not None else numpy.zeros(1, numpy.float32)
+        W, scale, shift = _f32(W), _f32(scale), _f32(shift)
+        cout = W.shape[1] if transposed else W.shape[0]
+        Ho = (H - 1) * stride + k - 2 * pad if transposed else (H + 2 * pad - k) // stride + 1
+        Wo = (Wd - 1) * stride + k - 2 * pad if transposed else (Wd + 2 * pad - k) // stride + 1
+        out = numpy.empty((B, Ho, Wo, cout), numpy.float32)
+        ms = ctypes.c_float()
+        self._check(self.lib.ryk_test_conv_layer(
+            self._h, int(transposed), int(k), int(stride), int(pad), B, H, Wd, C0, C1, cout, _fp(in0), _fp(in1a), _fp(W),
+            _fp(scale), _fp(shift), int(act), int(use_tc), int(repeat), _fp(out), ctypes.byref(ms)))
+        return out, ms.value
+
+    # ---- sessions ----
+    def session_create(self, cfg: SessionConfig) -> int:
+        sid = ctypes.c_int()
+        self._check(self.lib.ryk_session_create(self._h, ctypes.byref(cfg), ctypes.byref(sid)))
+        return sid.value
+
+    def session_destroy(self, sid: int):
+        self._check(self.lib.ryk_session_destroy(self._h, sid))
+
+    def session_push(self, sid: int, wave, out: Optional[numpy.ndarray] = None) -> numpy.ndarray:
+        w = _f32(wave)
+        if out is None:
+            out = numpy.empty(len(w) * 2 + 8192, dtype=numpy.float64)
+        n_out = ctypes.c_int()
+        self._check(self.lib.ryk_session_push(self._h, sid, _fp(w), len(w), _dp(out), len(out), ctypes.byref(n_out)))
+        return out[:n_out.value]
+
+    def session_push_device(self, sid: int, wave_dev_ptr: int, n: int, out_dev_ptr: int, out_capacity: int, n_out_dev_ptr: int):
+        self._check(self.lib.ryk_session_push_device(self._h, sid, ctypes.c_void_p(wave_dev_ptr), int(n), ctypes.c_void_p(out_dev_ptr),
+                                                     int(out_capacity), ctypes.c_void_p(n_out_dev_ptr)))
+
+
+_default: Optional[Engine] = None
+
+
+def default_engine() -> Engine:
+    """Process-wide engine on cuda:LOCAL_RANK (created on first use)."""
+    global _default
+    if _default is None:
+        _default = Engine()
+    return _default
+
+
+def set_default_engine(engine: Optional[Engine]):
+    global _default
+    _default = engine

@@ -1,0 +1,57 @@
+"""Unit parity of the two convolution kernels against torch's CPU conv on the same data:
+FP32 CUDA-core kernel (conv_direct.cu) and FP16 tcgen05 kernel (conv_tc.cu, TMA + UMMA + TMEM)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(in0, in1, W, scale, shift, transposed, k, stride, pad, act):
+    x = in0 if in1 is None else np.concatenate([in0, in1], axis=3)
+    xt = torch.from_numpy(x).permute(0, 3, 1, 2).double()
+    Wt = torch.from_numpy(W).double()
+    y = F.conv_transpose2d(xt, Wt, stride=stride, padding=pad) if transposed else F.conv2d(xt, Wt, stride=stride, padding=pad)
+    y = y * torch.from_numpy(scale).double()[None, :, None, None] + torch.from_numpy(shift).double()[None, :, None, None]
+    if act == 1:
+        y = torch.where(y > 0, y, 0.2 * y)
+    elif act == 2:
+        y = torch.relu(y)
+    return y.permute(0, 2, 3, 1).float().numpy()
+
+
+CASES = [
+    # transposed, k, s, p, B, H, W, C0, C1, Cout, act
+    (0, 3, 1, 1, 1, 16, 32, 1, 0, 16, 1),
+    (0, 4, 2, 1, 1, 32, 64, 64, 0, 128, 1),
+    (0, 4, 2, 1, 2, 16, 16, 128, 0, 256, 1),
+    (0, 4, 2, 1, 1, 6, 8, 256, 0, 256, 1),
+    (1, 4, 2, 1, 1, 3, 4, 256, 0, 256, 2),
+    (1, 4, 2, 1, 1, 12, 16, 128, 128, 64, 2),
+    (1, 4, 2, 1, 2, 24, 32, 64, 64, 128, 2),
+    (0, 3, 1, 1, 1, 16, 32, 16, 16, 1, 0),
+]
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_conv_kernels(engine, case):
+    tr, k, s, p, B, H, W, C0, C1, Cout, act = case
+    rng = np.random.default_rng(hash(case) % (2 ** 31))
+    in0 = rng.standard_normal((B, H, W, C0)).astype(np.float32)
+    in1 = rng.standard_normal((B, H, W, C1)).astype(np.float32) if C1 else None
+    Cin = C0 + C1
+    shape = (Cin, Cout, k, k) if tr else (Cout, Cin, k, k)
+    Wt = (rng.standard_normal(shape) / np.sqrt(Cin * k * k / (4 if tr else 1))).astype(np.float32)
+    scale = rng.uniform(0.8, 1.2, Cout).astype(np.float32)
+    shift = (0.1 * rng.standard_normal(Cout)).astype(np.float32)
+    ref = _ref(in0, in1, Wt, scale, shift, tr, k, s, p, act)
+    got, _ = engine.test_conv_layer(in0, in1, Wt, scale, shift, tr, k, s, p, act, use_tc=0)
+    err = np.abs(got - ref).max()
+    print('direct', case, 'max err', err)
+    assert err < 1e-4
+    if k == 4 and C0 % 64 == 0 and C1 % 64 == 0 and Cout % 64 == 0:
+        got16, ms = engine.test_conv_layer(in0, in1, Wt, scale, shift, tr, k, s, p, act, use_tc=1, repeat=3)
+        err16 = np.abs(got16 - ref).max()
+        print('tcgen05', case, 'max err', err16, 'ms', ms)
+        assert err16 < 3e-2, err16
