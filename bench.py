@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py -- chunks/s and real-time factor of the full encode -> stage 1 -> stage 2 -> vocode path.
+
+  python bench.py --gpus 1 --steps K --warmup W            (driver; N > 1 via torch.distributed.run)
+  python bench.py --impl reference ...                      (the CPU implementation of the same path)
+
+A "step" is one 0.3 s @ 24 kHz chunk of one audio stream pushed through the device-resident session
+(BASELINE.json configs[1]: single stream, buffer_time = 0.3 s, extras (0, 0.5, 0), frame 5 ms;
+stage-1 / stage-2 U-Nets at base width 64 with seeded synthetic weights; synthetic speech).
+  value : chunks/s with the chunk's samples already in HBM and the output left there
+          (ryk_session_push_device), K consecutive chunks, CUDA events, max over ranks
+  e2e   : the same K chunks through ryk_session_push with HOST buffers (H2D + kernels + D2H per step)
+Multi-GPU: one independent stream per rank ("weak"); NCCL only broadcasts the weights at init.
+"""
+import argparse
+import json
+import os
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+BUFFER_TIME = 0.3
+EXTRA = (0.0, 0.5, 0.0)
+FS = 24000
+THRESHOLD_DB = 60.0
+METRIC = 'chunks_per_s_0.3s_24kHz_encode_stage1_stage2_vocode'
+WORKLOAD = ('single stream per GPU, buffer_time=0.3 s, extras (0,0.5,0), frame_period 5 ms, 24 kHz in/out, '
+            'convert window 260 -> 384 frames, stage-1 1-D U-Net base 64 (13.6 M params), '
+            'stage-2 2-D U-Net base 64 on 384x512 (54.4 M params, 142 GFLOP/chunk), WORLD DIO+StoneMask/CheapTrick/D4C + realtime synthesis')
+
+# algorithmic work of the stage-2 k4 layers (the tcgen05 kernel launches) for one 384x512 forward, base 64
+STAGE2_TC_FLOP = None
+
+
+def stage2_tc_flop(Tp=384, base=64):
+    enc = [1, 2, 4, 8, 8, 8, 8, 8]
+    dec = [8, 8, 8, 8, 4, 2, 1]
+    fl = 0.0
+    for i in range(1, 8):
+        cin, cout = base * enc[i - 1], base * enc[i]
+        fl += 2.0 * 16 * cin * cout * (Tp >> i) * (512 >> i)
+    for d in range(7):
+        cin = base * enc[7] if d == 0 else base * dec[d - 1] + base * enc[7 - d]
+        cout = base * dec[d]
+        fl += 2.0 * 16 * cin * cout * (Tp >> (7 - d)) * (512 >> (7 - d))
+    return fl
+
+
+def measured_peaks():
+    p = ROOT / 'MEASURED_PEAKS.json'
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(tflops=float(d['bf16_tflops']), hbm=float(d['hbm_gbs']), source='measured (MEASURED_PEAKS.json, cuBLAS bf16 burst)')
+    return dict(tflops=1590.0, hbm=6650.0, source='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            names = {
+                getattr(pynvml, 'nvmlClocksEventReasonHwSlowdown', 0x8): 'hw_slowdown',
+                getattr(pynvml, 'nvmlClocksEventReasonHwThermalSlowdown', 0x40): 'hw_thermal_slowdown',
+                getattr(pynvml, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20): 'sw_thermal_slowdown',
+                getattr(pynvml, 'nvmlClocksEventReasonSwPowerCap', 0x4): 'sw_power_cap',
+            }
+            while not self._stop_evt.is_set():
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.02)
+        except Exception as exc:        # clocks are best-effort; never fail the bench for them
+            self.reasons.add(f'unavailable:{type(exc).__name__}')
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return dict(sm_mhz=med, sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons))
+
+
+def make_models(rank, world):
+    """rank 0 writes the seeded synthetic model files; with N > 1 the arrays are NCCL-broadcast so that
+    every rank uploads identical weights (the only collective of the whole job)."""
+    from realtime_yukarin_b200 import synthetic
+    d = Path(tempfile.mkdtemp(prefix=f'ryk_bench_r{rank}_'))
+    if world == 1:
+        return synthetic.write_synthetic_models(d, seed=0)
+    import torch
+    import torch.distributed as dist
+    p1 = synthetic.make_stage1_params(0) if rank == 0 else None
+    p2 = synthetic.make_stage2_params(0) if rank == 0 else None
+    meta = [None]
+    if rank == 0:
+        meta[0] = {'s1': {k: (v.shape, str(v.dtype)) for k, v in p1.items()}, 's2': {k: (v.shape, str(v.dtype)) for k, v in p2.items()}}
+    dist.broadcast_object_list(meta, src=0)
+    out = {}
+    for name, src in (('s1', p1), ('s2', p2)):
+        arrs = {}
+        for k, (shape, dtype) in meta[0][name].items():
+            t = torch.from_numpy(src[k]).cuda() if rank == 0 else torch.empty(shape, dtype=getattr(torch, dtype), device='cuda')
+            dist.broadcast(t, src=0)
+            arrs[k] = t.cpu().numpy()
+        out[name] = arrs
+    paths = synthetic.write_synthetic_models(d, seed=0) if rank == 0 else None
+    if rank != 0:
+        # same files, written from the broadcast tensors
+        paths = synthetic.write_synthetic_models(d, seed=0, base1=8, base2=8)     # configs / statistics
+        np.savez(paths['stage1_model_path'], **out['s1'])
+        np.savez(paths['stage2_model_path'], **out['s2'])
+    return paths
+
+
+class CpuPath:
+    """The CPU implementation of the same path (oracle port: C WORLD/SPTK + torch-CPU convs), one stream."""
+
+    def __init__(self, paths, stream=0, threads=None, n_chunks=64):
+        import torch
+        from oracle import nets as onets
+        from oracle import pipeline as opipe
+        from realtime_yukarin_b200 import synthetic
+        if threads:
+            torch.set_num_threads(threads)
+        self.cores = torch.get_num_threads()
+        p1, p2 = onets.load_npz(paths['stage1_model_path']), onets.load_npz(paths['stage2_model_path'])
+        stats = (float(np.log(150.0)), 0.2, float(np.log(250.0)), 0.2)
+        cfg = opipe.PathConfig(threshold_db=THRESHOLD_DB)
+        self.orc = opipe.StreamOracle(cfg, p1, p2, stats, buffer_time=BUFFER_TIME, extra=EXTRA, backend='torch')
+        self.n = round(BUFFER_TIME * FS)
+        self.x = synthetic.synthetic_speech((n_chunks + 1) * BUFFER_TIME, stream=stream)
+        self.k = 0
+
+    def step(self):
+        k = self.k % (len(self.x) // self.n)
+        self.orc.push(self.x[k * self.n:(k + 1) * self.n])
+        self.k += 1
+
+    def rate(self, n_chunks):
+        t0 = time.perf_counter()
+        for _ in range(n_chunks):
+            self.step()
+        return n_chunks / (time.perf_counter() - t0)
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from realtime_yukarin_b200 import synthetic
+    d = Path(tempfile.mkdtemp(prefix='ryk_ref_'))
+    paths = synthetic.write_synthetic_models(d, seed=0)
+    t0 = time.perf_counter()
+    cpu = CpuPath(paths, n_chunks=args.steps + args.warmup + 1)
+    for _ in range(max(1, args.warmup)):
+        cpu.step()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu.step()
+    dt = time.perf_counter() - t1
+    value = args.steps / dt
+    line = dict(
+        impl='reference', metric=METRIC, value=value, unit='chunks/s', rtf=value * BUFFER_TIME, n_gpus=args.gpus, steps=args.steps,
+        warmup=args.warmup, ms_per_step=1000.0 * dt / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+        dtype='f64 (WORLD/SPTK) + f32 (U-Nets)', data='synthetic',
+        config=dict(workload=WORKLOAD, note='reference arm = CPU restatement of the path on the host cores (the reference itself cannot run: its '
+                                            'arithmetic lives in un-vendored pyworld/pysptk/chainer, SURVEY 8c); one step = one 0.3 s chunk of one stream'),
+        cpu_baseline=dict(value=value, unit='chunks/s', cores=cpu.cores, kind='port',
+                          sample=f'{args.steps} consecutive 0.3 s chunks of one stream after {max(1, args.warmup)} warm-up chunk(s)'),
+        e2e=dict(value=value, unit='chunks/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+        wall_s=time.perf_counter() - t0)
+    print(json.dumps(line))
+
+
+def run_gpu(args):
+    import torch
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    from realtime_yukarin_b200 import synthetic
+    from realtime_yukarin_b200.engine import Engine, SessionConfig
+    from realtime_yukarin_b200.models import AcousticConverter, F0Converter, SuperResolution
+    from realtime_yukarin_b200.params import create_from_json, create_sr_from_json
+
+    paths = make_models(rank, world)
+    eng = Engine(device=local_rank)
+    f0c = F0Converter(paths['input_statistics_path'], paths['target_statistics_path'])
+    AcousticConverter(create_from_json(paths['stage1_config_path']), paths['stage1_model_path'], f0_converter=f0c, engine=eng)
+    SuperResolution(create_sr_from_json(paths['stage2_config_path']), paths['stage2_model_path'], engine=eng)
+    eng.set_precision('fp16')
+
+    def new_session():
+        cfg = SessionConfig(fs=FS, frame_period_ms=5.0, f0_floor=71.0, f0_ceil=800.0, fft_length=1024, order=8, alpha=0.466,
+                            buffer_time=BUFFER_TIME, encode_extra_time=EXTRA[0], convert_extra_time=EXTRA[1], decode_extra_time=EXTRA[2],
+                            threshold_db=THRESHOLD_DB, vocoder_buffer_size=1024)
+        return eng.session_create(cfg)
+
+    n = round(BUFFER_TIME * FS)
+    total = args.warmup + args.steps
+    x = synthetic.synthetic_speech((total + 1) * BUFFER_TIME, stream=rank)
+    chunks = [np.ascontiguousarray(x[k * n:(k + 1) * n]) for k in range(total)]
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+        eng.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        import torch.distributed as dist
+        t = torch.tensor([v], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- leg 1: device-resident ("value") ----
+    sid = new_session()
+    d_in = torch.from_numpy(np.stack(chunks)).cuda()
+    out_cap = 16 * 1024
+    d_out = torch.empty(out_cap, dtype=torch.float64, device='cuda')
+    d_n = torch.zeros(1, dtype=torch.int32, device='cuda')
+    for k in range(args.warmup):
+        eng.session_push_device(sid, d_in[k].data_ptr(), n, d_out.data_ptr(), out_cap, d_n.data_ptr())
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = eng.launch_count
+    eng.profile(True)
+    eng.timer_start()
+    for k in range(args.warmup, total):
+        eng.session_push_device(sid, d_in[k].data_ptr(), n, d_out.data_ptr(), out_cap, d_n.data_ptr())
+    t_dev = eng.timer_stop() * 1e-3          # CUDA events on the stream the kernels are launched on
+    barrier()
+    s2_ms, s2_runs = eng.profile_read()
+    eng.profile(False)
+    clocks = sampler.stop()
+    launches = eng.launch_count - launches0
+    t_dev = max_over_ranks(t_dev)
+    eng.session_destroy(sid)
+
+    # ---- leg 2: end to end with host buffers ("e2e") ----
+    sid = new_session()
+    host_out = np.empty(out_cap, dtype=np.float64)
+    produced = 0
+    for k in range(args.warmup):
+        eng.session_push(sid, chunks[k], host_out)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.warmup, total):
+        produced += len(eng.session_push(sid, chunks[k], host_out))
+    t_e2e = time.perf_counter() - t0
+    barrier()
+    t_e2e = max_over_ranks(t_e2e)
+    eng.session_destroy(sid)
+
+    if rank != 0:
+        return
+    value = world * args.steps / t_dev
+    e2e = world * args.steps / t_e2e
+    peaks = measured_peaks()
+    fl = stage2_tc_flop()
+    ach = fl * s2_runs / (s2_ms * 1e-3) / 1e12 if s2_ms > 0 else None
+    cpu = CpuPath(paths, n_chunks=8)
+    cpu.step()
+    cpu_rate, cores = cpu.rate(3), cpu.cores
+    line = dict(
+        metric=METRIC, value=value, unit='chunks/s', rtf=value * BUFFER_TIME, n_gpus=world, steps=args.steps, warmup=args.warmup,
+        ms_per_step=1000.0 * t_dev / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+        dtype='f64 (WORLD analysis/synthesis), f32 (stage 1), f16 in / f32 accumulate (stage 2 tcgen05)', data='synthetic',
+        config=dict(workload=WORKLOAD, timing='CUDA events on the engine stream around the K pushes, max over ranks',
+                    l2='per-step footprint (109 MB fp16 stage-2 weights + 54 MB stage-1 weights + ~100 MB activations) exceeds the 126 MB L2; no explicit flush',
+                    streams_per_gpu=1, silence_threshold_db=THRESHOLD_DB),
+        e2e=dict(value=e2e, unit='chunks/s', rtf=e2e * BUFFER_TIME, h2d_bytes_per_step=n * 4,
+                 d2h_bytes_per_step=int(produced / max(1, args.steps)) * 8 + 4 + 8),
+        gpu_launches=int(launches),
+        clocks=clocks,
+        roofline=dict(bound='tensor', kernel='k_conv_tc (stage-2 k4 layers 1..14, incl. split-K memset/finalize)', achieved=ach, peak=peaks['tflops'],
+                      unit='TFLOP/s', frac=(ach / peaks['tflops']) if ach else None, traffic=None, peak_source=peaks['source'],
+                      flop_per_step=fl, ms_per_step_in_kernel=(s2_ms / s2_runs) if s2_runs else None),
+        cpu_baseline=dict(value=cpu_rate, unit='chunks/s', cores=cores, kind='port',
+                          sample='3 chunks of 0.3 s after a warm-up chunk, C WORLD/SPTK restatement + torch-CPU U-Nets, same models/audio'),
+    )
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=None)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 20 if args.impl == 'b200' else 6
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == '__main__':
+    main()

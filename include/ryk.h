@@ -47,6 +47,11 @@ int ryk_engine_set_precision(ryk_engine* e, int mode);
 int ryk_engine_get_precision(ryk_engine* e);
 long long ryk_engine_launch_count(ryk_engine* e);        /* kernels launched by this engine so far */
 int ryk_engine_synchronize(ryk_engine* e);
+/* CUDA-event timing of the stage-2 k4-layer block (layers 1..14, the tcgen05 kernels) on the engine's stream */
+int ryk_engine_timer_start(ryk_engine* e);                    /* cudaEventRecord on the engine's stream */
+int ryk_engine_timer_stop(ryk_engine* e, float* elapsed_ms);  /* record + synchronize + elapsed */
+int ryk_engine_profile(ryk_engine* e, int enable);
+int ryk_engine_profile_read(ryk_engine* e, double* stage2_ms_total, int* stage2_runs);
 
 /* ---- WORLD analysis (encode) -------------------------------------------------------------- */
 /* wave_host: n float32 samples.  Outputs are n_frames = n / hop rows (hop = fs * frame_period / 1000):
@@ -129,6 +134,10 @@ int ryk_session_push_device(ryk_engine* e, int session_id, const float* wave_dev
                             int* n_out_dev);
 
 /* ---- diagnostics -------------------------------------------------------------------------------------- */
+/* DIO internals (raw contour before StoneMask, per-band candidates [bands][frames], normalised scores, event counts [bands][4])
+ * of the most recent analysis that used the (n, fs, frame_period, f0_floor, f0_ceil) plan. */
+int ryk_debug_dio(ryk_engine* e, int n, int fs, double frame_period_ms, double f0_floor, double f0_ceil,
+                  double* f0_raw, double* cand, double* score, int* counts);
 /* One conv (transposed = 0) or transposed-conv layer of the U-Nets in isolation, host fp32 NHWC tensors in and
  * out, weights in the Chainer layout; use_tc selects the FP16 tcgen05 kernel (1) or the FP32 CUDA-core kernel (0).
  * `repeat` extra timed runs report the mean device time per run (ms) -- used by the unit parity tests and ncu. */

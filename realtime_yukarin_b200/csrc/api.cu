@@ -187,6 +187,40 @@ int ryk_engine_get_precision(ryk_engine* h) { return E(h)->precision; }
 long long ryk_engine_launch_count(ryk_engine* h) { return E(h)->launches; }
 int ryk_engine_synchronize(ryk_engine* h) { RYK_CUDA(cudaStreamSynchronize(E(h)->stream)); return 0; }
 
+int ryk_engine_profile(ryk_engine* h, int enable) { E(h)->profile = enable != 0; return 0; }
+// total device time (ms) of the stage-2 k4 (tensor-core) layer block over all forwards since the last read
+int ryk_engine_profile_read(ryk_engine* h, double* stage2_ms_total, int* stage2_runs) {
+  Engine* e = E(h);
+  RYK_CUDA(cudaStreamSynchronize(e->stream));
+  double tot = 0.0;
+  for (auto& pr : e->prof_events) {
+    float ms = 0.f;
+    RYK_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+    tot += ms;
+    cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+  }
+  *stage2_ms_total = tot; *stage2_runs = (int)e->prof_events.size();
+  e->prof_events.clear();
+  return 0;
+}
+
+// device-side stopwatch on the engine's stream (bench.py brackets its timed region with it)
+int ryk_engine_timer_start(ryk_engine* h) {
+  Engine* e = E(h);
+  RYK_CUDA(cudaSetDevice(e->device));
+  for (int i = 0; i < 2; ++i) if (!e->timer_ev[i]) RYK_CUDA(cudaEventCreate(&e->timer_ev[i]));
+  RYK_CUDA(cudaEventRecord(e->timer_ev[0], e->stream));
+  return 0;
+}
+int ryk_engine_timer_stop(ryk_engine* h, float* elapsed_ms) {
+  Engine* e = E(h);
+  RYK_CHECK(e->timer_ev[0] != nullptr, "timer was not started");
+  RYK_CUDA(cudaEventRecord(e->timer_ev[1], e->stream));
+  RYK_CUDA(cudaEventSynchronize(e->timer_ev[1]));
+  RYK_CUDA(cudaEventElapsedTime(elapsed_ms, e->timer_ev[0], e->timer_ev[1]));
+  return 0;
+}
+
 int ryk_world_num_frames(int n, int fs, double frame_period_ms) { return (int)(1000.0 * n / fs / frame_period_ms) + 1; }
 
 int ryk_world_f0(ryk_engine* h, const float* wave, int n, int fs, double fp, double f0_floor, double f0_ceil, double* f0, double* t) {
@@ -526,6 +560,15 @@ int ryk_synth_decode(ryk_engine* h, int id, const double* f0, int n, const float
   return 0;
 }
 
+
+// ---- diagnostics: DIO internals of the last ryk_world_f0 / ryk_world_analyze call with this (n, fs, ...) plan
+int ryk_debug_dio(ryk_engine* h, int n, int fs, double fp, double f0_floor, double f0_ceil, double* f0_raw, double* cand, double* score, int* counts) {
+  Engine* e = E(h);
+  RYK_CUDA(cudaSetDevice(e->device));
+  DioPlan* plan = nullptr;
+  if (dio_get_plan(e, n, fs, fp, f0_floor, f0_ceil, &plan)) return -1;
+  return dio_plan_debug_copy(plan, f0_raw, cand, score, counts, e->stream);
+}
 
 // ---- diagnostics: one conv / transposed-conv layer in isolation (unit parity + profiling) -------
 // in0/in1: host fp32 NHWC [B][Hin][Win][C0|C1]; W: Chainer layout; out: host fp32 NHWC [B][Hout][Wout][Cout].

@@ -44,6 +44,10 @@ struct Engine {
   void* h_pinned = nullptr; size_t pinned_bytes = 0;
   // counters
   long long launches = 0;
+  // optional device-side timing of the stage-2 tensor-core layers (bench roofline): event pairs per forward
+  bool profile = false;
+  cudaEvent_t timer_ev[2] = {nullptr, nullptr};
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
 };
 
 int engine_scratch(Engine* e, size_t bytes, void** out);
@@ -58,6 +62,7 @@ int dio_stonemask_run(Engine* e, DioPlan* p, const float* d_x, cudaStream_t st);
 const double* dio_plan_f0(DioPlan* p);      // refined f0 (double) after dio_stonemask_run
 double* dio_plan_f0_mut(DioPlan* p);
 int dio_plan_frames(DioPlan* p);
+int dio_plan_debug_copy(DioPlan* p, double* f0_raw, double* cand, double* score, int* counts, cudaStream_t st);
 int spectral_analysis_run(Engine* e, const float* d_x, int n, int fs, double frame_period, const double* d_f0, int n_out,
                           int fft_size, int order, float* d_sp, float* d_ap, float* d_mc, float* d_f0_out, uint8_t* d_voiced,
                           cudaStream_t st);

@@ -279,7 +279,8 @@ __global__ void __launch_bounds__(256) k_stonemask(const float* __restrict__ x, 
   int half = (int)(1.5 * fs / f0i + 1.0);
   double wlen_time = (2.0 * half + 1.0) / fs;
   int blen = half * 2 + 1;
-  int fft_size = (int)pow(2.0, 2.0 + (int)(log(half * 2.0 + 1.0) / kLog2));
+  // NB: device pow() is not exact for integer powers (2 ulp): a truncated 2047 would wreck the FFT. Shift instead.
+  int fft_size = 1 << (2 + (int)(log(half * 2.0 + 1.0) / kLog2));
   int lg = ilog2(fft_size);
   double2* A = sm2;                 // main
   double2* B = sm2 + 4096;          // diff
@@ -541,14 +542,13 @@ __device__ inline void bitonic_sort_smem(double* v, int n2) {
 // one CTA (512 threads) per frame
 __global__ void __launch_bounds__(512) k_d4c(const float* __restrict__ x, int x_length, int fs, double frame_period,
                                             const double* __restrict__ f0, int fft_size_out, double threshold,
-                                            int n_out, float* __restrict__ ap_out, const double2* __restrict__ tw) {
+                                            int n_out, float* __restrict__ ap_out, const double2* __restrict__ tw,
+                                            int fft_d4c, int lt_fft) {
   extern __shared__ double2 sm2[];
   int frame = blockIdx.x;
   if (frame >= n_out) return;
   const int nb_out = fft_size_out / 2 + 1;
   float* out = ap_out + (size_t)frame * nb_out;
-  const int fft_d4c = (int)pow(2.0, 1.0 + (int)(log(4.0 * fs / 47.0 + 1) / kLog2));
-  const int lt_fft = (int)pow(2.0, 1.0 + (int)(log(3.0 * fs / 40.0 + 1) / kLog2));
   const int maxfft = fft_d4c > lt_fft ? fft_d4c : lt_fft;
   double2* A = sm2;
   double* base = (double*)(sm2 + maxfft);
@@ -770,6 +770,14 @@ int dio_stonemask_run(Engine* e, DioPlan* p, const float* d_x, cudaStream_t st) 
 }
 
 const double* dio_plan_f0(DioPlan* p) { return p->d_f0r; }
+int dio_plan_debug_copy(DioPlan* p, double* f0_raw, double* cand, double* score, int* counts, cudaStream_t st) {
+  RYK_CUDA(cudaMemcpyAsync(f0_raw, p->d_f0, sizeof(double) * p->f0_length, cudaMemcpyDeviceToHost, st));
+  RYK_CUDA(cudaMemcpyAsync(cand, p->d_cand, sizeof(double) * p->f0_length * p->nbands, cudaMemcpyDeviceToHost, st));
+  RYK_CUDA(cudaMemcpyAsync(score, p->d_score, sizeof(double) * p->f0_length * p->nbands, cudaMemcpyDeviceToHost, st));
+  RYK_CUDA(cudaMemcpyAsync(counts, p->d_counts, sizeof(int) * 4 * p->nbands, cudaMemcpyDeviceToHost, st));
+  RYK_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
 double* dio_plan_f0_mut(DioPlan* p) { return p->d_f0r; }
 int dio_plan_frames(DioPlan* p) { return p->f0_length; }
 
@@ -802,7 +810,9 @@ int spectral_analysis_run(Engine* e, const float* d_x, int n, int fs, double fra
   if (n_out <= 0) return 0;
   k_cheaptrick<<<n_out, 256, cheaptrick_smem_bytes(fft_size, fs), st>>>(d_x, n, fs, frame_period, d_f0, fft_size, -0.15, e->d_G, order,
                                                                       n_out, d_sp, d_mc, nullptr, e->d_twiddle);
-  k_d4c<<<n_out, 512, d4c_smem_bytes(fs), st>>>(d_x, n, fs, frame_period, d_f0, fft_size, 0.85, n_out, d_ap, e->d_twiddle);
+  const int fft_d4c = (int)pow(2.0, 1.0 + (int)(log(4.0 * fs / 47.0 + 1) / kLog2));   // host pow: exact
+  const int lt_fft = (int)pow(2.0, 1.0 + (int)(log(3.0 * fs / 40.0 + 1) / kLog2));
+  k_d4c<<<n_out, 512, d4c_smem_bytes(fs), st>>>(d_x, n, fs, frame_period, d_f0, fft_size, 0.85, n_out, d_ap, e->d_twiddle, fft_d4c, lt_fft);
   k_f0_out<<<(n_out + 127) / 128, 128, 0, st>>>(d_f0, n_out, d_f0_out, d_voiced);
   RYK_CUDA(cudaGetLastError());
   return 0;

@@ -46,7 +46,7 @@ EXPORTED_SYMBOLS = [
     'ryk_stage1_set_stats', 'ryk_f0_set_stats', 'ryk_stage1_convert', 'ryk_f0_convert', 'ryk_mc2sp',
     'ryk_stage2_convert', 'ryk_convert_window', 'ryk_synth_create', 'ryk_synth_destroy', 'ryk_synth_add_parameters',
     'ryk_synth_synthesis2', 'ryk_synth_decode', 'ryk_session_create', 'ryk_session_destroy', 'ryk_session_push',
-    'ryk_session_push_device', 'ryk_test_conv_layer',
+    'ryk_session_push_device', 'ryk_test_conv_layer', 'ryk_debug_dio', 'ryk_engine_profile', 'ryk_engine_profile_read', 'ryk_engine_timer_start', 'ryk_engine_timer_stop',
 ]
 
 
@@ -121,6 +121,22 @@ class Engine(object):
     @property
     def launch_count(self) -> int:
         return int(self.lib.ryk_engine_launch_count(self._h))
+
+    def timer_start(self):
+        self._check(self.lib.ryk_engine_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = ctypes.c_float()
+        self._check(self.lib.ryk_engine_timer_stop(self._h, ctypes.byref(ms)))
+        return ms.value
+
+    def profile(self, enable: bool):
+        self._check(self.lib.ryk_engine_profile(self._h, int(bool(enable))))
+
+    def profile_read(self):
+        ms, runs = ctypes.c_double(), ctypes.c_int()
+        self._check(self.lib.ryk_engine_profile_read(self._h, ctypes.byref(ms), ctypes.byref(runs)))
+        return ms.value, runs.value
 
     def synchronize(self):
         self._check(self.lib.ryk_engine_synchronize(self._h))
@@ -263,6 +279,14 @@ class Engine(object):
         return out[:nblk.value * B].copy()
 
     # ---- diagnostics ----
+    def debug_dio(self, n, fs, frame_period, f0_floor, f0_ceil):
+        nf = dio_num_frames(fs, n, frame_period)
+        nbands = 1 + int(numpy.log(f0_ceil / f0_floor) / 0.69314718055994529 * 2.0)
+        f0 = numpy.empty(nf); cand = numpy.empty((nbands, nf)); score = numpy.empty((nbands, nf)); counts = numpy.empty((nbands, 4), numpy.int32)
+        self._check(self.lib.ryk_debug_dio(self._h, int(n), int(fs), ctypes.c_double(frame_period), ctypes.c_double(f0_floor),
+                                           ctypes.c_double(f0_ceil), _dp(f0), _dp(cand), _dp(score), counts.ctypes.data_as(c_int_p)))
+        return f0, cand, score, counts
+
     def test_conv_layer(self, in0, in1, W, scale, shift, transposed, k, stride, pad, act, use_tc, repeat=0):
         """One conv layer in isolation; in0/in1 NHWC float32, W in the Chainer layout. Returns (out NHWC, ms per run)."""
         in0 = _f32(in0)

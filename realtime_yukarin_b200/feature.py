@@ -79,11 +79,14 @@ class AcousticFeature(object):
     @staticmethod
     def concatenate(fs: Sequence['AcousticFeature'], keys: Optional[Iterable[str]] = None) -> 'AcousticFeature':
         keys = _KEYS if keys is None else keys
-        return AcousticFeature(**{k: numpy.concatenate([getattr(f, k) for f in fs]) for k in keys})
+        # a key that is missing (NaN placeholder) on the inputs stays missing (the reference's own
+        # tests concatenate / pick f0-only wrappers with the default 4-key list)
+        return AcousticFeature(**{k: numpy.concatenate([getattr(f, k) for f in fs]) for k in keys
+                                  if not any(_is_missing(getattr(f, k)) for f in fs)})
 
     def pick(self, first: int, last: int, keys: Optional[Iterable[str]] = None) -> 'AcousticFeature':
         keys = _KEYS if keys is None else keys
-        return AcousticFeature(**{k: getattr(self, k)[first:last] for k in keys})
+        return AcousticFeature(**{k: getattr(self, k)[first:last] for k in keys if not _is_missing(getattr(self, k))})
 
     def indexing(self, index: numpy.ndarray) -> 'AcousticFeature':
         return AcousticFeature(**{k: v[index] for k, v in self._present()})

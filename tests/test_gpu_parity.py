@@ -205,3 +205,32 @@ def test_stream_api_end_to_end(engine, small_models):
         if tol is not None:
             assert rmse < tol
     engine.set_precision('fp16')
+
+
+def test_device_session_matches_oracle_stream(engine, small_models):
+    """The device-resident session (sliding windows in HBM) == the oracle's chunked stream."""
+    from realtime_yukarin_b200.engine import SessionConfig
+    ac, sr, f0c = _load(engine, small_models)
+    p1, p2 = onets.load_npz(small_models['stage1_model_path']), onets.load_npz(small_models['stage2_model_path'])
+    for T, extra in ((0.3, (0.0, 0.5, 0.0)), (0.1, (0.1, 0.2, 0.0))):
+        engine.set_precision('fp32')
+        cfg = SessionConfig(fs=24000, frame_period_ms=5.0, f0_floor=71.0, f0_ceil=800.0, fft_length=1024, order=8, alpha=0.466,
+                            buffer_time=T, encode_extra_time=extra[0], convert_extra_time=extra[1], decode_extra_time=extra[2],
+                            threshold_db=60.0, vocoder_buffer_size=1024)
+        sid = engine.session_create(cfg)
+        orc = opipe.StreamOracle(CFG, p1, p2, f0c.stats(), buffer_time=T, extra=extra, backend='torch')
+        x = _speech(2.4, 33)
+        n = round(T * 24000)
+        outs, refs = [], []
+        for k in range(len(x) // n):
+            y = engine.session_push(sid, x[k * n:(k + 1) * n])
+            r = orc.push(x[k * n:(k + 1) * n])
+            assert len(y) == len(r), (k, len(y), len(r))
+            outs.append(y.copy())
+            refs.append(r)
+        y, r = np.concatenate(outs), np.concatenate(refs)
+        rmse = float(np.sqrt(np.mean((y - r) ** 2)))
+        print(f'session T={T} extra={extra}: {len(y)} samples, rmse {rmse:.3e}, signal rms {float(np.sqrt(np.mean(r ** 2))):.3e}')
+        assert rmse < 1e-3
+        engine.session_destroy(sid)
+    engine.set_precision('fp16')

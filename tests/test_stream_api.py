@@ -1,0 +1,191 @@
+"""Host-side plugin API conformance (no GPU): the framing / indexing contract of the reference's
+Stream + SegmentMethod layer, restated as known-answer tests, plus -- when the reference checkout is
+present -- the reference's own mock-based unit tests executed unmodified against this package
+through the drop-in import aliases."""
+import importlib.util
+import sys
+import unittest
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from realtime_yukarin_b200 import dropin
+from realtime_yukarin_b200.feature import AcousticFeature, AcousticFeatureWrapper, Wave
+from realtime_yukarin_b200.params import AcousticParam, Param
+from realtime_yukarin_b200.segment import (BaseSegmentMethod, FeatureWrapperSegmentMethod, Segment, WaveSegmentMethod)
+from realtime_yukarin_b200.stream import BaseStream, ConvertStream, EncodeStream, StreamWrapper
+
+
+class TextMethod(BaseSegmentMethod):
+    def length(self, data):
+        return len(data)
+
+    def pad(self, width):
+        return ' ' * width
+
+    def pick(self, data, first, last):
+        return data[first:last]
+
+    def concat(self, datas):
+        return ''.join(datas)
+
+
+class TextStream(BaseStream):
+    def process(self, start_time, time_length, extra_time):
+        return self.fetch(start_time, time_length, extra_time)
+
+
+def make_text_stream(rate=10):
+    s = TextStream(TextMethod(rate), TextMethod(rate))
+    s.add(start_time=0, data='a' * rate)
+    s.add(start_time=1, data='b' * rate)
+    return s
+
+
+def test_segment_record():
+    m = TextMethod(4)
+    seg = Segment(start_time=1, data='xxxxxxxx', method=m)
+    assert (seg.start_time, seg.data, seg.method) == (1, 'xxxxxxxx', m)
+    assert seg.length == 8 and seg.time_length == 2.0 and seg.end_time == 3.0 and seg.sampling_rate == 4
+    assert tuple(seg) == (1, 'xxxxxxxx', m)
+
+
+def test_fetch_known_answers():            # base_stream.py:32-79 via tests/test_base_stream.py:65-93
+    s = make_text_stream()
+    assert s.fetch(0, 1, 0) == 'a' * 10
+    assert s.fetch(0.5, 1, 0) == 'a' * 5 + 'b' * 5
+    assert s.fetch(-0.5, 1, 0) == ' ' * 5 + 'a' * 5
+    assert s.fetch(1.5, 1, 0) == 'b' * 5 + ' ' * 5
+    assert s.fetch(0, 1, 0.3) == ' ' * 3 + 'a' * 10 + 'b' * 3
+    assert s.fetch(0, 2, 0.3) == ' ' * 3 + 'a' * 10 + 'b' * 10 + ' ' * 3
+
+
+def test_remove_keeps_segments_ending_after():   # tests/test_base_stream.py:47-63
+    s = make_text_stream()
+    s.add(start_time=2, data='c' * 10)
+    for end, left in ((0, 3), (1, 2), (2, 1), (3, 0)):
+        s.remove(end_time=end)
+        assert len(s.stream) == left
+
+
+def test_fetch_gap_between_segments_is_padded():
+    s = TextStream(TextMethod(10), TextMethod(10))
+    s.add(start_time=0, data='a' * 10)
+    s.add(start_time=2, data='c' * 10)
+    assert s.fetch(0.5, 2, 0) == 'a' * 5 + ' ' * 10 + 'c' * 5
+
+
+class VocoderMock:
+    acoustic_param = AcousticParam()
+
+
+def test_encode_stream_wave_fetch():       # tests/test_encode_stream.py:34-85
+    st = EncodeStream(vocoder=VocoderMock())
+    sr = VocoderMock.acoustic_param.sampling_rate
+    one, two = np.ones(sr, np.float32), np.ones(sr, np.float32) * 2
+    st.add(0, one)
+    st.add(1, two)
+    np.testing.assert_equal(st.fetch(0, 1, 0), one)
+    np.testing.assert_equal(st.fetch(0.5, 1, 0), np.concatenate([one[:sr // 2], two[:sr // 2]]))
+    np.testing.assert_equal(st.fetch(-0.5, 1, 0), np.concatenate([np.zeros(sr // 2, np.float32), one[:sr // 2]]))
+    np.testing.assert_equal(st.fetch(0, 2, 0.3), np.concatenate([np.zeros(sr // 10 * 3), one, two, np.zeros(sr // 10 * 3)]))
+    assert st.out_segment_method.sampling_rate == 200
+
+
+class AttrDict(dict):
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.__dict__ = self
+
+
+def _wrapper(values, lengths, sr=16000, rate=200):
+    return AcousticFeatureWrapper(
+        wave=Wave(np.concatenate([np.ones(round(t * sr), np.float32) * v for v, t in zip(values, lengths)]), sr),
+        f0=np.concatenate([np.ones((round(t * rate), 1), np.float32) * v for v, t in zip(values, lengths)]))
+
+
+def test_convert_stream_feature_wrapper_fetch():   # tests/test_convert_stream.py:19-104
+    vc = AttrDict(
+        acoustic_converter=AttrDict(config=AttrDict(dataset=AttrDict(acoustic_param=AcousticParam(sampling_rate=16000)))),
+        super_resolution=AttrDict(config=AttrDict(dataset=AttrDict(param=Param()))),
+        output_sampling_rate=24000)
+    st = ConvertStream(voice_changer=vc)
+    st.in_segment_method._keys = ['f0']
+    st.add(0, _wrapper([1], [1]))
+    st.add(1, _wrapper([2], [1]))
+    assert st.fetch(0, 1, 0) == _wrapper([1], [1])
+    assert st.fetch(0.5, 1, 0) == _wrapper([1, 2], [0.5, 0.5])
+    assert st.fetch(-0.5, 1, 0) == _wrapper([0, 1], [0.5, 0.5])
+    assert st.fetch(1.5, 1, 0) == _wrapper([2, 0], [0.5, 0.5])
+    assert st.fetch(0, 1, 0.3) == _wrapper([0, 1, 2], [0.3, 1, 0.3])
+    assert st.fetch(0, 2, 0.3) == _wrapper([0, 1, 2, 0], [0.3, 1, 1, 0.3])
+
+
+def test_feature_wrapper_segment_method():          # tests/test_feature_wrapper_segment_method.py:17-70
+    m = FeatureWrapperSegmentMethod(sampling_rate=100, wave_sampling_rate=10000, order=5, frame_period=10)
+    seg = lambda v, t: _wrapper(v, t, sr=10000, rate=100)
+    pad = m.pad(width=100)
+    assert pad == seg([0], [1])
+    assert pad.wave.wave.dtype == np.float32 and pad.f0.shape == (100, 1) and pad.mc.shape == (100, 6)
+    full = seg([1], [1])
+    assert m.pick(full, 0, 50) == seg([1], [0.5])
+    assert m.pick(full, 50, 100) == seg([1], [0.5])
+    m._keys = ['f0']
+    assert m.concat([seg([0], [1]), seg([1], [1])]) == seg([0, 1], [1, 1])
+
+
+def test_acoustic_feature_helpers():
+    sizes = AcousticFeature.get_sizes(sampling_rate=24000, order=8)
+    assert sizes == dict(f0=1, sp=513, ap=513, coded_ap=3, mc=9, voiced=1)
+    s = AcousticFeature.silent(4, sizes, keys=['f0', 'ap', 'mc', 'voiced'])
+    assert s.f0.shape == (4, 1) and s.voiced.dtype == bool and not s.voiced.any() and (s.ap == 0).all()
+    assert set(s.__dict__) == {'f0', 'sp', 'ap', 'coded_ap', 'mc', 'voiced'}
+    rebuilt = AcousticFeature(**s.__dict__)                       # __dict__ round-trips through the constructor
+    assert rebuilt.mc is s.mc
+    p = s.pick(1, -1, keys=['f0', 'mc'])
+    assert len(p.f0) == 2
+    c = AcousticFeature.concatenate([s, s], keys=['f0'])
+    assert len(c.f0) == 8
+    idx = s.indexing(np.array([True, False, True, False]))
+    assert len(idx.f0) == 2 and len(idx.mc) == 2
+
+
+@pytest.mark.parametrize('rate,T,extra', [(24000, 0.3, 0.0), (24000, 0.3, 0.1), (200, 0.3, 0.5), (200, 0.1, 0.5), (200, 1.0, 0.5), (200, 0.3, 0.05)])
+def test_worker_drive_window_identity(rate, T, extra):
+    """driven like the workers (add at extra + k T, process_next(T)), step k's window is
+    exactly round((T + 2 extra) rate) items long and item i is input item k n - 2 e + i (0 where negative)."""
+    class Ident(BaseStream):
+        def process(self, start_time, time_length, extra_time):
+            return self.fetch(start_time, time_length, extra_time)
+    st = Ident(WaveSegmentMethod(rate), WaveSegmentMethod(rate))
+    w = StreamWrapper(st, extra_time=extra)
+    n, e = round(T * rate), round(extra * rate)
+    start = extra
+    for k in range(400):
+        st.add(start_time=start, data=np.arange(k * n, (k + 1) * n, dtype=np.float32) + 1)
+        start += T
+        win = w.process_next(T)
+        assert len(win) == round((T + 2 * extra) * rate)
+        idx = k * n - 2 * e + np.arange(len(win))
+        np.testing.assert_array_equal(win, np.where(idx >= 0, idx + 1, 0).astype(np.float32))
+        if k % 50 == 49:
+            st.remove(end_time=start - 3 * T - 4 * extra)
+
+
+REF_TESTS = Path('/root/reference/tests')
+
+
+@pytest.mark.skipif(not REF_TESTS.exists(), reason='reference checkout not present (GPU box)')
+@pytest.mark.parametrize('name', ['test_segment', 'test_base_stream', 'test_encode_stream', 'test_convert_stream',
+                                  'test_feature_wrapper_segment_method'])
+def test_reference_unit_tests_run_unmodified(name):
+    """Import the reference's own test module (read-only) with our package answering to
+    `realtime_voice_conversion`, `yukarin`, `become_yukarin`, and run it."""
+    dropin.install()
+    spec = importlib.util.spec_from_file_location(f'_reference_{name}', REF_TESTS / f'{name}.py')
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    suite = unittest.defaultTestLoader.loadTestsFromModule(mod)
+    result = unittest.TextTestRunner(verbosity=0).run(suite)
+    assert result.testsRun > 0 and result.wasSuccessful(), result.failures + result.errors
