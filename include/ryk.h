@@ -134,6 +134,11 @@ int ryk_session_push_device(ryk_engine* e, int session_id, const float* wave_dev
                             int* n_out_dev);
 
 /* ---- diagnostics -------------------------------------------------------------------------------------- */
+/* Synthesizer pulse ring entries [first, first+count) and state {n_pulses, next_pulse, last_location, synthesized_sample,
+ * cumulative_frame, rng_generated, blocks_out}. */
+int ryk_debug_synth_pulses(ryk_engine* e, int synth_id, long long first, int count, long long* index, double* time, int* vuv, long long* state7);
+/* Per-sample time base of the last AddParameters call (interpolated f0, vuv, total phase), first n samples. */
+int ryk_debug_synth_timebase(ryk_engine* e, int synth_id, int n, double* if0, double* ivuv, double* tp);
 /* DIO internals (raw contour before StoneMask, per-band candidates [bands][frames], normalised scores, event counts [bands][4])
  * of the most recent analysis that used the (n, fs, frame_period, f0_floor, f0_ceil) plan. */
 int ryk_debug_dio(ryk_engine* e, int n, int fs, double frame_period_ms, double f0_floor, double f0_ceil,

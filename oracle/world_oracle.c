@@ -843,9 +843,26 @@ int wo_synth_add(void *h, const double *f0, int n, const float *sp, const float 
   /* pulse locations */
   int np_ = ns + hf;
   double *tp = (double *)malloc(sizeof(double) * (np_ + 1)), *wp = (double *)malloc(sizeof(double) * (np_ + 1));
-  tp[0] = hf == 1 ? s->handoff_phase : 2.0 * WO_PI * if0[0] / s->fs;
-  if (np_ > 1) tp[1] = tp[0] + 2.0 * WO_PI * if0[0] / s->fs;
-  for (int i = 1 + hf; i < np_; ++i) tp[i] = tp[i - 1] + 2.0 * WO_PI * if0[i - hf] / s->fs;
+  /* DECIDE: total phase = hand-off phase + prefix sum of the per-sample increments, summed in a FIXED
+   * blocked order (256-sample blocks summed left to right, then block totals left to right) instead of
+   * WORLD's single running sum.  The two differ only in the last bits, but the unvoiced default f0 (500 Hz
+   * at 24 kHz) puts every pulse exactly on a 2*pi multiple, where those last bits decide the pulse's
+   * sample; a fixed order makes the CPU and the parallel GPU scan bit-identical. */
+  {
+    double tp0 = hf == 1 ? s->handoff_phase : 2.0 * WO_PI * if0[0] / s->fs;
+    const int BLK = 256;
+    double base = tp0;
+    for (int b0 = 0; b0 < np_; b0 += BLK) {
+      int b1 = b0 + BLK < np_ ? b0 + BLK : np_;
+      double local = 0.0;
+      for (int i = b0; i < b1; ++i) {
+        double inc = i == 0 ? 0.0 : 2.0 * WO_PI * if0[i - hf] / s->fs;
+        local = local + inc;
+        tp[i] = base + local;
+      }
+      base = base + local;
+    }
+  }
   s->handoff_phase = tp[np_ - 1];
   for (int i = 0; i < np_; ++i) wp[i] = fmod(tp[i], 2.0 * WO_PI);
   for (int i = 0; i < np_ - 1; ++i) {

@@ -561,6 +561,37 @@ int ryk_synth_decode(ryk_engine* h, int id, const double* f0, int n, const float
 }
 
 
+// ---- diagnostics: the synthesizer's pulse ring (index, time, vuv) and scalar state
+int ryk_debug_synth_pulses(ryk_engine* h, int id, long long first, int count, long long* index, double* time, int* vuv, long long* state7) {
+  Engine* e = E(h);
+  RYK_CUDA(cudaSetDevice(e->device));
+  Synth* s = get_synth(e, id);
+  RYK_CHECK(s != nullptr, "no such synthesizer");
+  RYK_CUDA(cudaStreamSynchronize(e->stream));
+  SynthState st;
+  RYK_CUDA(cudaMemcpy(&st, s->dev.state, sizeof(st), cudaMemcpyDeviceToHost));
+  state7[0] = st.n_pulses; state7[1] = st.next_pulse; state7[2] = st.last_location; state7[3] = st.synthesized_sample;
+  state7[4] = st.cumulative_frame; state7[5] = st.rng_generated; state7[6] = st.blocks_out;
+  for (int i = 0; i < count; ++i) {
+    int slot = (int)((first + i) % s->dev.cap_pulses);
+    RYK_CUDA(cudaMemcpy(index + i, s->dev.p_index + slot, sizeof(long long), cudaMemcpyDeviceToHost));
+    RYK_CUDA(cudaMemcpy(time + i, s->dev.p_time + slot, sizeof(double), cudaMemcpyDeviceToHost));
+    RYK_CUDA(cudaMemcpy(vuv + i, s->dev.p_vuv + slot, sizeof(int), cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
+int ryk_debug_synth_timebase(ryk_engine* h, int id, int n, double* if0, double* ivuv, double* tp) {
+  Engine* e = E(h);
+  Synth* s = get_synth(e, id);
+  RYK_CHECK(s != nullptr, "no such synthesizer");
+  RYK_CUDA(cudaStreamSynchronize(e->stream));
+  RYK_CUDA(cudaMemcpy(if0, s->dev.if0, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  RYK_CUDA(cudaMemcpy(ivuv, s->dev.ivuv, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  RYK_CUDA(cudaMemcpy(tp, s->dev.tp, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 // ---- diagnostics: DIO internals of the last ryk_world_f0 / ryk_world_analyze call with this (n, fs, ...) plan
 int ryk_debug_dio(ryk_engine* h, int n, int fs, double fp, double f0_floor, double f0_ceil, double* f0_raw, double* cand, double* score, int* counts) {
   Engine* e = E(h);

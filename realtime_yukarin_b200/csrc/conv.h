@@ -24,6 +24,8 @@ struct ConvLayer {
   const float* w_direct = nullptr;        // [KH][KW][Cin][Cout] fp32
   const float* scale = nullptr;           // [Cout] folded BN scale (1 when no BN)
   const float* shift = nullptr;           // [Cout] folded bias / BN shift
+  bool host_scale_valid = false;          // Cout == 1 layers: scalar scale/shift mirrored on the host
+  float host_scale = 1.f, host_shift = 0.f;
   // tensor-core path (filled by tc_layer_prepare)
   const __half* w_tc = nullptr;           // conv: [Cout][KH*KW*Cin]; deconv: [4 classes][Cout][4*Cin]
   float* splitk_ws = nullptr;             // [pixels][Cout] fp32 when ksplit > 1

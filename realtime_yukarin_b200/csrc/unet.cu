@@ -79,6 +79,7 @@ int unet_set_layer(Engine* e, UNet* n, int idx, const float* W, const float* sca
   RYK_CUDA(cudaMemcpyAsync(L.d_shift, shift, L.cout * sizeof(float), cudaMemcpyHostToDevice, e->stream));
   RYK_CUDA(cudaStreamSynchronize(e->stream));
   RYK_CUDA(cudaFree(d_tmp));
+  L.h_scale0 = scale[0]; L.h_shift0 = shift[0];
   L.loaded = true;
   return 0;
 }
@@ -121,6 +122,7 @@ int unet_get_plan(Engine* e, UNet* n, int B, int H, int W, int precision, UNetPl
     L.SH = n->ndim == 2 ? LW.s : 1; L.SW = LW.s;
     L.PH = n->ndim == 2 ? LW.p : 0; L.PW = LW.p;
     L.w_direct = LW.d_w_direct; L.w_tc = LW.d_w_tc; L.scale = LW.d_scale; L.shift = LW.d_shift;
+    L.host_scale_valid = true; L.host_scale = LW.h_scale0; L.host_shift = LW.h_shift0;
     L.in_dtype = act_dt; L.out_dtype = act_dt;
     if (i == 0) {
       L.Hin = lvlH(0); L.Win = lvlW(0); L.Hout = lvlH(0); L.Wout = lvlW(0);

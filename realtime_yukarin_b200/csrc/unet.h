@@ -16,6 +16,7 @@ struct UNetLayerW {
   __half* d_w_tc = nullptr;
   float* d_scale = nullptr;
   float* d_shift = nullptr;
+  float h_scale0 = 1.f, h_shift0 = 0.f;   // first channel's scale/shift (used by the Cout = 1 kernel)
   bool loaded = false;
 };
 

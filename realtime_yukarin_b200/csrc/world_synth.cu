@@ -72,7 +72,9 @@ __global__ void __launch_bounds__(1024) k_synth_add(SynthDev S, const double* __
   const int nc = n + hf;
   const double hf0 = sh_handoff_f0;
   // c. sample-rate f0 / vuv (coarse axis evaluated on the fly)
-  auto ct = [&](int j) { return j == 0 ? (double)cum0 * fp : (double)(j - hf + cum0 + hf) * fp; };
+  // every product below is rounded on its own (__dmul_rn): nvcc would otherwise fuse `t - m * fp` into one FMA and the
+  // exact-midpoint voiced/unvoiced tie (s == 0.5) would resolve differently from the CPU code
+  auto ct = [&](int j) { return j == 0 ? __dmul_rn((double)cum0, fp) : __dmul_rn((double)(j - hf + cum0 + hf), fp); };
   auto cf = [&](int j) { return (hf && j == 0) ? hf0 : f0[j - hf]; };
   for (int i = threadIdx.x; i < ns; i += blockDim.x) {
     double t = (double)(i + start) / fs;
@@ -80,25 +82,43 @@ __global__ void __launch_bounds__(1024) k_synth_add(SynthDev S, const double* __
     while (lo < hi) { int mid = (lo + hi) >> 1; if (ct(mid) <= t) lo = mid + 1; else hi = mid; }
     int k = lo < 1 ? 1 : (lo > nc - 1 ? nc - 1 : lo);
     double x0 = ct(k - 1), x1 = ct(k);
-    double s = (t - x0) / (x1 - x0);
+    double s = __ddiv_rn(__dsub_rn(t, x0), __dsub_rn(x1, x0));
     double fa = cf(k - 1), fb = cf(k);
     double va = fa == 0.0 ? 0.0 : 1.0, vb = fb == 0.0 ? 0.0 : 1.0;
-    double fi = fa + s * (fb - fa);
-    double vi = va + s * (vb - va);
+    double fi = __dadd_rn(fa, __dmul_rn(s, __dsub_rn(fb, fa)));      // no FMA contraction: must round like the CPU code
+    double vi = __dadd_rn(va, __dmul_rn(s, __dsub_rn(vb, va)));
     vi = vi > 0.5 ? 1.0 : 0.0;
     S.if0[i] = vi == 0.0 ? kDefaultF0 : fi;
     S.ivuv[i] = vi;
   }
   __syncthreads();
-  // d. total phase: tp[0] given, tp[i] = tp[i-1] + 2 pi if0[i - hf] / fs
+  // d. total phase = hand-off phase + prefix sum of the increments in a FIXED blocked order (256-sample blocks
+  //    left to right, then block totals left to right): bit-identical to the oracle, which matters because the
+  //    unvoiced default f0 puts every pulse exactly on a 2*pi multiple (see oracle/world_oracle.c).
   const int np_ = ns + hf;
-  if (threadIdx.x == 0) sh_tp0 = hf == 1 ? st->handoff_phase : 2.0 * kPi * S.if0[0] / fs;
-  for (int i = threadIdx.x; i < np_; i += blockDim.x) S.tp[i] = i == 0 ? 0.0 : 2.0 * kPi * S.if0[i - hf] / fs;
-  __syncthreads();
-  block_inclusive_scan(S.tp, np_, scan_scratch);
-  const double tp0 = sh_tp0;
-  for (int i = threadIdx.x; i < np_; i += blockDim.x) S.tp[i] = tp0 + S.tp[i];
-  __syncthreads();
+  {
+    const int BLK = 256;
+    const int nblk = (np_ + BLK - 1) / BLK;
+    double* totals = scan_scratch;                       // nblk <= 1024 (max_samples_per_add / 256)
+    for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
+      int b0 = b * BLK, b1 = min(b0 + BLK, np_);
+      double local = 0.0;
+      for (int i = b0; i < b1; ++i) {
+        double inc = i == 0 ? 0.0 : 2.0 * kPi * S.if0[i - hf] / fs;
+        local = __dadd_rn(local, inc);
+        S.tp[i] = local;
+      }
+      totals[b] = local;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double base = hf == 1 ? st->handoff_phase : 2.0 * kPi * S.if0[0] / fs;
+      for (int b = 0; b < nblk; ++b) { double t = totals[b]; totals[b] = base; base = __dadd_rn(base, t); }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < np_; i += blockDim.x) S.tp[i] = __dadd_rn(totals[i / BLK], S.tp[i]);
+    __syncthreads();
+  }
   // e. ordered pulse compaction
   int per = (np_ - 1 + blockDim.x - 1) / blockDim.x;
   int lo = threadIdx.x * per, hi = min(lo + per, np_ - 1);
@@ -446,6 +466,7 @@ void synth_destroy(Synth* s) {
 int synth_add_async(Engine* e, Synth* s, const double* d_f0, int n, const float* d_sp, const float* d_ap, cudaStream_t st) {
   SynthDev& D = s->dev;
   RYK_CHECK((long long)n * D.frame_period * D.fs + 2 < D.max_samples_per_add, "too many frames in one AddParameters call");
+  static_assert((1 << 17) / 256 <= 1024, "block totals must fit the scan scratch");
   k_synth_add<<<1, 1024, 0, st>>>(D, d_f0, n, d_sp, d_ap);
   s->host_cum_frames += n;
   long long need = (long long)ceil((double)(s->host_cum_frames < 0 ? 0 : s->host_cum_frames) * D.frame_period * D.fs) + D.fft_size + 2;

@@ -46,7 +46,7 @@ EXPORTED_SYMBOLS = [
     'ryk_stage1_set_stats', 'ryk_f0_set_stats', 'ryk_stage1_convert', 'ryk_f0_convert', 'ryk_mc2sp',
     'ryk_stage2_convert', 'ryk_convert_window', 'ryk_synth_create', 'ryk_synth_destroy', 'ryk_synth_add_parameters',
     'ryk_synth_synthesis2', 'ryk_synth_decode', 'ryk_session_create', 'ryk_session_destroy', 'ryk_session_push',
-    'ryk_session_push_device', 'ryk_test_conv_layer', 'ryk_debug_dio', 'ryk_engine_profile', 'ryk_engine_profile_read', 'ryk_engine_timer_start', 'ryk_engine_timer_stop',
+    'ryk_session_push_device', 'ryk_test_conv_layer', 'ryk_debug_dio', 'ryk_debug_synth_pulses', 'ryk_debug_synth_timebase', 'ryk_engine_profile', 'ryk_engine_profile_read', 'ryk_engine_timer_start', 'ryk_engine_timer_stop',
 ]
 
 
@@ -279,6 +279,23 @@ class Engine(object):
         return out[:nblk.value * B].copy()
 
     # ---- diagnostics ----
+    def debug_synth_pulses(self, sid, first=0, count=None):
+        st = numpy.zeros(7, numpy.int64)
+        z = numpy.zeros(1, numpy.int64); zd = numpy.zeros(1); zi = numpy.zeros(1, numpy.int32)
+        self._check(self.lib.ryk_debug_synth_pulses(self._h, sid, ctypes.c_longlong(0), 0, z.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)),
+                                                    _dp(zd), zi.ctypes.data_as(c_int_p), st.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong))))
+        if count is None:
+            count = int(st[0]) - first
+        idx = numpy.zeros(max(count, 1), numpy.int64); tm = numpy.zeros(max(count, 1)); vuv = numpy.zeros(max(count, 1), numpy.int32)
+        self._check(self.lib.ryk_debug_synth_pulses(self._h, sid, ctypes.c_longlong(first), count, idx.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)),
+                                                    _dp(tm), vuv.ctypes.data_as(c_int_p), st.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong))))
+        return idx[:count], tm[:count], vuv[:count], st
+
+    def debug_synth_timebase(self, sid, n):
+        a, b, c = numpy.zeros(n), numpy.zeros(n), numpy.zeros(n)
+        self._check(self.lib.ryk_debug_synth_timebase(self._h, sid, int(n), _dp(a), _dp(b), _dp(c)))
+        return a, b, c
+
     def debug_dio(self, n, fs, frame_period, f0_floor, f0_ceil):
         nf = dio_num_frames(fs, n, frame_period)
         nbands = 1 + int(numpy.log(f0_ceil / f0_floor) / 0.69314718055994529 * 2.0)

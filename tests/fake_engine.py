@@ -1,0 +1,68 @@
+"""A CPU stand-in for realtime_yukarin_b200.engine.Engine built on the oracle -- TESTS ONLY.
+It lets the host-side Stream/VoiceChanger/Vocoder logic be checked end to end without a GPU
+(the product never uses it; the product path raises when libryk / a B200 is missing)."""
+import numpy as np
+
+from oracle import nets as onets
+from oracle import pipeline as opipe
+from oracle import world as W
+
+
+class OracleEngine:
+    def __init__(self, stage1_npz, stage2_npz, cfg=None, backend='torch'):
+        self.cfg = cfg or opipe.PathConfig()
+        self.p1, self.p2 = onets.load_npz(stage1_npz), onets.load_npz(stage2_npz)
+        self.backend = backend
+        self.stats = None
+        self.synths = {}
+
+    # model upload is a no-op: the oracle reads the same npz files
+    def model_create(self, *a):
+        pass
+
+    def model_layer_shape(self, stage, layer):
+        p = self.p1 if stage == 1 else self.p2
+        part, i = ('encoder', layer) if layer < 8 else ('decoder', layer - 8)
+        plain = (part == 'encoder' and i == 0) or (part == 'decoder' and i == 7)
+        Wt = p[f'{part}/c{i}/W'] if plain else p[f'{part}/c{i}/c/W']
+        tr = part == 'decoder' and i < 7
+        cin, cout = (Wt.shape[0], Wt.shape[1]) if tr else (Wt.shape[1], Wt.shape[0])
+        return tr, cin, cout, Wt.shape[-1]
+
+    def model_set_layer(self, *a):
+        pass
+
+    def stage1_set_stats(self, *a):
+        pass
+
+    def f0_set_stats(self, *stats):
+        self.stats = stats
+
+    def world_analyze(self, x, fs, frame_period, f0_floor, f0_ceil, fft_length, order, alpha, f0=None):
+        f = opipe.extract_features(np.asarray(x, np.float32), self.cfg)
+        return dict(f0=f['f0'].ravel(), sp=f['sp'], ap=f['ap'], mc=f['mc'], voiced=f['voiced'].ravel())
+
+    def silence_mask(self, wave, frame_length, hop, threshold_db, n_frames):
+        return opipe.effective_mask(np.asarray(wave, np.float32), n_frames, self.cfg, threshold_db)
+
+    def stage1_convert(self, x):
+        return onets.stage1_convert(x, self.p1, self.backend)
+
+    def f0_convert(self, f0, voiced):
+        return opipe.f0_convert(f0, voiced, self.stats)
+
+    def mc2sp(self, mc, alpha, fftlen):
+        return W.mc2sp(np.asarray(mc, np.float32), alpha, fftlen)
+
+    def stage2_convert(self, sp):
+        return onets.stage2_convert(sp, self.p2, self.backend)
+
+    def synth_create(self, fs, frame_period, fft_size, buffer_size, number_of_pointers=16):
+        self.synths[len(self.synths)] = W.RealtimeSynthesizer(fs, frame_period, fft_size, buffer_size)
+        return len(self.synths) - 1
+
+    def synth_decode(self, sid, f0, sp, ap, max_blocks=None):
+        return self.synths[sid].decode(np.asarray(f0, np.float64).ravel(), sp, ap)
+
+    def synth_destroy(self, sid):
+        self.synths.pop(sid, None)
