@@ -119,7 +119,7 @@ __global__ void k_f0_convert(const float* __restrict__ f0, const uint8_t* __rest
 // stage-1 forward on device buffers: x already normalised+padded in plan->d_in; returns plan
 static int stage1_plan_for(Engine* e, int Tp, UNetPlan** plan) {
   RYK_CHECK(e->stage1 != nullptr, "stage-1 model not loaded");
-  return unet_get_plan(e, e->stage1, 1, 1, Tp, 0, plan);
+  return unet_get_plan(e, e->stage1, 1, 1, Tp, e->precision, plan);
 }
 static int stage2_plan_for(Engine* e, int Tp, UNetPlan** plan) {
   RYK_CHECK(e->stage2 != nullptr, "stage-2 model not loaded");
@@ -613,11 +613,12 @@ int ryk_test_conv_layer(ryk_engine* h, int transposed, int k, int stride, int pa
   ConvLayer L;
   L.transposed = transposed; L.B = B; L.Hin = Hin; L.Win = Win; L.C0 = C0; L.C1 = C1; L.Cout = Cout;
   L.KH = L.KW = k; L.SH = L.SW = stride; L.PH = L.PW = pad; L.act = act;
-  if (transposed) { L.Hout = (Hin - 1) * stride + k - 2 * pad; L.Wout = (Win - 1) * stride + k - 2 * pad; }
-  else { L.Hout = (Hin + 2 * pad - k) / stride + 1; L.Wout = (Win + 2 * pad - k) / stride + 1; }
+  if (Hin == 1) { L.KH = 1; L.SH = 1; L.PH = 0; }      // 1-D layer (stage-1 nets): kernel (1 x k), stride (1, s), padding (0, p)
+  if (transposed) { L.Hout = (Hin - 1) * L.SH + L.KH - 2 * L.PH; L.Wout = (Win - 1) * stride + k - 2 * pad; }
+  else { L.Hout = (Hin + 2 * L.PH - L.KH) / L.SH + 1; L.Wout = (Win + 2 * pad - k) / stride + 1; }
   const int Cin = C0 + C1;
   size_t n0 = (size_t)B * Hin * Win * C0, n1 = (size_t)B * Hin * Win * C1, no = (size_t)B * L.Hout * L.Wout * Cout;
-  size_t nw = (size_t)Cin * Cout * k * k;
+  size_t nw = (size_t)Cin * Cout * L.KH * k;
   std::vector<void*> frees;
   auto A = [&](size_t bytes) -> void* { void* p = nullptr; if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) return nullptr; frees.push_back(p); return p; };
   float* d_in0 = (float*)A(n0 * 4); float* d_in1 = (float*)A(n1 * 4); float* d_w = (float*)A(nw * 4);
@@ -630,13 +631,13 @@ int ryk_test_conv_layer(ryk_engine* h, int transposed, int k, int stride, int pa
   RYK_CUDA(cudaMemcpyAsync(d_w, W, nw * 4, cudaMemcpyHostToDevice, st));
   RYK_CUDA(cudaMemcpyAsync(d_scale, scale, Cout * 4, cudaMemcpyHostToDevice, st));
   RYK_CUDA(cudaMemcpyAsync(d_shift, shift, Cout * 4, cudaMemcpyHostToDevice, st));
-  if (pack_weights_direct(d_w, transposed, Cin, Cout, k, k, d_wd, st)) return -1;
+  if (pack_weights_direct(d_w, transposed, Cin, Cout, L.KH, k, d_wd, st)) return -1;
   L.w_direct = d_wd; L.scale = d_scale; L.shift = d_shift;
   int rc = 0;
   cudaEvent_t ev0, ev1;
   RYK_CUDA(cudaEventCreate(&ev0)); RYK_CUDA(cudaEventCreate(&ev1));
   if (use_tc) {
-    if (pack_weights_tc(d_w, transposed, Cin, Cout, k, k, d_wt, st)) return -1;
+    if (pack_weights_tc(d_w, transposed, Cin, Cout, L.KH, k, L.SH, stride, d_wt, st)) return -1;
     k_f32_to_f16<<<1184, 256, 0, st>>>(d_in0, d_h0, n0);
     if (n1) k_f32_to_f16<<<1184, 256, 0, st>>>(d_in1, d_h1, n1);
     L.in0 = d_h0; L.in1 = n1 ? d_h1 : nullptr; L.in_dtype = DT_F16; L.out = d_ho; L.out_dtype = DT_F16; L.w_tc = d_wt;

@@ -39,7 +39,7 @@ struct ConvLayer {
 // Weight repacking from the Chainer layouts the model files use:
 //   conv   W: (Cout, Cin, KH, KW)      deconv W: (Cin, Cout, KH, KW)
 int pack_weights_direct(const float* d_w_chainer, int transposed, int Cin, int Cout, int KH, int KW, float* d_out, cudaStream_t st);
-int pack_weights_tc(const float* d_w_chainer, int transposed, int Cin, int Cout, int KH, int KW, __half* d_out, cudaStream_t st);
+int pack_weights_tc(const float* d_w_chainer, int transposed, int Cin, int Cout, int KH, int KW, int SH, int SW, __half* d_out, cudaStream_t st);
 
 int conv_direct_run(const ConvLayer& L, cudaStream_t st);
 

@@ -288,9 +288,11 @@ int pack_weights_direct(const float* d_w, int transposed, int Cin, int Cout, int
 }
 
 // tensor-core packing: fp16, K-major rows.
-//   conv  : out[n][(ky*KW+kx)*Cin + c]                       = W[n][c][ky][kx]
-//   deconv: out[cls][n][(dy*2+dx)*Cin + c], cls = py*2+px    = W[c][n][3-2dy-py][3-2dx-px]   (k4 s2 p1 only)
-__global__ void k_pack_tc(const float* __restrict__ w, int transposed, int Cin, int Cout, int KH, int KW, __half* __restrict__ out) {
+//   conv  : out[n][(ky*KW+kx)*Cin + c]                                    = W[n][c][ky][kx]
+//   deconv: out[cls][n][(dy*(KW/SW)+dx)*Cin + c], cls = py*SW+px          = W[c][n][ky][kx]
+//           with k = 3 - 2d - parity along a k4 s2 p1 dimension and k = 0 along a k1 s1 p0 dimension (1-D nets)
+__global__ void k_pack_tc(const float* __restrict__ w, int transposed, int Cin, int Cout, int KH, int KW, int SH, int SW,
+                          __half* __restrict__ out) {
   size_t total = (size_t)KH * KW * Cin * Cout;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     if (!transposed) {
@@ -300,20 +302,21 @@ __global__ void k_pack_tc(const float* __restrict__ w, int transposed, int Cin, 
       int ky = tap / KW, kx = tap % KW;
       out[i] = __float2half_rn(w[(((size_t)n * Cin + c) * KH + ky) * KW + kx]);
     } else {
-      size_t K = (size_t)4 * Cin;
+      int th = KH / SH, tw = KW / SW;
+      size_t K = (size_t)th * tw * Cin;
       size_t per_cls = K * Cout;
       int cls = i / per_cls; size_t r = i % per_cls;
       int n = r / K; size_t k = r % K;
       int tap = k / Cin, c = k % Cin;
-      int dy = tap >> 1, dx = tap & 1, py = cls >> 1, px = cls & 1;
-      int ky = 3 - 2 * dy - py, kx = 3 - 2 * dx - px;
+      int dy = tap / tw, dx = tap % tw, py = cls / SW, px = cls % SW;
+      int ky = SH == 2 ? 3 - 2 * dy - py : 0, kx = SW == 2 ? 3 - 2 * dx - px : 0;
       out[i] = __float2half_rn(w[(((size_t)c * Cout + n) * KH + ky) * KW + kx]);
     }
   }
 }
 
-int pack_weights_tc(const float* d_w, int transposed, int Cin, int Cout, int KH, int KW, __half* d_out, cudaStream_t st) {
-  k_pack_tc<<<512, 256, 0, st>>>(d_w, transposed, Cin, Cout, KH, KW, d_out);
+int pack_weights_tc(const float* d_w, int transposed, int Cin, int Cout, int KH, int KW, int SH, int SW, __half* d_out, cudaStream_t st) {
+  k_pack_tc<<<512, 256, 0, st>>>(d_w, transposed, Cin, Cout, KH, KW, SH, SW, d_out);
   RYK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -87,8 +87,9 @@ struct TcParams {
   int Hc, Wc;                    // class-local output grid (== Hout, Wout for convs)
   int tile_w, tile_h, tiles_w, tiles_h;
   int chunks0, chunks1;          // 64-channel chunks of source 0 / 1
-  int taps_w, ntaps;             // taps_w = KW (conv: 4) or 2 (deconv class)
-  int stride;                    // 2 for convs, 1 for deconv classes
+  int taps_w, ntaps;             // taps per class: conv KH*KW (taps_w = KW); deconv (KH/SH)*(KW/SW)
+  int sh, sw, ph, pw;            // conv stride / padding per dimension (1-D nets: sh = 1, ph = 0)
+  int classes_w;                 // deconv output-parity classes along W (SW); along H it is SH
   int ksplit, chunks_per_split;
   int act;
   const float* scale; const float* shift;
@@ -121,7 +122,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
   const int b = mt;
   const int n0 = blockIdx.y * BLOCK_N;
   const int cls = blockIdx.z / p.ksplit, split = blockIdx.z % p.ksplit;
-  const int py = cls >> 1, px = cls & 1;
+  const int py = cls / p.classes_w, px = cls % p.classes_w;
   const int oy0 = th * p.tile_h, ox0 = tw * p.tile_w;       // class-local output origin of the tile
   const int chunks_per_tap = p.chunks0 + p.chunks1;
   const int total_chunks = p.ntaps * chunks_per_tap;
@@ -159,8 +160,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
       const int cc = kc - tap * chunks_per_tap;
       const int ty = tap / p.taps_w, tx = tap - ty * p.taps_w;
       int ix, iy;
-      if (!p.transposed) { ix = ox0 * 2 + tx - 1; iy = oy0 * 2 + ty - 1; }
-      else { ix = ox0 + tx - 1 + px; iy = oy0 + ty - 1 + py; }
+      if (!p.transposed) { ix = ox0 * p.sw + tx - p.pw; iy = oy0 * p.sh + ty - p.ph; }
+      else {   // k4 s2 p1 along a strided dimension: input = m + d - 1 + parity; k1 s1 p0 along the other: input = m
+        ix = p.sw == 2 ? ox0 + tx - 1 + px : ox0;
+        iy = p.sh == 2 ? oy0 + ty - 1 + py : oy0;
+      }
       mbar_expect_tx(&full_bar[s], kABytes + kBBytes);
       if (cc < p.chunks0) tma_load_4d(smem_a + s * kABytes, &tmA0, &full_bar[s], cc * kBlockK, ix, iy, b);
       else tma_load_4d(smem_a + s * kABytes, &tmA1, &full_bar[s], (cc - p.chunks0) * kBlockK, ix, iy, b);
@@ -194,7 +198,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
     const int my = oy0 + hl, mx = ox0 + wl;            // class-local output coordinate
     const bool valid = (my < p.Hc) && (mx < p.Wc) && my_chunks > 0;
     int oy = my, ox = mx;
-    if (p.transposed) { oy = my * 2 + py; ox = mx * 2 + px; }
+    if (p.transposed) { oy = my * p.sh + py; ox = mx * p.sw + px; }
     const size_t pix = ((size_t)(b * p.Hout + oy) * p.Wout + ox);
 #pragma unroll 1
     for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
@@ -277,7 +281,9 @@ int tc_init() {
 }
 
 bool tc_layer_eligible(const ConvLayer& L) {
-  if (L.KH != 4 || L.KW != 4 || L.SH != 2 || L.SW != 2 || L.PH != 1 || L.PW != 1) return false;
+  const bool k2d = L.KH == 4 && L.KW == 4 && L.SH == 2 && L.SW == 2 && L.PH == 1 && L.PW == 1;
+  const bool k1d = L.KH == 1 && L.KW == 4 && L.SH == 1 && L.SW == 2 && L.PH == 0 && L.PW == 1;
+  if (!k2d && !k1d) return false;
   if (L.C0 % kBlockK != 0 || L.C1 % kBlockK != 0 || L.C0 == 0) return false;
   if (L.Cout % 64 != 0) return false;
   if (L.in_dtype != DT_F16 || L.out_dtype != DT_F16) return false;
@@ -286,11 +292,11 @@ bool tc_layer_eligible(const ConvLayer& L) {
 
 static int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
 
-static int make_act_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int B, int box_w, int box_h, int stride) {
+static int make_act_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int B, int box_w, int box_h, int stride_w, int stride_h) {
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(box_w * stride), (cuuint32_t)(box_h * stride), 1};
-  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(box_w * stride_w), (cuuint32_t)(box_h * stride_h), 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride_w, (cuuint32_t)stride_h, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -316,8 +322,9 @@ static void tc_geometry(const ConvLayer& L, int num_sms, int* tile_w, int* tile_
   int tw = pow2_floor(Wc < kBlockM ? Wc : kBlockM);
   int th = kBlockM / tw;
   int bn = L.Cout >= 256 ? 256 : (L.Cout >= 128 ? 128 : 64);
-  int tiles = L.B * ((Wc + tw - 1) / tw) * ((Hc + th - 1) / th) * (L.Cout / bn) * (L.transposed ? 4 : 1);
-  int ntaps = L.transposed ? 4 : 16;
+  int classes = L.transposed ? L.SH * L.SW : 1;
+  int tiles = L.B * ((Wc + tw - 1) / tw) * ((Hc + th - 1) / th) * (L.Cout / bn) * classes;
+  int ntaps = L.transposed ? (L.KH / L.SH) * (L.KW / L.SW) : L.KH * L.KW;
   int total_chunks = ntaps * (L.C0 + L.C1) / kBlockK;
   int ks = 1;
   if (tiles < num_sms) {
@@ -338,12 +345,14 @@ int tc_layer_prepare(ConvLayer& L, int num_sms) {
   RYK_CHECK(g_encode != nullptr, "tc_init() was not called");
   RYK_CHECK(tc_layer_eligible(L), "layer is not eligible for the tensor-core path");
   tc_geometry(L, num_sms, &L.tile_w, &L.tile_h, &L.block_n, &L.ksplit);
-  int stride = L.transposed ? 1 : 2;
-  if (make_act_map(&L.tmA0, L.in0, L.C0, L.Win, L.Hin, L.B, L.tile_w, L.tile_h, stride)) return -1;
-  if (L.C1 > 0) { if (make_act_map(&L.tmA1, L.in1, L.C1, L.Win, L.Hin, L.B, L.tile_w, L.tile_h, stride)) return -1; }
+  int stw = L.transposed ? 1 : L.SW, sth = L.transposed ? 1 : L.SH;
+  if (make_act_map(&L.tmA0, L.in0, L.C0, L.Win, L.Hin, L.B, L.tile_w, L.tile_h, stw, sth)) return -1;
+  if (L.C1 > 0) { if (make_act_map(&L.tmA1, L.in1, L.C1, L.Win, L.Hin, L.B, L.tile_w, L.tile_h, stw, sth)) return -1; }
   else L.tmA1 = L.tmA0;
-  size_t K = (size_t)(L.transposed ? 4 : 16) * (L.C0 + L.C1);
-  size_t rows = (size_t)(L.transposed ? 4 : 1) * L.Cout;
+  int classes = L.transposed ? L.SH * L.SW : 1;
+  int ntaps = L.transposed ? (L.KH / L.SH) * (L.KW / L.SW) : L.KH * L.KW;
+  size_t K = (size_t)ntaps * (L.C0 + L.C1);
+  size_t rows = (size_t)classes * L.Cout;
   if (make_weight_map(&L.tmB, L.w_tc, K, rows, L.block_n)) return -1;
   RYK_CHECK(L.ksplit == 1 || L.splitk_ws != nullptr, "split-K layer without a workspace");
   L.tc_ready = true;
@@ -358,8 +367,11 @@ int conv_tc_run(const ConvLayer& L, cudaStream_t st) {
   p.tile_w = L.tile_w; p.tile_h = L.tile_h;
   p.tiles_w = (p.Wc + L.tile_w - 1) / L.tile_w; p.tiles_h = (p.Hc + L.tile_h - 1) / L.tile_h;
   p.chunks0 = L.C0 / kBlockK; p.chunks1 = L.C1 / kBlockK;
-  p.taps_w = L.transposed ? 2 : 4; p.ntaps = L.transposed ? 4 : 16;
-  p.stride = L.transposed ? 1 : 2;
+  p.taps_w = L.transposed ? L.KW / L.SW : L.KW;
+  p.ntaps = L.transposed ? (L.KH / L.SH) * (L.KW / L.SW) : L.KH * L.KW;
+  p.sh = L.SH; p.sw = L.SW; p.ph = L.PH; p.pw = L.PW;
+  p.classes_w = L.transposed ? L.SW : 1;
+  const int classes = L.transposed ? L.SH * L.SW : 1;
   p.ksplit = L.ksplit;
   int total_chunks = p.ntaps * (p.chunks0 + p.chunks1);
   p.chunks_per_split = (total_chunks + L.ksplit - 1) / L.ksplit;
@@ -367,7 +379,7 @@ int conv_tc_run(const ConvLayer& L, cudaStream_t st) {
   p.ws = L.ksplit > 1 ? L.splitk_ws : nullptr;
   size_t out_elems = (size_t)L.B * L.Hout * L.Wout * L.Cout;
   if (p.ws) RYK_CUDA(cudaMemsetAsync(p.ws, 0, out_elems * sizeof(float), st));
-  dim3 grid(L.B * p.tiles_w * p.tiles_h, L.Cout / L.block_n, (L.transposed ? 4 : 1) * L.ksplit);
+  dim3 grid(L.B * p.tiles_w * p.tiles_h, L.Cout / L.block_n, classes * L.ksplit);
   if (L.block_n == 256) k_conv_tc<256, 4><<<grid, kTcThreads, tc_smem_bytes<256, 4>(), st>>>(L.tmA0, L.tmA1, L.tmB, p);
   else if (L.block_n == 128) k_conv_tc<128, 6><<<grid, kTcThreads, tc_smem_bytes<128, 6>(), st>>>(L.tmA0, L.tmA1, L.tmB, p);
   else k_conv_tc<64, 6><<<grid, kTcThreads, tc_smem_bytes<64, 6>(), st>>>(L.tmA0, L.tmA1, L.tmB, p);

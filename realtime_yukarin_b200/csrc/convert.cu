@@ -36,7 +36,7 @@ int convert_window_device(Engine* e, const ConvertBuffers& cb, int T, int n_wave
   const float* d_y = nullptr;
   if (cnt[0] > 0) {   // voice_changer.py:32-35: stage 1 is skipped when no frame is effective
     UNetPlan* p1 = nullptr;
-    if (unet_get_plan(e, e->stage1, 1, 1, cnt[1], 0, &p1)) return -1;
+    if (unet_get_plan(e, e->stage1, 1, 1, cnt[1], e->precision, &p1)) return -1;
     if (stage1_prologue_run(e, cb.d_mc, cb.d_index, cb.d_count, C, (float*)p1->d_in, cnt[1], st)) return -1;
     if (unet_forward(e, p1, st)) return -1;
     d_y = (const float*)p1->d_out;

@@ -39,6 +39,7 @@ struct Engine {
   // synthesizers
   std::vector<Synth*> synths;
   std::vector<Session*> sessions;
+  float* d_colmin = nullptr;         // stage-2 prologue column-minimum partials
   // scratch arena for the per-op host-pointer API (grown on demand)
   void* d_scratch = nullptr; size_t scratch_bytes = 0;
   void* h_pinned = nullptr; size_t pinned_bytes = 0;

@@ -223,18 +223,26 @@ __global__ void k_stage1_epilogue(const float* __restrict__ y /*[Tp][C] network 
 }
 
 // ------------------------------------------------------------------------------------ stage-2 prologue / epilogue
-// x[b][t][k] = log(sp_pad[t][k]) for k < nb-1, where rows t >= T repeat the per-bin minimum over t < T.
-__global__ void k_sr_prologue(const float* __restrict__ sp, int T, int Tp, int nb, float* __restrict__ x) {
+// x[t][k] = log(sp_pad[t][k]) for k < nb-1, where rows t >= T repeat the per-bin minimum over t < T
+// ('minimum' padding of become_yukarin's convert).  Pass 1: per-bin minimum (one thread per bin strip, coalesced
+// across bins); pass 2: one thread per output element.
+__global__ void k_sr_colmin(const float* __restrict__ sp, int T, int nb, int rows_per_block, float* __restrict__ partial) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= nb - 1) return;
+  int t0 = blockIdx.y * rows_per_block, t1 = min(T, t0 + rows_per_block);
   float m = INFINITY;
-  for (int t = 0; t < T; ++t) {
-    float v = sp[(size_t)t * nb + k];
-    m = fminf(m, v);
-    x[(size_t)t * (nb - 1) + k] = logf(v);
-  }
-  float lm = logf(m);
-  for (int t = T; t < Tp; ++t) x[(size_t)t * (nb - 1) + k] = lm;
+  for (int t = t0; t < t1; ++t) m = fminf(m, sp[(size_t)t * nb + k]);
+  partial[(size_t)blockIdx.y * (nb - 1) + k] = m;
+}
+__global__ void k_sr_prologue(const float* __restrict__ sp, const float* __restrict__ partial, int nparts, int T, int Tp, int nb,
+                              float* __restrict__ x) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  int t = blockIdx.y;
+  if (k >= nb - 1 || t >= Tp) return;
+  float v;
+  if (t < T) v = sp[(size_t)t * nb + k];
+  else { v = INFINITY; for (int q = 0; q < nparts; ++q) v = fminf(v, partial[(size_t)q * (nb - 1) + k]); }
+  x[(size_t)t * (nb - 1) + k] = logf(v);
 }
 
 __global__ void k_sr_epilogue(const float* __restrict__ y, int T, int nb, float* __restrict__ sp_out) {
@@ -265,9 +273,13 @@ int stage1_epilogue_run(Engine* e, const float* d_y, const int* d_index, const u
 }
 
 int sr_prologue_run(Engine* e, const float* d_sp, int T, int Tp, int nb, float* d_x, cudaStream_t st) {
-  k_sr_prologue<<<(nb - 1 + 127) / 128, 128, 0, st>>>(d_sp, T, Tp, nb, d_x);
+  const int rows_per_block = 32, nparts = (T + rows_per_block - 1) / rows_per_block;
+  RYK_CHECK((size_t)nparts * (nb - 1) * sizeof(float) <= sizeof(float) * 64 * 512, "window too long for the column-minimum scratch");
+  if (!e->d_colmin) RYK_CUDA(cudaMalloc(&e->d_colmin, sizeof(float) * 64 * 512));
+  k_sr_colmin<<<dim3((nb - 1 + 127) / 128, nparts), 128, 0, st>>>(d_sp, T, nb, rows_per_block, e->d_colmin);
+  k_sr_prologue<<<dim3((nb - 1 + 127) / 128, Tp), 128, 0, st>>>(d_sp, e->d_colmin, nparts, T, Tp, nb, d_x);
   RYK_CUDA(cudaGetLastError());
-  e->launches++;
+  e->launches += 2;
   return 0;
 }
 

@@ -222,7 +222,7 @@ int ryk_session_create(ryk_engine* h, const ryk_session_config* cfg, int* sessio
   if (synth_create(e, cfg->fs, cfg->frame_period_ms, cheaptrick_fft_size(cfg->fs, 71.0), cfg->vocoder_buffer_size, 4096, &s->synth)) return -1;
   // build the U-Net plans this session can need up front (allocation + tensor maps), not on the first chunk
   UNetPlan* p = nullptr;
-  for (int Tp = 128; Tp <= s->Tw + 128; Tp += 128) if (unet_get_plan(e, e->stage1, 1, 1, Tp, 0, &p)) return -1;
+  for (int Tp = 128; Tp <= s->Tw + 128; Tp += 128) if (unet_get_plan(e, e->stage1, 1, 1, Tp, e->precision, &p)) return -1;
   if (unet_get_plan(e, e->stage2, 1, s->Tw + (128 - s->Tw % 128), 512, e->precision, &p)) return -1;
   RYK_CUDA(cudaStreamSynchronize(e->stream));
   e->sessions.push_back(s);

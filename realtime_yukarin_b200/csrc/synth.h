@@ -15,8 +15,8 @@ struct SynthState {            // lives in device memory
   double handoff_phase, handoff_f0;
   long long last_location, synthesized_sample;
   long long n_pulses, next_pulse;
-  long long rng_generated;     // noise ring holds stream positions [.., rng_generated)
-  uint32_t rng_state[4];       // xorshift128 state at position rng_generated
+  long long rng_generated;     // (unused on device; the host tracks how far the noise ring is filled)
+  uint32_t rng_state[2][4];    // xorshift128 state at the fill position, double-buffered across bulk launches
   int plan_blocks, plan_count; long long plan_first;
   int blocks_out;              // result of the last drain
   int carry_sel;
@@ -41,6 +41,7 @@ struct Synth {
   std::vector<void*> allocs;
   long long host_cum_frames = -1;
   long long host_noise_generated = 0;
+  int host_noise_slot = 0;
 };
 
 int synth_create(Engine* e, int fs, double frame_period_ms, int fft_size, int buffer_size, int ring_frames, Synth** out);

@@ -68,10 +68,10 @@ int unet_set_layer(Engine* e, UNet* n, int idx, const float* W, const float* sca
   RYK_CUDA(cudaMemcpyAsync(d_tmp, W, nw * sizeof(float), cudaMemcpyHostToDevice, e->stream));
   if (!L.d_w_direct) RYK_CUDA(cudaMalloc(&L.d_w_direct, nw * sizeof(float)));
   if (pack_weights_direct(d_tmp, L.transposed, L.cin, L.cout, KH, KW, L.d_w_direct, e->stream)) return -1;
-  bool tc_shape = n->ndim == 2 && L.k == 4 && L.cin % 64 == 0 && L.cout % 64 == 0;
+  bool tc_shape = L.k == 4 && L.cin % 64 == 0 && L.cout % 64 == 0;
   if (tc_shape) {
     if (!L.d_w_tc) RYK_CUDA(cudaMalloc(&L.d_w_tc, nw * sizeof(__half)));
-    if (pack_weights_tc(d_tmp, L.transposed, L.cin, L.cout, KH, KW, L.d_w_tc, e->stream)) return -1;
+    if (pack_weights_tc(d_tmp, L.transposed, L.cin, L.cout, KH, KW, n->ndim == 2 ? L.s : 1, L.s, L.d_w_tc, e->stream)) return -1;
   }
   if (!L.d_scale) RYK_CUDA(cudaMalloc(&L.d_scale, L.cout * sizeof(float)));
   if (!L.d_shift) RYK_CUDA(cudaMalloc(&L.d_shift, L.cout * sizeof(float)));
@@ -87,7 +87,6 @@ int unet_set_layer(Engine* e, UNet* n, int idx, const float* W, const float* sca
 // Plan for a (batch, H, W) input; H = 1 for 1-D nets. precision: 0 = FP32 everywhere, 1 = FP16 activations + tcgen05.
 int unet_get_plan(Engine* e, UNet* n, int B, int H, int W, int precision, UNetPlan** out) {
   for (auto& L : n->layers) RYK_CHECK(L.loaded, "U-Net layer weights not loaded");
-  if (n->ndim == 1) precision = 0;
   auto key = std::make_tuple(B, H, W, precision);
   auto it = n->plans.find(key);
   if (it != n->plans.end()) { *out = it->second; return 0; }
@@ -155,7 +154,7 @@ int unet_get_plan(Engine* e, UNet* n, int B, int H, int W, int precision, UNetPl
 
 // d_in / d_out live in the plan (p->d_in, p->d_out); callers fill / read them stream-ordered.
 int unet_forward(Engine* e, UNetPlan* p, cudaStream_t st, int first_layer, int last_layer) {
-  const bool prof = e->profile && p->H > 1;        // time the k4 layers (1..14) of the 2-D net
+  const bool prof = e->profile && p->H > 1;        // time the k4 layers (1..14) of the 2-D (stage-2) net
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   for (int i = first_layer; i <= last_layer; ++i) {
     const ConvLayer& L = p->layers[i];

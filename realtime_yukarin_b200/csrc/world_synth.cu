@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(1024) k_synth_add(SynthDev S, const double* __
   __syncthreads();
   // d. total phase = hand-off phase + prefix sum of the increments in a FIXED blocked order (256-sample blocks
   //    left to right, then block totals left to right): bit-identical to the oracle, which matters because the
-  //    unvoiced default f0 puts every pulse exactly on a 2*pi multiple (see oracle/world_oracle.c).
+  //    unvoiced default f0 puts every pulse exactly on a 2*pi multiple ("discrete decisions").
   const int np_ = ns + hf;
   {
     const int BLK = 256;
@@ -184,28 +184,27 @@ __device__ inline void gf2_apply(const uint32_t* __restrict__ M, uint32_t s[4]) 
   s[0] = o[0]; s[1] = o[1]; s[2] = o[2]; s[3] = o[3];
 }
 
-// Generates `tiles` tiles of kNoiseTile positions starting at state->rng_generated. 256 threads, 32 positions each.
-__global__ void __launch_bounds__(256) k_synth_noise(SynthDev S, const uint32_t* __restrict__ jump /*[8][128][4]*/, int tiles) {
+// Bulk generation of `gridDim.x` tiles of kNoiseTile stream positions starting at base_pos, all tiles in parallel:
+// CTA b jumps the base state ahead by b tiles (tile-stride matrices), thread t by another 32 t positions.
+// state_in/state_out are separate slots so that the read of the base state never races the write of the next one.
+__global__ void __launch_bounds__(256) k_synth_noise(SynthDev S, const uint32_t* __restrict__ jump /*[8][128][4]: T^(384 * 2^j)*/,
+                                                    const uint32_t* __restrict__ jump_tile /*[16][128][4]: T^(12 * 8192 * 2^j)*/,
+                                                    long long base_pos, int slot_in) {
   SynthState* st = S.state;
-  __shared__ uint32_t base[4];
-  for (int tile = 0; tile < tiles; ++tile) {
-    __syncthreads();
-    if (threadIdx.x == 0) { base[0] = st->rng_state[0]; base[1] = st->rng_state[1]; base[2] = st->rng_state[2]; base[3] = st->rng_state[3]; }
-    __syncthreads();
-    uint32_t s[4] = {base[0], base[1], base[2], base[3]};
-    for (int j = 0; j < 8; ++j) if (threadIdx.x & (1 << j)) gf2_apply(jump + j * 512, s);
-    long long pos0 = st->rng_generated + (long long)threadIdx.x * 32;
-    for (int i = 0; i < 32; ++i) {
-      uint32_t tmp = 0;
+  uint32_t s[4] = {st->rng_state[slot_in][0], st->rng_state[slot_in][1], st->rng_state[slot_in][2], st->rng_state[slot_in][3]};
+  const int tile = blockIdx.x;
+  for (int j = 0; j < 16; ++j) if (tile & (1 << j)) gf2_apply(jump_tile + j * 512, s);
+  for (int j = 0; j < 8; ++j) if (threadIdx.x & (1 << j)) gf2_apply(jump + j * 512, s);
+  long long pos0 = base_pos + (long long)tile * kNoiseTile + (long long)threadIdx.x * 32;
+  for (int i = 0; i < 32; ++i) {
+    uint32_t tmp = 0;
 #pragma unroll
-      for (int k = 0; k < 12; ++k) { xs_step(s[0], s[1], s[2], s[3]); tmp += s[3] >> 4; }
-      S.noise[(pos0 + i) % S.cap_noise] = tmp;
-    }
-    __syncthreads();
-    if (threadIdx.x == 255) {
-      st->rng_state[0] = s[0]; st->rng_state[1] = s[1]; st->rng_state[2] = s[2]; st->rng_state[3] = s[3];
-      st->rng_generated += kNoiseTile;
-    }
+    for (int k = 0; k < 12; ++k) { xs_step(s[0], s[1], s[2], s[3]); tmp += s[3] >> 4; }
+    S.noise[(pos0 + i) % S.cap_noise] = tmp;
+  }
+  if (tile == (int)gridDim.x - 1 && threadIdx.x == 255) {
+    st->rng_state[slot_in ^ 1][0] = s[0]; st->rng_state[slot_in ^ 1][1] = s[1];
+    st->rng_state[slot_in ^ 1][2] = s[2]; st->rng_state[slot_in ^ 1][3] = s[3];
   }
 }
 
@@ -392,9 +391,10 @@ static void build_jump_matrices(std::vector<uint32_t>& jump) {
     }
     gf2_mul(pw.data(), pw.data(), Q.data()); pw = Q;
   }
-  jump.resize(8 * 512);
+  // jump[0..8): T^(384 * 2^j) (32 positions * 2^j);  jump[8..24): T^(12 * 8192 * 2^j) = (T^384)^(256 * 2^j)
+  jump.resize(24 * 512);
   P = acc;
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < 24; ++j) {
     memcpy(&jump[j * 512], P.data(), 512 * sizeof(uint32_t));
     gf2_mul(P.data(), P.data(), Q.data()); P = Q;
   }
@@ -421,7 +421,7 @@ int synth_create(Engine* e, int fs, double frame_period_ms, int fft_size, int bu
   Synth* s = new Synth();
   SynthDev& D = s->dev;
   D.fs = fs; D.fft_size = fft_size; D.buffer_size = buffer_size; D.frame_period = frame_period_ms / 1000.0;
-  D.cap_frames = ring_frames; D.cap_pulses = 1 << 15; D.cap_noise = 1 << 18; D.max_pulses = 2048;
+  D.cap_frames = ring_frames; D.cap_pulses = 1 << 15; D.cap_noise = 1 << 22; D.max_pulses = 2048;
   D.carry_len = buffer_size + fft_size;
   D.max_samples_per_add = 1 << 17;
   int nb = fft_size / 2 + 1;
@@ -449,9 +449,9 @@ int synth_create(Engine* e, int fs, double frame_period_ms, int fft_size, int bu
   SynthState init;
   memset(&init, 0, sizeof(init));
   init.cumulative_frame = -1;
-  init.rng_state[0] = 123456789u; init.rng_state[1] = 362436069u; init.rng_state[2] = 521288629u; init.rng_state[3] = 88675123u;
+  init.rng_state[0][0] = 123456789u; init.rng_state[0][1] = 362436069u; init.rng_state[0][2] = 521288629u; init.rng_state[0][3] = 88675123u;
   RYK_CUDA(cudaMemcpy(D.state, &init, sizeof(init), cudaMemcpyHostToDevice));
-  s->host_cum_frames = -1; s->host_noise_generated = 0;
+  s->host_cum_frames = -1; s->host_noise_generated = 0; s->host_noise_slot = 0;
   *out = s;
   return 0;
 }
@@ -471,9 +471,12 @@ int synth_add_async(Engine* e, Synth* s, const double* d_f0, int n, const float*
   s->host_cum_frames += n;
   long long need = (long long)ceil((double)(s->host_cum_frames < 0 ? 0 : s->host_cum_frames) * D.frame_period * D.fs) + D.fft_size + 2;
   if (need > s->host_noise_generated) {
-    int tiles = (int)((need - s->host_noise_generated + kNoiseTile - 1) / kNoiseTile);
-    k_synth_noise<<<1, 256, 0, st>>>(D, e->d_jump, tiles);
+    // top the ring up in one bulk launch: half a ring ahead (cap_noise / 2 positions = 87 s of audio at 24 kHz),
+    // so the noise stream costs one ~1 ms launch every few hundred chunks instead of a kernel per chunk
+    int tiles = D.cap_noise / 2 / kNoiseTile;
+    k_synth_noise<<<tiles, 256, 0, st>>>(D, e->d_jump, e->d_jump + 8 * 512, s->host_noise_generated, s->host_noise_slot);
     s->host_noise_generated += (long long)tiles * kNoiseTile;
+    s->host_noise_slot ^= 1;
     e->launches++;
   }
   e->launches++;

@@ -312,7 +312,10 @@ class Engine(object):
         in1a = _f32(in1) if in1 is not None else numpy.zeros(1, numpy.float32)
         W, scale, shift = _f32(W), _f32(scale), _f32(shift)
         cout = W.shape[1] if transposed else W.shape[0]
-        Ho = (H - 1) * stride + k - 2 * pad if transposed else (H + 2 * pad - k) // stride + 1
+        if H == 1:
+            Ho = 1
+        else:
+            Ho = (H - 1) * stride + k - 2 * pad if transposed else (H + 2 * pad - k) // stride + 1
         Wo = (Wd - 1) * stride + k - 2 * pad if transposed else (Wd + 2 * pad - k) // stride + 1
         out = numpy.empty((B, Ho, Wo, cout), numpy.float32)
         ms = ctypes.c_float()

@@ -12,7 +12,10 @@ def _ref(in0, in1, W, scale, shift, transposed, k, stride, pad, act):
     x = in0 if in1 is None else np.concatenate([in0, in1], axis=3)
     xt = torch.from_numpy(x).permute(0, 3, 1, 2).double()
     Wt = torch.from_numpy(W).double()
-    y = F.conv_transpose2d(xt, Wt, stride=stride, padding=pad) if transposed else F.conv2d(xt, Wt, stride=stride, padding=pad)
+    st, pd = (stride, stride), (pad, pad)
+    if x.shape[1] == 1:                       # 1-D layer: kernel (1, k), stride (1, s), padding (0, p)
+        st, pd = (1, stride), (0, pad)
+    y = F.conv_transpose2d(xt, Wt, stride=st, padding=pd) if transposed else F.conv2d(xt, Wt, stride=st, padding=pd)
     y = y * torch.from_numpy(scale).double()[None, :, None, None] + torch.from_numpy(shift).double()[None, :, None, None]
     if act == 1:
         y = torch.where(y > 0, y, 0.2 * y)
@@ -31,6 +34,13 @@ CASES = [
     (1, 4, 2, 1, 1, 12, 16, 128, 128, 64, 2),
     (1, 4, 2, 1, 2, 24, 32, 64, 64, 128, 2),
     (0, 3, 1, 1, 1, 16, 32, 16, 16, 1, 0),
+    (0, 3, 1, 1, 1, 16, 32, 64, 64, 1, 0),
+    # 1-D (stage-1) layers: H == 1
+    (0, 4, 2, 1, 1, 1, 384, 64, 0, 128, 1),
+    (0, 4, 2, 1, 1, 1, 6, 512, 0, 512, 1),
+    (1, 4, 2, 1, 1, 1, 3, 512, 0, 512, 2),
+    (1, 4, 2, 1, 1, 1, 96, 256, 256, 128, 2),
+    (0, 3, 1, 1, 1, 1, 256, 128, 0, 9, 0),
 ]
 
 
@@ -41,8 +51,9 @@ def test_conv_kernels(engine, case):
     in0 = rng.standard_normal((B, H, W, C0)).astype(np.float32)
     in1 = rng.standard_normal((B, H, W, C1)).astype(np.float32) if C1 else None
     Cin = C0 + C1
-    shape = (Cin, Cout, k, k) if tr else (Cout, Cin, k, k)
-    Wt = (rng.standard_normal(shape) / np.sqrt(Cin * k * k / (4 if tr else 1))).astype(np.float32)
+    kh = 1 if H == 1 else k
+    shape = (Cin, Cout, kh, k) if tr else (Cout, Cin, kh, k)
+    Wt = (rng.standard_normal(shape) / np.sqrt(Cin * kh * k / (4 if tr else 1))).astype(np.float32)
     scale = rng.uniform(0.8, 1.2, Cout).astype(np.float32)
     shift = (0.1 * rng.standard_normal(Cout)).astype(np.float32)
     ref = _ref(in0, in1, Wt, scale, shift, tr, k, s, p, act)

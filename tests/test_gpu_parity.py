@@ -79,9 +79,14 @@ def test_stage1_matches_oracle(engine, small_models, full_models):
         for T in (60, 128, 260):
             mc = (synthetic.MC_MEAN_IN + synthetic.MC_STD_IN * rng.standard_normal((T, 9))).astype(np.float32)
             ref = onets.stage1_convert(mc, p1, backend='torch')
+            engine.set_precision('fp32')
             got = engine.stage1_convert(mc)
-            err = np.abs(got - ref).max()
+            engine.set_precision('fp16')
+            got16 = engine.stage1_convert(mc)
+            err, err16 = np.abs(got - ref).max(), np.abs(got16 - ref).max()
+            print(f'stage1 T={T}: fp32 max err {err:.2e}; fp16-tc max err {err16:.2e} (feature std ~0.1-0.9)')
             assert err < 5e-4, (T, err)
+            assert err16 < 2e-2, (T, err16)
 
 
 def _logspec_err(a, b):
