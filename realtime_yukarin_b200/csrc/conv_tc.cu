@@ -22,6 +22,7 @@
 //   kernel applies the epilogue.
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 #include "conv.h"
 
@@ -94,11 +95,12 @@ struct TcParams {
   int act;
   const float* scale; const float* shift;
   __half* out;
-  float* ws;                     // split-K workspace or nullptr
+  float* ws;                     // split-K workspace [ksplit][pixels][Cout] or nullptr
+  size_t out_pixels;             // B * Hout * Wout
 };
 
-template <int BLOCK_N, int kStages>
-__global__ void __launch_bounds__(kTcThreads, 1)
+template <int BLOCK_N, int kStages, int kMinBlocks>
+__global__ void __launch_bounds__(kTcThreads, kMinBlocks)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
           const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -217,9 +219,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
       if (valid) {
         const int n = n0 + c0;
         if (p.ws) {
-          float* w = p.ws + pix * p.Cout + n;
+          // split-K partial tile: plain (deterministic) stores into this split's slice; k_splitk_reduce sums the slices
+          float4* w = reinterpret_cast<float4*>(p.ws + ((size_t)split * p.out_pixels + pix) * p.Cout + n);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(w + j, __uint_as_float(r[j]));
+          for (int j = 0; j < 8; ++j)
+            w[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
         } else {
           __half* o = p.out + pix * p.Cout + n;
 #pragma unroll
@@ -247,15 +251,26 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
   }
 }
 
-// split-K finalize: out = act(ws * scale + shift) as fp16
-__global__ void k_splitk_finalize(const float* __restrict__ ws, size_t total, int Cout, const float* __restrict__ scale,
-                                  const float* __restrict__ shift, int act, __half* __restrict__ out) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    int n = i % Cout;
-    float v = ws[i] * scale[n] + shift[n];
-    if (act == ACT_LEAKY) v = v > 0.f ? v : 0.2f * v;
-    else if (act == ACT_RELU) v = fmaxf(v, 0.f);
-    out[i] = __float2half_rn(v);
+// split-K reduce + epilogue: out = act((sum over splits of ws[s]) * scale + shift) as fp16, 4 channels per thread
+__global__ void k_splitk_reduce(const float* __restrict__ ws, size_t total4, size_t slice_elems, int ksplit, int Cout,
+                                const float* __restrict__ scale, const float* __restrict__ shift, int act, __half* __restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4* p = reinterpret_cast<const float4*>(ws) + i;
+    float4 a = __ldg(p);
+    for (int s = 1; s < ksplit; ++s) {
+      float4 b = __ldg(p + (size_t)s * (slice_elems / 4));
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    int n = (int)((i * 4) % Cout);
+    float v[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float t = v[j] * __ldg(scale + n + j) + __ldg(shift + n + j);
+      if (act == ACT_LEAKY) t = t > 0.f ? t : 0.2f * t; else if (act == ACT_RELU) t = fmaxf(t, 0.f);
+      v[j] = t;
+    }
+    __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+    reinterpret_cast<uint2*>(out)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
   }
 }
 
@@ -266,6 +281,13 @@ template <int BN, int ST> static constexpr size_t tc_smem_bytes() {
   return (size_t)ST * (kBlockM * kBlockK * 2 + BN * kBlockK * 2) + (2 * ST + 1) * 8 + 16 + 1024;
 }
 
+// kernel variants: (BLOCK_N, stages, CTAs/SM). Two co-resident CTAs let one tile's epilogue overlap the other's main loop.
+static int g_variant = -1;
+static int tc_variant() {
+  if (g_variant < 0) { const char* v = getenv("RYK_TC_VARIANT"); g_variant = v ? atoi(v) : 1; }
+  return g_variant;
+}
+
 int tc_init() {
   if (!g_encode) {
     void* fn = nullptr;
@@ -274,9 +296,12 @@ int tc_init() {
     RYK_CHECK(qres == cudaDriverEntryPointSuccess && fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
     g_encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
   }
-  RYK_CUDA(cudaFuncSetAttribute(k_conv_tc<64, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<64, 6>()));
-  RYK_CUDA(cudaFuncSetAttribute(k_conv_tc<128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<128, 6>()));
-  RYK_CUDA(cudaFuncSetAttribute(k_conv_tc<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<256, 4>()));
+  RYK_CUDA(cudaFuncSetAttribute(k_conv_tc<64, 6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<64, 6>()));
+  RYK_CUDA(cudaFuncSetAttribute(k_conv_tc<128, 6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<128, 6>()));
+  RYK_CUDA(cudaFuncSetAttribute(k_conv_tc<256, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<256, 4>()));
+  RYK_CUDA(cudaFuncSetAttribute(k_conv_tc<64, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<64, 4>()));
+  RYK_CUDA(cudaFuncSetAttribute(k_conv_tc<128, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<128, 3>()));
+  RYK_CUDA(cudaFuncSetAttribute(k_conv_tc<256, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<256, 2>()));
   return 0;
 }
 
@@ -322,15 +347,19 @@ static void tc_geometry(const ConvLayer& L, int num_sms, int* tile_w, int* tile_
   int tw = pow2_floor(Wc < kBlockM ? Wc : kBlockM);
   int th = kBlockM / tw;
   int bn = L.Cout >= 256 ? 256 : (L.Cout >= 128 ? 128 : 64);
+  if (tc_variant() == 1 && bn == 256) bn = 128;        // variant 1: N <= 128 tiles, 3 stages, 2 CTAs/SM
   int classes = L.transposed ? L.SH * L.SW : 1;
   int tiles = L.B * ((Wc + tw - 1) / tw) * ((Hc + th - 1) / th) * (L.Cout / bn) * classes;
   int ntaps = L.transposed ? (L.KH / L.SH) * (L.KW / L.SW) : L.KH * L.KW;
   int total_chunks = ntaps * (L.C0 + L.C1) / kBlockK;
   int ks = 1;
-  if (tiles < num_sms) {
-    ks = num_sms / tiles;
+  int slots = num_sms * (tc_variant() == 0 ? 1 : 2);
+  if (tiles < slots) {
+    ks = slots / tiles;
     if (ks > total_chunks / 2) ks = total_chunks / 2;   // at least 2 chunks per split
     if (ks < 1) ks = 1;
+    int cps = (total_chunks + ks - 1) / ks;
+    ks = (total_chunks + cps - 1) / cps;                // every split owns at least one chunk
   }
   *tile_w = tw; *tile_h = th; *block_n = bn; *ksplit = ks;
 }
@@ -338,7 +367,7 @@ static void tc_geometry(const ConvLayer& L, int num_sms, int* tile_w, int* tile_
 size_t tc_splitk_ws_bytes(const ConvLayer& L, int num_sms) {
   int tw, th, bn, ks;
   tc_geometry(L, num_sms, &tw, &th, &bn, &ks);
-  return ks > 1 ? (size_t)L.B * L.Hout * L.Wout * L.Cout * sizeof(float) : 0;
+  return ks > 1 ? (size_t)ks * L.B * L.Hout * L.Wout * L.Cout * sizeof(float) : 0;
 }
 
 int tc_layer_prepare(ConvLayer& L, int num_sms) {
@@ -377,16 +406,24 @@ int conv_tc_run(const ConvLayer& L, cudaStream_t st) {
   p.chunks_per_split = (total_chunks + L.ksplit - 1) / L.ksplit;
   p.act = L.act; p.scale = L.scale; p.shift = L.shift; p.out = (__half*)L.out;
   p.ws = L.ksplit > 1 ? L.splitk_ws : nullptr;
+  p.out_pixels = (size_t)L.B * L.Hout * L.Wout;
   size_t out_elems = (size_t)L.B * L.Hout * L.Wout * L.Cout;
-  if (p.ws) RYK_CUDA(cudaMemsetAsync(p.ws, 0, out_elems * sizeof(float), st));
   dim3 grid(L.B * p.tiles_w * p.tiles_h, L.Cout / L.block_n, classes * L.ksplit);
-  if (L.block_n == 256) k_conv_tc<256, 4><<<grid, kTcThreads, tc_smem_bytes<256, 4>(), st>>>(L.tmA0, L.tmA1, L.tmB, p);
-  else if (L.block_n == 128) k_conv_tc<128, 6><<<grid, kTcThreads, tc_smem_bytes<128, 6>(), st>>>(L.tmA0, L.tmA1, L.tmB, p);
-  else k_conv_tc<64, 6><<<grid, kTcThreads, tc_smem_bytes<64, 6>(), st>>>(L.tmA0, L.tmA1, L.tmB, p);
+  const int variant = tc_variant();
+  if (variant == 0) {
+    if (L.block_n == 256) k_conv_tc<256, 4, 1><<<grid, kTcThreads, tc_smem_bytes<256, 4>(), st>>>(L.tmA0, L.tmA1, L.tmB, p);
+    else if (L.block_n == 128) k_conv_tc<128, 6, 1><<<grid, kTcThreads, tc_smem_bytes<128, 6>(), st>>>(L.tmA0, L.tmA1, L.tmB, p);
+    else k_conv_tc<64, 6, 1><<<grid, kTcThreads, tc_smem_bytes<64, 6>(), st>>>(L.tmA0, L.tmA1, L.tmB, p);
+  } else {
+    if (L.block_n == 256) k_conv_tc<256, 2, 2><<<grid, kTcThreads, tc_smem_bytes<256, 2>(), st>>>(L.tmA0, L.tmA1, L.tmB, p);
+    else if (L.block_n == 128) k_conv_tc<128, 3, 2><<<grid, kTcThreads, tc_smem_bytes<128, 3>(), st>>>(L.tmA0, L.tmA1, L.tmB, p);
+    else k_conv_tc<64, 4, 2><<<grid, kTcThreads, tc_smem_bytes<64, 4>(), st>>>(L.tmA0, L.tmA1, L.tmB, p);
+  }
   RYK_CUDA(cudaGetLastError());
   if (p.ws) {
-    int blocks = (int)((out_elems + 255) / 256); if (blocks > 1184) blocks = 1184;
-    k_splitk_finalize<<<blocks, 256, 0, st>>>(p.ws, out_elems, L.Cout, L.scale, L.shift, L.act, (__half*)L.out);
+    size_t total4 = out_elems / 4;
+    int blocks = (int)((total4 + 255) / 256); if (blocks > 1184) blocks = 1184;
+    k_splitk_reduce<<<blocks, 256, 0, st>>>(p.ws, total4, out_elems, L.ksplit, L.Cout, L.scale, L.shift, L.act, (__half*)L.out);
     RYK_CUDA(cudaGetLastError());
   }
   return 0;
