@@ -129,7 +129,13 @@ int ryk_session_destroy(ryk_engine* e, int session_id);
  * wave: round(fs * buffer_time) float32 samples; out: up to out_capacity float64 samples; *n_out is a
  * multiple of vocoder_buffer_size (the remainder stays in the synthesizer, as in the reference). */
 int ryk_session_push(ryk_engine* e, int session_id, const float* wave, int n, double* out, int out_capacity, int* n_out);
-/* Same chunk step with the input already resident in HBM and the output left there (throughput measurement). */
+/* Pipelined host API: submit queues a chunk and returns at once (ticket = chunk number), collect waits for that
+ * chunk's output.  Up to 5 chunks may be in flight; encode / convert / decode of consecutive chunks then overlap on
+ * three CUDA streams, exactly like the reference's three worker processes (run.py:58-93).  push == submit + collect. */
+int ryk_session_submit(ryk_engine* e, int session_id, const float* wave, int n, long long* ticket);
+int ryk_session_collect(ryk_engine* e, int session_id, long long ticket, double* out, int out_capacity, int* n_out);
+/* Same chunk step with the input already resident in HBM and the output left there (throughput measurement);
+ * asynchronous: returns when the work is queued, results are valid after ryk_engine_synchronize. */
 int ryk_session_push_device(ryk_engine* e, int session_id, const float* wave_dev, int n, double* out_dev, int out_capacity,
                             int* n_out_dev);
 

@@ -185,13 +185,13 @@ int ryk_engine_set_precision(ryk_engine* h, int mode) {
 }
 int ryk_engine_get_precision(ryk_engine* h) { return E(h)->precision; }
 long long ryk_engine_launch_count(ryk_engine* h) { return E(h)->launches; }
-int ryk_engine_synchronize(ryk_engine* h) { RYK_CUDA(cudaStreamSynchronize(E(h)->stream)); return 0; }
+int ryk_engine_synchronize(ryk_engine* h) { RYK_CUDA(cudaSetDevice(E(h)->device)); RYK_CUDA(cudaDeviceSynchronize()); return 0; }
 
 int ryk_engine_profile(ryk_engine* h, int enable) { E(h)->profile = enable != 0; return 0; }
 // total device time (ms) of the stage-2 k4 (tensor-core) layer block over all forwards since the last read
 int ryk_engine_profile_read(ryk_engine* h, double* stage2_ms_total, int* stage2_runs) {
   Engine* e = E(h);
-  RYK_CUDA(cudaStreamSynchronize(e->stream));
+  RYK_CUDA(cudaDeviceSynchronize());
   double tot = 0.0;
   for (auto& pr : e->prof_events) {
     float ms = 0.f;
@@ -209,12 +209,14 @@ int ryk_engine_timer_start(ryk_engine* h) {
   Engine* e = E(h);
   RYK_CUDA(cudaSetDevice(e->device));
   for (int i = 0; i < 2; ++i) if (!e->timer_ev[i]) RYK_CUDA(cudaEventCreate(&e->timer_ev[i]));
+  RYK_CUDA(cudaDeviceSynchronize());
   RYK_CUDA(cudaEventRecord(e->timer_ev[0], e->stream));
-  return 0;
+  return session_streams_fork(e, e->timer_ev[0]);      // the pipelined sessions run on their own streams
 }
 int ryk_engine_timer_stop(ryk_engine* h, float* elapsed_ms) {
   Engine* e = E(h);
   RYK_CHECK(e->timer_ev[0] != nullptr, "timer was not started");
+  if (session_streams_join(e)) return -1;
   RYK_CUDA(cudaEventRecord(e->timer_ev[1], e->stream));
   RYK_CUDA(cudaEventSynchronize(e->timer_ev[1]));
   RYK_CUDA(cudaEventElapsedTime(elapsed_ms, e->timer_ev[0], e->timer_ev[1]));

@@ -27,5 +27,7 @@ int convert_window_device(Engine* e, const ConvertBuffers& cb, int T, int n_wave
                           int order, int fftlen, cudaStream_t st);
 
 void session_destroy_all(Engine* e);
+int session_streams_fork(Engine* e, cudaEvent_t ev);
+int session_streams_join(Engine* e);
 
 }  // namespace ryk

@@ -1,15 +1,24 @@
-// session.cu -- one audio stream's encode -> convert -> decode chain kept resident in HBM.
+// session.cu -- one audio stream's encode -> convert -> decode chain kept resident in HBM and run as a
+// three-stage software pipeline on three CUDA streams.
 //
 // Semantics = the reference's three StreamWrapper-driven stages as the workers run them
-// (realtime_voice_conversion/worker/{encode,convert,decode}_worker.py with stream/*.py):
-// stage input chunk j is added at start_time = extra + j*T and step k processes [k*T - extra, k*T + T + extra),
-// i.e. window item i of step k is item k*n - 2e + i of the stage's input sequence, silent where that is
-// negative (verified against the reference's BaseStream.fetch).  Instead of Python segment
-// lists, each stage keeps its last window on the device and slides it by one chunk per push:
-//   wave window   (n_wave + 2 e_wave samples)                      -> WORLD analysis -> trim
-//   feature window (n_feat + 2 e_conv frames of f0/ap/mc/voiced + the aligned samples) -> convert -> trim
-//   converted window (n_feat + 2 e_dec frames of f0/ap/sp)         -> realtime synthesizer -> NaN scrub
-// Only the chunk's samples go in and whole synthesizer blocks come out.
+// (realtime_voice_conversion/worker/{encode,convert,decode}_worker.py with stream/*.py): stage input chunk j
+// is added at start_time = extra + j*T and step k processes [k*T - extra, k*T + T + extra), i.e. window item i
+// of step k is item k*n - 2e + i of the stage's input sequence, silent where that is negative (SURVEY A.9a,
+// verified against the reference's BaseStream.fetch).  Instead of Python segment lists each stage keeps its
+// last window on the device and slides it by one chunk per step:
+//   wave window      (n_wave + 2 e_wave samples)                                -> WORLD analysis -> trim
+//   feature window   (n_feat + 2 e_conv frames of f0/ap/mc/voiced + aligned samples) -> gate, stage 1, stage 2 -> trim
+//   converted window (n_feat + 2 e_dec frames of f0/ap/sp)                      -> realtime synthesizer -> NaN scrub
+//
+// Pipelining = what run.py does with three OS processes and queues (run.py:58-93), done with streams and events:
+//   stream E: slide wave, silence gate (needs only the samples), DIO/StoneMask/CheapTrick/D4C          of chunk k+1
+//   stream C: slide features, stage-1 U-Net (+f0 map), mc2sp, stage-2 U-Net                           of chunk k
+//   stream D: slide converted features, synthesizer add/plan/pulse/overlap-add, NaN scrub             of chunk k-1
+// Inter-stage buffers are double-buffered (index = step parity); events order producer/consumer and guard reuse.
+// The only host<->device handshake inside a step is the 8-byte effective-frame count that selects the stage-1
+// plan (T_eff + 128 - T_eff % 128); the gate runs first in stream E so the count is on the host long before
+// stream C needs it.
 #include <math.h>
 #include <string.h>
 #include <vector>
@@ -22,30 +31,35 @@
 
 namespace ryk {
 
+constexpr int kRing = 8;          // event / output-slot ring (pipeline depth is bounded by the buffer guards below)
+
 struct Session {
   ryk_session_config cfg;
   int hop, rate, n_wave, n_feat, e_wave, e_enc_frames, e_conv, e_dec;
   int Lw, Tw, Td, nb, C;
-  int flip = 0;
-  long long step = 0;
-  // sliding windows (double-buffered)
+  long long step = 0;              // chunks submitted
+  long long collected = 0;         // chunks collected through the host API
+  cudaStream_t sE = nullptr, sC = nullptr, sD = nullptr;
+  cudaEvent_t ev_count[kRing], ev_enc[kRing], ev_cslide[kRing], ev_conv[kRing], ev_dslide[kRing], ev_dec[kRing];
+  // sliding windows, double-buffered by step parity
   float* wave_win[2];
   float *cw_f0[2], *cw_ap[2], *cw_mc[2], *cw_wave[2]; uint8_t* cw_voiced[2];
   float *dw_f0[2], *dw_ap[2], *dw_sp[2];
-  // per-step scratch
-  float *enc_f0, *enc_sp, *enc_ap, *enc_mc; uint8_t* enc_voiced;
+  // inter-stage buffers, double-buffered by step parity
+  float *enc_f0[2], *enc_sp[2], *enc_ap[2], *enc_mc[2]; uint8_t* enc_voiced[2];
+  double* d_mse; uint8_t* d_mask[2]; int* d_index[2]; int* d_count[2];
+  float *cv_mc_out[2], *cv_f0_out[2], *cv_ap_out[2], *cv_sp_out[2]; uint8_t* cv_voiced_out[2];
+  float* cv_sp_mid;
   double* dec_f0_f64;
-  double* out_blocks; int max_blocks;
-  int* d_n_out;
-  float* d_chunk;
-  ConvertBuffers cb;
-  double* d_mse; uint8_t* d_mask; int* d_index; int* d_count;
-  float *cv_mc_out, *cv_f0_out, *cv_ap_out, *cv_sp_mid, *cv_sp_out; uint8_t* cv_voiced_out;
+  int max_blocks;
+  // host-API staging rings (pinned host + device), slot = step % kRing
+  float* d_chunk[kRing]; float* h_in[kRing];
+  double* d_out[kRing]; double* h_out[kRing];
+  int* d_n_out[kRing]; int* h_n[kRing];
+  int* h_count[kRing];
   Synth* synth = nullptr;
   DioPlan* dio = nullptr;
-  std::vector<void*> allocs;
-  // pinned staging
-  float* h_in = nullptr; double* h_out = nullptr; int* h_n = nullptr;
+  std::vector<void*> allocs, pinned;
 };
 
 // dst = [old[shift..L), new[0..shift)] row-wise (rows of `row` elements)
@@ -91,10 +105,11 @@ static Session* get_session(Engine* e, int id) { return (id >= 0 && id < (int)e-
 
 static void session_free(Session* s) {
   if (!s) return;
+  for (cudaStream_t st : {s->sE, s->sC, s->sD}) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+  for (int i = 0; i < kRing; ++i)
+    for (cudaEvent_t ev : {s->ev_count[i], s->ev_enc[i], s->ev_cslide[i], s->ev_conv[i], s->ev_dslide[i], s->ev_dec[i]}) if (ev) cudaEventDestroy(ev);
   for (void* p : s->allocs) cudaFree(p);
-  if (s->h_in) cudaFreeHost(s->h_in);
-  if (s->h_out) cudaFreeHost(s->h_out);
-  if (s->h_n) cudaFreeHost(s->h_n);
+  for (void* p : s->pinned) cudaFreeHost(p);
   synth_destroy(s->synth);
   delete s;
 }
@@ -104,46 +119,99 @@ void session_destroy_all(Engine* e) {
   e->sessions.clear();
 }
 
-static int session_step(Engine* e, Session* s, const float* d_chunk, double* d_out, int out_capacity, int* d_n_out, cudaStream_t st) {
-  const int f = s->flip, g = f ^ 1;
+// make every session stream wait for what is already queued on the engine's main stream
+int session_streams_fork(Engine* e, cudaEvent_t ev) {
+  for (Session* s : e->sessions) {
+    if (!s) continue;
+    for (cudaStream_t st : {s->sE, s->sC, s->sD}) RYK_CUDA(cudaStreamWaitEvent(st, ev, 0));
+  }
+  return 0;
+}
+// make the engine's main stream wait for everything queued on the session streams
+int session_streams_join(Engine* e) {
+  for (Session* s : e->sessions) {
+    if (!s) continue;
+    for (cudaStream_t st : {s->sE, s->sC, s->sD}) {
+      cudaEvent_t ev;
+      RYK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      RYK_CUDA(cudaEventRecord(ev, st));
+      RYK_CUDA(cudaStreamWaitEvent(e->stream, ev, 0));
+      RYK_CUDA(cudaEventDestroy(ev));
+    }
+  }
+  return 0;
+}
+
+// Enqueue step k = s->step on the three streams. d_chunk: n_wave samples (device); d_out: >= out_capacity doubles (device).
+static int session_enqueue(Engine* e, Session* s, const float* d_chunk, double* d_out, int out_capacity, int* d_n_out) {
+  const long long k = s->step;
+  const int b = (int)(k & 1), f = b, g = b ^ 1;           // windows: read [f], write [g]; inter-stage sets: [b]
+  const int r = (int)(k % kRing);
   const ryk_session_config& c = s->cfg;
-  // ---- encode: slide the wave window, analyse it, keep the central n_feat frames ----
-  if (slide<float>(s->wave_win[f], d_chunk, s->wave_win[g], s->Lw, s->n_wave, 1, st)) return -1;
-  if (dio_stonemask_run(e, s->dio, s->wave_win[g], st)) return -1;
+  const int pe = s->e_enc_frames, pc = s->e_conv;
+
+  // ================= stream E: gate + WORLD analysis =================
+  if (slide<float>(s->wave_win[f], d_chunk, s->wave_win[g], s->Lw, s->n_wave, 1, s->sE)) return -1;
+  if (slide<float>(s->cw_wave[f], s->wave_win[g] + (size_t)pe * s->hop, s->cw_wave[g], (size_t)s->Tw * s->hop, (size_t)s->n_feat * s->hop, 1, s->sE)) return -1;
+  if (k >= 2) RYK_CUDA(cudaStreamWaitEvent(s->sE, s->ev_conv[(k - 2) % kRing], 0));     // mask/index/count[b] free again
+  if (gate_mask_run(e, s->cw_wave[g], s->Tw * s->hop, c.fft_length, s->hop, c.threshold_db, s->Tw, s->d_mse, s->d_mask[b], s->d_index[b],
+                    s->d_count[b], s->sE)) return -1;
+  RYK_CUDA(cudaMemcpyAsync(s->h_count[r], s->d_count[b], sizeof(int) * 2, cudaMemcpyDeviceToHost, s->sE));
+  RYK_CUDA(cudaEventRecord(s->ev_count[r], s->sE));
+  if (k >= 2) RYK_CUDA(cudaStreamWaitEvent(s->sE, s->ev_cslide[(k - 2) % kRing], 0));   // enc_*[b] consumed by convert k-2
+  if (dio_stonemask_run(e, s->dio, s->wave_win[g], s->sE)) return -1;
   const int n_enc = s->Lw / s->hop;
   if (spectral_analysis_run(e, s->wave_win[g], s->Lw, c.fs, c.frame_period_ms, dio_plan_f0(s->dio), n_enc, c.fft_length, c.order,
-                            s->enc_sp, s->enc_ap, s->enc_mc, s->enc_f0, s->enc_voiced, st)) return -1;
-  e->launches += 13;
-  const int pe = s->e_enc_frames;
-  // ---- convert window: append the new frames (and their aligned samples) ----
-  if (slide<float>(s->cw_f0[f], s->enc_f0 + pe, s->cw_f0[g], s->Tw, s->n_feat, 1, st)) return -1;
-  if (slide<float>(s->cw_ap[f], s->enc_ap + (size_t)pe * s->nb, s->cw_ap[g], s->Tw, s->n_feat, s->nb, st)) return -1;
-  if (slide<float>(s->cw_mc[f], s->enc_mc + (size_t)pe * s->C, s->cw_mc[g], s->Tw, s->n_feat, s->C, st)) return -1;
-  if (slide<uint8_t>(s->cw_voiced[f], s->enc_voiced + pe, s->cw_voiced[g], s->Tw, s->n_feat, 1, st)) return -1;
-  if (slide<float>(s->cw_wave[f], s->wave_win[g] + (size_t)pe * s->hop, s->cw_wave[g], (size_t)s->Tw * s->hop, (size_t)s->n_feat * s->hop, 1, st)) return -1;
-  e->launches += 6;
-  ConvertBuffers cb;
-  cb.d_wave = s->cw_wave[g]; cb.d_f0 = s->cw_f0[g]; cb.d_ap = s->cw_ap[g]; cb.d_mc = s->cw_mc[g]; cb.d_voiced = s->cw_voiced[g];
-  cb.d_mse = s->d_mse; cb.d_mask = s->d_mask; cb.d_index = s->d_index; cb.d_count = s->d_count;
-  cb.d_mc_out = s->cv_mc_out; cb.d_f0_out = s->cv_f0_out; cb.d_ap_out = s->cv_ap_out; cb.d_sp_mid = s->cv_sp_mid;
-  cb.d_sp_out = s->cv_sp_out; cb.d_voiced_out = s->cv_voiced_out;
-  if (convert_window_device(e, cb, s->Tw, s->Tw * s->hop, c.fft_length, s->hop, c.threshold_db, c.order, c.fft_length, st)) return -1;
-  // ---- decode window: central n_feat converted frames ----
-  const int pc = s->e_conv;
-  if (slide<float>(s->dw_f0[f], s->cv_f0_out + pc, s->dw_f0[g], s->Td, s->n_feat, 1, st)) return -1;
-  if (slide<float>(s->dw_ap[f], s->cv_ap_out + (size_t)pc * s->nb, s->dw_ap[g], s->Td, s->n_feat, s->nb, st)) return -1;
-  if (slide<float>(s->dw_sp[f], s->cv_sp_out + (size_t)pc * s->nb, s->dw_sp[g], s->Td, s->n_feat, s->nb, st)) return -1;
-  k_f32_to_f64<<<(s->Td + 127) / 128, 128, 0, st>>>(s->dw_f0[g], s->dec_f0_f64, s->Td);
+                            s->enc_sp[b], s->enc_ap[b], s->enc_mc[b], s->enc_f0[b], s->enc_voiced[b], s->sE)) return -1;
+  RYK_CUDA(cudaEventRecord(s->ev_enc[r], s->sE));
+  e->launches += 15;
+
+  // ================= stream C: stage 1 + stage 2 =================
+  RYK_CUDA(cudaStreamWaitEvent(s->sC, s->ev_enc[r], 0));
+  if (slide<float>(s->cw_f0[f], s->enc_f0[b] + pe, s->cw_f0[g], s->Tw, s->n_feat, 1, s->sC)) return -1;
+  if (slide<float>(s->cw_ap[f], s->enc_ap[b] + (size_t)pe * s->nb, s->cw_ap[g], s->Tw, s->n_feat, s->nb, s->sC)) return -1;
+  if (slide<float>(s->cw_mc[f], s->enc_mc[b] + (size_t)pe * s->C, s->cw_mc[g], s->Tw, s->n_feat, s->C, s->sC)) return -1;
+  if (slide<uint8_t>(s->cw_voiced[f], s->enc_voiced[b] + pe, s->cw_voiced[g], s->Tw, s->n_feat, 1, s->sC)) return -1;
+  RYK_CUDA(cudaEventRecord(s->ev_cslide[r], s->sC));
+  if (k >= 2) RYK_CUDA(cudaStreamWaitEvent(s->sC, s->ev_dslide[(k - 2) % kRing], 0));   // cv_*[b] consumed by decode k-2
+  RYK_CUDA(cudaEventSynchronize(s->ev_count[r]));                                        // effective-frame count of THIS step
+  const int t_eff = s->h_count[r][0], tp1 = s->h_count[r][1];
+  const float* d_y = nullptr;
+  if (t_eff > 0) {      // voice_changer.py:32-35: stage 1 is skipped when no frame is effective
+    UNetPlan* p1 = nullptr;
+    if (unet_get_plan(e, e->stage1, 1, 1, tp1, e->precision, &p1)) return -1;
+    if (stage1_prologue_run(e, s->cw_mc[g], s->d_index[b], s->d_count[b], s->C, (float*)p1->d_in, tp1, s->sC)) return -1;
+    if (unet_forward(e, p1, s->sC)) return -1;
+    d_y = (const float*)p1->d_out;
+  }
+  if (stage1_epilogue_run(e, d_y, s->d_index[b], s->d_mask[b], s->d_count[b], s->Tw, s->C, s->cw_f0[g], s->cw_ap[g], s->cw_voiced[g], s->nb,
+                          kSilentMc0, s->cv_mc_out[b], s->cv_f0_out[b], s->cv_ap_out[b], s->cv_voiced_out[b], s->sC)) return -1;
+  if (mc2sp_run(e, s->cv_mc_out[b], s->Tw, c.order, c.fft_length, 1e-16, s->cv_sp_mid, nullptr, s->sC)) return -1;
+  const int Tp = s->Tw + (128 - s->Tw % 128);
+  UNetPlan* p2 = nullptr;
+  if (unet_get_plan(e, e->stage2, 1, Tp, 512, e->precision, &p2)) return -1;
+  if (sr_prologue_run(e, s->cv_sp_mid, s->Tw, Tp, s->nb, (float*)p2->d_in, s->sC)) return -1;
+  if (unet_forward(e, p2, s->sC)) return -1;
+  if (sr_epilogue_run(e, (const float*)p2->d_out, s->Tw, s->nb, s->cv_sp_out[b], s->sC)) return -1;
+  RYK_CUDA(cudaEventRecord(s->ev_conv[r], s->sC));
   e->launches += 4;
-  if (synth_add_async(e, s->synth, s->dec_f0_f64, s->Td, s->dw_sp[g], s->dw_ap[g], st)) return -1;
+
+  // ================= stream D: realtime synthesizer =================
+  RYK_CUDA(cudaStreamWaitEvent(s->sD, s->ev_conv[r], 0));
+  if (slide<float>(s->dw_f0[f], s->cv_f0_out[b] + pc, s->dw_f0[g], s->Td, s->n_feat, 1, s->sD)) return -1;
+  if (slide<float>(s->dw_ap[f], s->cv_ap_out[b] + (size_t)pc * s->nb, s->dw_ap[g], s->Td, s->n_feat, s->nb, s->sD)) return -1;
+  if (slide<float>(s->dw_sp[f], s->cv_sp_out[b] + (size_t)pc * s->nb, s->dw_sp[g], s->Td, s->n_feat, s->nb, s->sD)) return -1;
+  RYK_CUDA(cudaEventRecord(s->ev_dslide[r], s->sD));
+  k_f32_to_f64<<<(s->Td + 127) / 128, 128, 0, s->sD>>>(s->dw_f0[g], s->dec_f0_f64, s->Td);
+  if (synth_add_async(e, s->synth, s->dec_f0_f64, s->Td, s->dw_sp[g], s->dw_ap[g], s->sD)) return -1;
   int max_blocks = out_capacity / c.vocoder_buffer_size;
   if (max_blocks > s->max_blocks) max_blocks = s->max_blocks;
   RYK_CHECK(max_blocks > 0, "output capacity is smaller than one synthesizer block");
-  if (synth_drain_async(e, s->synth, d_out, max_blocks, st)) return -1;
-  k_scrub<<<8, 256, 0, st>>>(d_out, s->synth->dev.state, c.vocoder_buffer_size, max_blocks * c.vocoder_buffer_size, d_n_out);
-  e->launches += 1;
+  if (synth_drain_async(e, s->synth, d_out, max_blocks, s->sD)) return -1;
+  k_scrub<<<8, 256, 0, s->sD>>>(d_out, s->synth->dev.state, c.vocoder_buffer_size, max_blocks * c.vocoder_buffer_size, d_n_out);
+  e->launches += 5;
   RYK_CUDA(cudaGetLastError());
-  s->flip = g;
+  // ev_dec[r] is recorded by the caller after any device->host copies it appends to stream D
   s->step++;
   return 0;
 }
@@ -161,6 +229,8 @@ int ryk_session_create(ryk_engine* h, const ryk_session_config* cfg, int* sessio
   RYK_CHECK(cfg && session_id, "null argument");
   RYK_CHECK(e->stage1 && e->stage2, "load both models before creating a session");
   Session* s = new Session();
+  memset(s->ev_count, 0, sizeof(s->ev_count)); memset(s->ev_enc, 0, sizeof(s->ev_enc)); memset(s->ev_cslide, 0, sizeof(s->ev_cslide));
+  memset(s->ev_conv, 0, sizeof(s->ev_conv)); memset(s->ev_dslide, 0, sizeof(s->ev_dslide)); memset(s->ev_dec, 0, sizeof(s->ev_dec));
   s->cfg = *cfg;
   s->hop = (int)(cfg->fs * cfg->frame_period_ms / 1000.0);
   s->rate = (int)lround(1000.0 / cfg->frame_period_ms);
@@ -179,7 +249,15 @@ int ryk_session_create(ryk_engine* h, const ryk_session_config* cfg, int* sessio
   RYK_CHECK(s->Lw / s->hop - 2 * s->e_enc_frames == s->n_feat, "encode window does not trim to one chunk of frames");
   RYK_CHECK(s->nb == 513 && e->stage1->in_ch == s->C, "session configuration does not match the loaded models");
   if (sptk_prepare(e, cfg->order, cfg->alpha, cfg->fft_length)) return -1;
+  RYK_CUDA(cudaStreamCreateWithFlags(&s->sE, cudaStreamNonBlocking));
+  RYK_CUDA(cudaStreamCreateWithFlags(&s->sC, cudaStreamNonBlocking));
+  RYK_CUDA(cudaStreamCreateWithFlags(&s->sD, cudaStreamNonBlocking));
+  for (int i = 0; i < kRing; ++i) {
+    cudaEvent_t* evs[] = {&s->ev_count[i], &s->ev_enc[i], &s->ev_cslide[i], &s->ev_conv[i], &s->ev_dslide[i], &s->ev_dec[i]};
+    for (cudaEvent_t* ev : evs) RYK_CUDA(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+  }
   auto A = [&](void** p, size_t bytes) -> int { RYK_CUDA(cudaMalloc(p, bytes ? bytes : 16)); RYK_CUDA(cudaMemset(*p, 0, bytes ? bytes : 16)); s->allocs.push_back(*p); return 0; };
+  auto P = [&](void** p, size_t bytes) -> int { RYK_CUDA(cudaMallocHost(p, bytes ? bytes : 16)); memset(*p, 0, bytes ? bytes : 16); s->pinned.push_back(*p); return 0; };
   const int n_enc = s->Lw / s->hop;
   for (int i = 0; i < 2; ++i) {
     if (A((void**)&s->wave_win[i], sizeof(float) * s->Lw)) return -1;
@@ -193,30 +271,34 @@ int ryk_session_create(ryk_engine* h, const ryk_session_config* cfg, int* sessio
     if (A((void**)&s->dw_sp[i], sizeof(float) * (size_t)s->Td * s->nb)) return -1;
     // silent template mel-cepstrum in the not-yet-filled part of the convert window
     k_fill_rows<float><<<64, 256, 0, e->stream>>>(s->cw_mc[i], s->Tw, s->C, kSilentMc0, 0.f);
+    if (A((void**)&s->enc_f0[i], sizeof(float) * n_enc)) return -1;
+    if (A((void**)&s->enc_sp[i], sizeof(float) * (size_t)n_enc * s->nb)) return -1;
+    if (A((void**)&s->enc_ap[i], sizeof(float) * (size_t)n_enc * s->nb)) return -1;
+    if (A((void**)&s->enc_mc[i], sizeof(float) * (size_t)n_enc * s->C)) return -1;
+    if (A((void**)&s->enc_voiced[i], (size_t)n_enc)) return -1;
+    if (A((void**)&s->d_mask[i], (size_t)s->Tw)) return -1;
+    if (A((void**)&s->d_index[i], sizeof(int) * s->Tw)) return -1;
+    if (A((void**)&s->d_count[i], sizeof(int) * 2)) return -1;
+    if (A((void**)&s->cv_mc_out[i], sizeof(float) * (size_t)s->Tw * s->C)) return -1;
+    if (A((void**)&s->cv_f0_out[i], sizeof(float) * s->Tw)) return -1;
+    if (A((void**)&s->cv_ap_out[i], sizeof(float) * (size_t)s->Tw * s->nb)) return -1;
+    if (A((void**)&s->cv_sp_out[i], sizeof(float) * (size_t)s->Tw * s->nb)) return -1;
+    if (A((void**)&s->cv_voiced_out[i], (size_t)s->Tw)) return -1;
   }
-  if (A((void**)&s->enc_f0, sizeof(float) * n_enc)) return -1;
-  if (A((void**)&s->enc_sp, sizeof(float) * (size_t)n_enc * s->nb)) return -1;
-  if (A((void**)&s->enc_ap, sizeof(float) * (size_t)n_enc * s->nb)) return -1;
-  if (A((void**)&s->enc_mc, sizeof(float) * (size_t)n_enc * s->C)) return -1;
-  if (A((void**)&s->enc_voiced, (size_t)n_enc)) return -1;
+  if (A((void**)&s->d_mse, sizeof(double) * s->Tw)) return -1;
+  if (A((void**)&s->cv_sp_mid, sizeof(float) * (size_t)s->Tw * s->nb)) return -1;
   if (A((void**)&s->dec_f0_f64, sizeof(double) * s->Td)) return -1;
   s->max_blocks = (s->Td * s->hop) / cfg->vocoder_buffer_size + 4;
-  if (A((void**)&s->out_blocks, sizeof(double) * (size_t)s->max_blocks * cfg->vocoder_buffer_size)) return -1;
-  if (A((void**)&s->d_n_out, sizeof(int))) return -1;
-  if (A((void**)&s->d_chunk, sizeof(float) * s->n_wave)) return -1;
-  if (A((void**)&s->d_mse, sizeof(double) * s->Tw)) return -1;
-  if (A((void**)&s->d_mask, (size_t)s->Tw)) return -1;
-  if (A((void**)&s->d_index, sizeof(int) * s->Tw)) return -1;
-  if (A((void**)&s->d_count, sizeof(int) * 2)) return -1;
-  if (A((void**)&s->cv_mc_out, sizeof(float) * (size_t)s->Tw * s->C)) return -1;
-  if (A((void**)&s->cv_f0_out, sizeof(float) * s->Tw)) return -1;
-  if (A((void**)&s->cv_ap_out, sizeof(float) * (size_t)s->Tw * s->nb)) return -1;
-  if (A((void**)&s->cv_sp_mid, sizeof(float) * (size_t)s->Tw * s->nb)) return -1;
-  if (A((void**)&s->cv_sp_out, sizeof(float) * (size_t)s->Tw * s->nb)) return -1;
-  if (A((void**)&s->cv_voiced_out, (size_t)s->Tw)) return -1;
-  RYK_CUDA(cudaMallocHost(&s->h_in, sizeof(float) * s->n_wave));
-  RYK_CUDA(cudaMallocHost(&s->h_out, sizeof(double) * (size_t)s->max_blocks * cfg->vocoder_buffer_size));
-  RYK_CUDA(cudaMallocHost(&s->h_n, sizeof(int)));
+  const size_t out_samples = (size_t)s->max_blocks * cfg->vocoder_buffer_size;
+  for (int i = 0; i < kRing; ++i) {
+    if (A((void**)&s->d_chunk[i], sizeof(float) * s->n_wave)) return -1;
+    if (A((void**)&s->d_out[i], sizeof(double) * out_samples)) return -1;
+    if (A((void**)&s->d_n_out[i], sizeof(int))) return -1;
+    if (P((void**)&s->h_in[i], sizeof(float) * s->n_wave)) return -1;
+    if (P((void**)&s->h_out[i], sizeof(double) * out_samples)) return -1;
+    if (P((void**)&s->h_n[i], sizeof(int))) return -1;
+    if (P((void**)&s->h_count[i], sizeof(int) * 2)) return -1;
+  }
   if (dio_plan_create(e, s->Lw, cfg->fs, cfg->frame_period_ms, cfg->f0_floor, cfg->f0_ceil, &s->dio)) return -1;
   e->dio_plans[std::make_tuple(-(int)e->sessions.size() - 1, cfg->fs, 0, 0, 0)] = s->dio;   // owned by the engine's plan table
   if (synth_create(e, cfg->fs, cfg->frame_period_ms, cheaptrick_fft_size(cfg->fs, 71.0), cfg->vocoder_buffer_size, 4096, &s->synth)) return -1;
@@ -225,6 +307,7 @@ int ryk_session_create(ryk_engine* h, const ryk_session_config* cfg, int* sessio
   for (int Tp = 128; Tp <= s->Tw + 128; Tp += 128) if (unet_get_plan(e, e->stage1, 1, 1, Tp, e->precision, &p)) return -1;
   if (unet_get_plan(e, e->stage2, 1, s->Tw + (128 - s->Tw % 128), 512, e->precision, &p)) return -1;
   RYK_CUDA(cudaStreamSynchronize(e->stream));
+  RYK_CUDA(cudaDeviceSynchronize());
   e->sessions.push_back(s);
   *session_id = (int)e->sessions.size() - 1;
   return 0;
@@ -240,34 +323,62 @@ int ryk_session_destroy(ryk_engine* h, int id) {
   return 0;
 }
 
-int ryk_session_push(ryk_engine* h, int id, const float* wave, int n, double* out, int out_capacity, int* n_out) {
+// Queue one chunk (host samples) without waiting for its output; *ticket identifies it for ryk_session_collect.
+int ryk_session_submit(ryk_engine* h, int id, const float* wave, int n, long long* ticket) {
   Engine* e = &h->impl;
   RYK_CUDA(cudaSetDevice(e->device));
   Session* s = get_session(e, id);
   RYK_CHECK(s != nullptr, "no such session");
   RYK_CHECK(n == s->n_wave, "chunk length must be round(fs * buffer_time)");
-  cudaStream_t st = e->stream;
-  memcpy(s->h_in, wave, sizeof(float) * n);
-  RYK_CUDA(cudaMemcpyAsync(s->d_chunk, s->h_in, sizeof(float) * n, cudaMemcpyHostToDevice, st));
-  int cap = out_capacity < s->max_blocks * s->cfg.vocoder_buffer_size ? out_capacity : s->max_blocks * s->cfg.vocoder_buffer_size;
-  if (session_step(e, s, s->d_chunk, s->out_blocks, cap, s->d_n_out, st)) return -1;
-  RYK_CUDA(cudaMemcpyAsync(s->h_n, s->d_n_out, sizeof(int), cudaMemcpyDeviceToHost, st));
-  RYK_CUDA(cudaMemcpyAsync(s->h_out, s->out_blocks, sizeof(double) * (size_t)(cap / s->cfg.vocoder_buffer_size) * s->cfg.vocoder_buffer_size,
-                           cudaMemcpyDeviceToHost, st));
-  RYK_CUDA(cudaStreamSynchronize(st));
-  int produced = *s->h_n;
-  memcpy(out, s->h_out, sizeof(double) * produced);
-  *n_out = produced;
+  RYK_CHECK(s->step - s->collected < kRing - 2, "too many chunks in flight: collect before submitting more");
+  const long long k = s->step;
+  const int r = (int)(k % kRing);
+  memcpy(s->h_in[r], wave, sizeof(float) * n);
+  RYK_CUDA(cudaMemcpyAsync(s->d_chunk[r], s->h_in[r], sizeof(float) * n, cudaMemcpyHostToDevice, s->sE));
+  const int cap = s->max_blocks * s->cfg.vocoder_buffer_size;
+  if (session_enqueue(e, s, s->d_chunk[r], s->d_out[r], cap, s->d_n_out[r])) return -1;
+  RYK_CUDA(cudaMemcpyAsync(s->h_n[r], s->d_n_out[r], sizeof(int), cudaMemcpyDeviceToHost, s->sD));
+  RYK_CUDA(cudaMemcpyAsync(s->h_out[r], s->d_out[r], sizeof(double) * (size_t)cap, cudaMemcpyDeviceToHost, s->sD));
+  RYK_CUDA(cudaEventRecord(s->ev_dec[r], s->sD));
+  if (ticket) *ticket = k;
   return 0;
 }
 
+// Wait for the chunk `ticket` (tickets must be collected in order) and copy its samples out.
+int ryk_session_collect(ryk_engine* h, int id, long long ticket, double* out, int out_capacity, int* n_out) {
+  Engine* e = &h->impl;
+  Session* s = get_session(e, id);
+  RYK_CHECK(s != nullptr, "no such session");
+  RYK_CHECK(ticket == s->collected && ticket < s->step, "tickets are collected in submission order");
+  const int r = (int)(ticket % kRing);
+  RYK_CUDA(cudaEventSynchronize(s->ev_dec[r]));
+  int produced = *s->h_n[r];
+  RYK_CHECK(produced <= out_capacity, "output buffer too small for the produced blocks");
+  memcpy(out, s->h_out[r], sizeof(double) * produced);
+  *n_out = produced;
+  s->collected++;
+  return 0;
+}
+
+int ryk_session_push(ryk_engine* h, int id, const float* wave, int n, double* out, int out_capacity, int* n_out) {
+  long long ticket = 0;
+  if (ryk_session_submit(h, id, wave, n, &ticket)) return -1;
+  return ryk_session_collect(h, id, ticket, out, out_capacity, n_out);
+}
+
+// Device-resident step, asynchronous: returns as soon as the work is queued (output valid after ryk_engine_synchronize
+// or any later stream-ordered work of this session).
 int ryk_session_push_device(ryk_engine* h, int id, const float* wave_dev, int n, double* out_dev, int out_capacity, int* n_out_dev) {
   Engine* e = &h->impl;
   RYK_CUDA(cudaSetDevice(e->device));
   Session* s = get_session(e, id);
   RYK_CHECK(s != nullptr, "no such session");
   RYK_CHECK(n == s->n_wave, "chunk length must be round(fs * buffer_time)");
-  return session_step(e, s, wave_dev, out_dev, out_capacity, n_out_dev, e->stream);
+  const int r = (int)(s->step % kRing);
+  if (session_enqueue(e, s, wave_dev, out_dev, out_capacity, n_out_dev)) return -1;
+  RYK_CUDA(cudaEventRecord(s->ev_dec[r], s->sD));
+  s->collected = s->step;         // device-resident steps are not collected through the host API
+  return 0;
 }
 
 }  // extern "C"

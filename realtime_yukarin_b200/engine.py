@@ -46,7 +46,7 @@ EXPORTED_SYMBOLS = [
     'ryk_stage1_set_stats', 'ryk_f0_set_stats', 'ryk_stage1_convert', 'ryk_f0_convert', 'ryk_mc2sp',
     'ryk_stage2_convert', 'ryk_convert_window', 'ryk_synth_create', 'ryk_synth_destroy', 'ryk_synth_add_parameters',
     'ryk_synth_synthesis2', 'ryk_synth_decode', 'ryk_session_create', 'ryk_session_destroy', 'ryk_session_push',
-    'ryk_session_push_device', 'ryk_test_conv_layer', 'ryk_debug_dio', 'ryk_debug_synth_pulses', 'ryk_debug_synth_timebase', 'ryk_engine_profile', 'ryk_engine_profile_read', 'ryk_engine_timer_start', 'ryk_engine_timer_stop',
+    'ryk_session_push_device', 'ryk_session_submit', 'ryk_session_collect', 'ryk_test_conv_layer', 'ryk_debug_dio', 'ryk_debug_synth_pulses', 'ryk_debug_synth_timebase', 'ryk_engine_profile', 'ryk_engine_profile_read', 'ryk_engine_timer_start', 'ryk_engine_timer_stop',
 ]
 
 
@@ -339,6 +339,17 @@ class Engine(object):
             out = numpy.empty(len(w) * 2 + 8192, dtype=numpy.float64)
         n_out = ctypes.c_int()
         self._check(self.lib.ryk_session_push(self._h, sid, _fp(w), len(w), _dp(out), len(out), ctypes.byref(n_out)))
+        return out[:n_out.value]
+
+    def session_submit(self, sid: int, wave) -> int:
+        w = _f32(wave)
+        ticket = ctypes.c_longlong()
+        self._check(self.lib.ryk_session_submit(self._h, sid, _fp(w), len(w), ctypes.byref(ticket)))
+        return ticket.value
+
+    def session_collect(self, sid: int, ticket: int, out: numpy.ndarray) -> numpy.ndarray:
+        n_out = ctypes.c_int()
+        self._check(self.lib.ryk_session_collect(self._h, sid, ctypes.c_longlong(ticket), _dp(out), len(out), ctypes.byref(n_out)))
         return out[:n_out.value]
 
     def session_push_device(self, sid: int, wave_dev_ptr: int, n: int, out_dev_ptr: int, out_capacity: int, n_out_dev_ptr: int):
