@@ -109,28 +109,12 @@ def make_models(rank, world):
     d = Path(tempfile.mkdtemp(prefix=f'ryk_bench_r{rank}_'))
     if world == 1:
         return synthetic.write_synthetic_models(d, seed=0)
-    import torch
-    import torch.distributed as dist
-    p1 = synthetic.make_stage1_params(0) if rank == 0 else None
-    p2 = synthetic.make_stage2_params(0) if rank == 0 else None
-    meta = [None]
-    if rank == 0:
-        meta[0] = {'s1': {k: (v.shape, str(v.dtype)) for k, v in p1.items()}, 's2': {k: (v.shape, str(v.dtype)) for k, v in p2.items()}}
-    dist.broadcast_object_list(meta, src=0)
-    out = {}
-    for name, src in (('s1', p1), ('s2', p2)):
-        arrs = {}
-        for k, (shape, dtype) in meta[0][name].items():
-            t = torch.from_numpy(src[k]).cuda() if rank == 0 else torch.empty(shape, dtype=getattr(torch, dtype), device='cuda')
-            dist.broadcast(t, src=0)
-            arrs[k] = t.cpu().numpy()
-        out[name] = arrs
-    paths = synthetic.write_synthetic_models(d, seed=0) if rank == 0 else None
-    if rank != 0:
-        # same files, written from the broadcast tensors
-        paths = synthetic.write_synthetic_models(d, seed=0, base1=8, base2=8)     # configs / statistics
-        np.savez(paths['stage1_model_path'], **out['s1'])
-        np.savez(paths['stage2_model_path'], **out['s2'])
+    from realtime_yukarin_b200.distributed import broadcast_params
+    p1 = broadcast_params(synthetic.make_stage1_params(0) if rank == 0 else None, src=0, device='cuda')
+    p2 = broadcast_params(synthetic.make_stage2_params(0) if rank == 0 else None, src=0, device='cuda')
+    paths = synthetic.write_synthetic_models(d, seed=0, base1=8, base2=8)     # configs / statistics files
+    np.savez(paths['stage1_model_path'], **p1)
+    np.savez(paths['stage2_model_path'], **p2)
     return paths
 
 

@@ -239,3 +239,37 @@ def test_device_session_matches_oracle_stream(engine, small_models):
         assert rmse < 1e-3
         engine.session_destroy(sid)
     engine.set_precision('fp16')
+
+
+def test_pipelined_submit_collect_equals_sequential(engine, small_models):
+    """Keeping several chunks in flight (encode | convert | decode overlapped on three streams) must not change a
+    single sample: compare submit/collect at depth 4 with the oracle stream, fp32 mode."""
+    from realtime_yukarin_b200.engine import SessionConfig
+    ac, sr, f0c = _load(engine, small_models)
+    p1, p2 = onets.load_npz(small_models['stage1_model_path']), onets.load_npz(small_models['stage2_model_path'])
+    engine.set_precision('fp32')
+    T, extra = 0.3, (0.0, 0.5, 0.0)
+    cfg = SessionConfig(fs=24000, frame_period_ms=5.0, f0_floor=71.0, f0_ceil=800.0, fft_length=1024, order=8, alpha=0.466,
+                        buffer_time=T, encode_extra_time=extra[0], convert_extra_time=extra[1], decode_extra_time=extra[2],
+                        threshold_db=60.0, vocoder_buffer_size=1024)
+    sid = engine.session_create(cfg)
+    orc = opipe.StreamOracle(CFG, p1, p2, f0c.stats(), buffer_time=T, extra=extra, backend='torch')
+    x = _speech(3.6, 44)
+    n = round(T * 24000)
+    nchunks = len(x) // n
+    buf = np.empty(32768)
+    tickets, outs = [], []
+    for k in range(nchunks):
+        tickets.append(engine.session_submit(sid, x[k * n:(k + 1) * n]))
+        if len(tickets) > 4:
+            outs.append(engine.session_collect(sid, tickets.pop(0), buf).copy())
+    while tickets:
+        outs.append(engine.session_collect(sid, tickets.pop(0), buf).copy())
+    refs = [orc.push(x[k * n:(k + 1) * n]) for k in range(nchunks)]
+    assert [len(o) for o in outs] == [len(r) for r in refs]
+    y, r = np.concatenate(outs), np.concatenate(refs)
+    rmse = float(np.sqrt(np.mean((y - r) ** 2)))
+    print(f'pipelined depth 4: {len(y)} samples rmse {rmse:.3e}')
+    assert rmse < 1e-3
+    engine.session_destroy(sid)
+    engine.set_precision('fp16')
