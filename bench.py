@@ -69,12 +69,14 @@ class ClockSampler(threading.Thread):
         self.reasons = set()
         self.max_mhz = None
         self._stop_evt = threading.Event()
+        self.ready = threading.Event()
 
     def run(self):
         try:
             import pynvml
             pynvml.nvmlInit()
             h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.ready.set()
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
             names = {
                 getattr(pynvml, 'nvmlClocksEventReasonHwSlowdown', 0x8): 'hw_slowdown',
@@ -91,7 +93,7 @@ class ClockSampler(threading.Thread):
                 for bit, name in names.items():
                     if r & bit:
                         self.reasons.add(name)
-                time.sleep(0.02)
+                time.sleep(0.005)
         except Exception as exc:        # clocks are best-effort; never fail the bench for them
             self.reasons.add(f'unavailable:{type(exc).__name__}')
 
@@ -241,11 +243,14 @@ def run_gpu(args):
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    sampler.ready.wait(timeout=5)
     launches0 = eng.launch_count
     eng.profile(True)
     eng.timer_start()
+    t_host0 = time.perf_counter()
     for k in range(args.warmup, total):
         push_dev(k)
+    t_host = time.perf_counter() - t_host0          # host time to queue the K steps (launch overhead view)
     t_dev = eng.timer_stop() * 1e-3          # CUDA events on the stream the kernels are launched on
     barrier()
     s2_ms, s2_runs = eng.profile_read()
@@ -276,6 +281,10 @@ def run_gpu(args):
     t_e2e = max_over_ranks(t_e2e)
     eng.session_destroy(sid)
 
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     value = world * args.steps / t_dev
@@ -283,9 +292,11 @@ def run_gpu(args):
     peaks = measured_peaks()
     fl = stage2_tc_flop()
     ach = fl * s2_runs / (s2_ms * 1e-3) / 1e12 if s2_ms > 0 else None
-    cpu = CpuPath(paths, n_chunks=8)
-    cpu.step()
-    cpu_rate, cores = cpu.rate(3), cpu.cores
+    cpu_rate = cores = None
+    if world == 1:                      # reported baseline: rank 0 at N = 1 only
+        cpu = CpuPath(paths, n_chunks=8)
+        cpu.step()
+        cpu_rate, cores = cpu.rate(3), cpu.cores
     line = dict(
         metric=METRIC, value=value, unit='chunks/s', rtf=value * BUFFER_TIME, n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=1000.0 * t_dev / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
@@ -295,15 +306,16 @@ def run_gpu(args):
                     streams_per_gpu=1, silence_threshold_db=THRESHOLD_DB),
         e2e=dict(value=e2e, unit='chunks/s', rtf=e2e * BUFFER_TIME, h2d_bytes_per_step=n * 4,
                  d2h_bytes_per_step=int(produced / max(1, args.steps)) * 8 + 4 + 8),
-        gpu_launches=int(launches),
+        gpu_launches=int(launches), host_enqueue_ms_per_step=1000.0 * t_host / args.steps,
         clocks=clocks,
         roofline=dict(bound='tensor', kernel='k_conv_tc (stage-2 k4 layers 1..14, incl. split-K memset/finalize)', achieved=ach, peak=peaks['tflops'],
                       unit='TFLOP/s', frac=(ach / peaks['tflops']) if ach else None, traffic=None, peak_source=peaks['source'],
                       flop_per_step=fl, ms_per_step_in_kernel=(s2_ms / s2_runs) if s2_runs else None),
-        cpu_baseline=dict(value=cpu_rate, unit='chunks/s', cores=cores, kind='port',
-                          sample='3 chunks of 0.3 s after a warm-up chunk, C WORLD/SPTK restatement + torch-CPU U-Nets, same models/audio'),
     )
-    print(json.dumps(line))
+    if cpu_rate is not None:
+        line['cpu_baseline'] = dict(value=cpu_rate, unit='chunks/s', cores=cores, kind='port',
+                                    sample='3 chunks of 0.3 s after a warm-up chunk, C WORLD/SPTK restatement + torch-CPU U-Nets, same models/audio')
+    print(json.dumps(line), flush=True)
 
 
 def main():

@@ -157,6 +157,7 @@ int ryk_engine_create(int device, ryk_engine** out) {
   RYK_CUDA(cudaMemcpy(e->d_twiddle, tw.data(), sizeof(double2) * tw.size(), cudaMemcpyHostToDevice));
   if (analysis_kernels_init()) return -1;
   if (tc_init()) return -1;
+  RYK_CUDA(cudaMalloc(&e->d_colmin, sizeof(float) * 64 * 512));   // stage-2 prologue scratch (never allocated inside a graph capture)
   *out = h;
   return 0;
 }
@@ -170,7 +171,7 @@ int ryk_engine_destroy(ryk_engine* h) {
   unet_destroy(e->stage1); unet_destroy(e->stage2);
   for (Synth* s : e->synths) synth_destroy(s);
   session_destroy_all(e);
-  void* ptrs[] = {e->d_twiddle, e->d_jump, e->d_G, e->d_H, e->d_s1_in_mean, e->d_s1_in_std, e->d_s1_out_mean, e->d_s1_out_std, e->d_scratch};
+  void* ptrs[] = {e->d_colmin, e->d_twiddle, e->d_jump, e->d_G, e->d_H, e->d_s1_in_mean, e->d_s1_in_std, e->d_s1_out_mean, e->d_s1_out_std, e->d_scratch};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (e->h_pinned) cudaFreeHost(e->h_pinned);
   cudaStreamDestroy(e->stream);

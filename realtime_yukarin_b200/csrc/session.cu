@@ -13,14 +13,17 @@
 //
 // Pipelining = what run.py does with three OS processes and queues (run.py:58-93), done with streams and events:
 //   stream E: slide wave, silence gate (needs only the samples), DIO/StoneMask/CheapTrick/D4C          of chunk k+1
-//   stream C: slide features, stage-1 U-Net (+f0 map), mc2sp, stage-2 U-Net                           of chunk k
-//   stream D: slide converted features, synthesizer add/plan/pulse/overlap-add, NaN scrub             of chunk k-1
+//   stream C: slide features, stage-1 U-Net (+f0 map), mc2sp                                          of chunk k
+//   stream C2: stage-2 U-Net (the tcgen05 layers)                                                     of chunk k-1
+//   stream D: slide converted features, synthesizer add/plan/pulse/overlap-add, NaN scrub             of chunk k-2
 // Inter-stage buffers are double-buffered (index = step parity); events order producer/consumer and guard reuse.
 // The only host<->device handshake inside a step is the 8-byte effective-frame count that selects the stage-1
 // plan (T_eff + 128 - T_eff % 128); the gate runs first in stream E so the count is on the host long before
 // stream C needs it.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
+#include <map>
 #include <vector>
 
 #include "../../include/ryk.h"
@@ -33,14 +36,15 @@ namespace ryk {
 
 constexpr int kRing = 8;          // event / output-slot ring (pipeline depth is bounded by the buffer guards below)
 
+struct StageGraph { cudaGraphExec_t exec = nullptr; long long launches = 0; };
 struct Session {
   ryk_session_config cfg;
   int hop, rate, n_wave, n_feat, e_wave, e_enc_frames, e_conv, e_dec;
   int Lw, Tw, Td, nb, C;
   long long step = 0;              // chunks submitted
   long long collected = 0;         // chunks collected through the host API
-  cudaStream_t sE = nullptr, sC = nullptr, sD = nullptr;
-  cudaEvent_t ev_count[kRing], ev_enc[kRing], ev_cslide[kRing], ev_conv[kRing], ev_dslide[kRing], ev_dec[kRing];
+  cudaStream_t sE = nullptr, sC = nullptr, sC2 = nullptr, sD = nullptr;     // encode | stage 1 | stage 2 | decode
+  cudaEvent_t ev_count[kRing], ev_enc[kRing], ev_cslide[kRing], ev_s1[kRing], ev_conv[kRing], ev_dslide[kRing], ev_dec[kRing];
   // sliding windows, double-buffered by step parity
   float* wave_win[2];
   float *cw_f0[2], *cw_ap[2], *cw_mc[2], *cw_wave[2]; uint8_t* cw_voiced[2];
@@ -49,7 +53,7 @@ struct Session {
   float *enc_f0[2], *enc_sp[2], *enc_ap[2], *enc_mc[2]; uint8_t* enc_voiced[2];
   double* d_mse; uint8_t* d_mask[2]; int* d_index[2]; int* d_count[2];
   float *cv_mc_out[2], *cv_f0_out[2], *cv_ap_out[2], *cv_sp_out[2]; uint8_t* cv_voiced_out[2];
-  float* cv_sp_mid;
+  float* cv_sp_mid[2];
   double* dec_f0_f64;
   int max_blocks;
   // host-API staging rings (pinned host + device), slot = step % kRing
@@ -57,6 +61,11 @@ struct Session {
   double* d_out[kRing]; double* h_out[kRing];
   int* d_n_out[kRing]; int* h_n[kRing];
   int* h_count[kRing];
+  float* d_chunk_fixed = nullptr;      // the chunk the (captured) encode graph reads
+  double* d_out_fixed[2];              // blocks written by the (captured) decode graph, by parity
+  int* d_n_fixed[2];
+  bool use_graphs = true;
+  std::map<int, StageGraph> graphs;
   Synth* synth = nullptr;
   DioPlan* dio = nullptr;
   std::vector<void*> allocs, pinned;
@@ -69,6 +78,21 @@ __global__ void k_slide(const T* __restrict__ old_, const T* __restrict__ new_, 
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     size_t r = i / row;
     dst[i] = r + shift < L ? old_[i + shift * row] : new_[i - (L - shift) * row];
+  }
+}
+
+// several windows slid by one launch (blockIdx.y = window): dst = [old[shift..L), new[0..shift)] in units of `elem` bytes
+struct SlideDesc { const void* old_; const void* new_; void* dst; size_t L, shift, row; int elem; };
+struct SlideBatch { SlideDesc d[5]; int n; };
+__global__ void k_slide_multi(SlideBatch b) {
+  const SlideDesc& d = b.d[blockIdx.y];
+  size_t total = d.L * d.row;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t r = i / d.row;
+    bool keep = r + d.shift < d.L;
+    size_t src = keep ? i + d.shift * d.row : i - (d.L - d.shift) * d.row;
+    if (d.elem == 4) ((uint32_t*)d.dst)[i] = keep ? ((const uint32_t*)d.old_)[src] : ((const uint32_t*)d.new_)[src];
+    else ((uint8_t*)d.dst)[i] = keep ? ((const uint8_t*)d.old_)[src] : ((const uint8_t*)d.new_)[src];
   }
 }
 
@@ -101,13 +125,29 @@ static int slide(const T* old_, const T* new_, T* dst, size_t L, size_t shift, s
   return 0;
 }
 
+static int slide_batch(SlideBatch& b, cudaStream_t st) {
+  size_t mx = 0;
+  for (int i = 0; i < b.n; ++i) { size_t t = b.d[i].L * b.d[i].row; if (t > mx) mx = t; }
+  if (mx == 0) return 0;
+  int blocks = (int)((mx + 255) / 256); if (blocks > 592) blocks = 592;
+  k_slide_multi<<<dim3(blocks, b.n), 256, 0, st>>>(b);
+  RYK_CUDA(cudaGetLastError());
+  return 0;
+}
+template <typename T>
+static void slide_add(SlideBatch& b, const T* old_, const T* new_, T* dst, size_t L, size_t shift, size_t row) {
+  SlideDesc& d = b.d[b.n++];
+  d.old_ = old_; d.new_ = new_; d.dst = dst; d.L = L; d.shift = shift; d.row = row; d.elem = (int)sizeof(T);
+}
+
 static Session* get_session(Engine* e, int id) { return (id >= 0 && id < (int)e->sessions.size()) ? e->sessions[id] : nullptr; }
 
 static void session_free(Session* s) {
   if (!s) return;
-  for (cudaStream_t st : {s->sE, s->sC, s->sD}) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+  for (cudaStream_t st : {s->sE, s->sC, s->sC2, s->sD}) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
   for (int i = 0; i < kRing; ++i)
-    for (cudaEvent_t ev : {s->ev_count[i], s->ev_enc[i], s->ev_cslide[i], s->ev_conv[i], s->ev_dslide[i], s->ev_dec[i]}) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : {s->ev_count[i], s->ev_enc[i], s->ev_cslide[i], s->ev_s1[i], s->ev_conv[i], s->ev_dslide[i], s->ev_dec[i]}) if (ev) cudaEventDestroy(ev);
+  for (auto& kv : s->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   for (void* p : s->allocs) cudaFree(p);
   for (void* p : s->pinned) cudaFreeHost(p);
   synth_destroy(s->synth);
@@ -123,7 +163,7 @@ void session_destroy_all(Engine* e) {
 int session_streams_fork(Engine* e, cudaEvent_t ev) {
   for (Session* s : e->sessions) {
     if (!s) continue;
-    for (cudaStream_t st : {s->sE, s->sC, s->sD}) RYK_CUDA(cudaStreamWaitEvent(st, ev, 0));
+    for (cudaStream_t st : {s->sE, s->sC, s->sC2, s->sD}) RYK_CUDA(cudaStreamWaitEvent(st, ev, 0));
   }
   return 0;
 }
@@ -131,7 +171,7 @@ int session_streams_fork(Engine* e, cudaEvent_t ev) {
 int session_streams_join(Engine* e) {
   for (Session* s : e->sessions) {
     if (!s) continue;
-    for (cudaStream_t st : {s->sE, s->sC, s->sD}) {
+    for (cudaStream_t st : {s->sE, s->sC, s->sC2, s->sD}) {
       cudaEvent_t ev;
       RYK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
       RYK_CUDA(cudaEventRecord(ev, st));
@@ -142,76 +182,142 @@ int session_streams_join(Engine* e) {
   return 0;
 }
 
-// Enqueue step k = s->step on the three streams. d_chunk: n_wave samples (device); d_out: >= out_capacity doubles (device).
-static int session_enqueue(Engine* e, Session* s, const float* d_chunk, double* d_out, int out_capacity, int* d_n_out) {
+// ---- CUDA-graph cache ---------------------------------------------------------------------------------
+// Every stage of a step is a fixed kernel sequence over fixed buffers (selected by chunk parity, and for stage 1 by the
+// padded effective length), so each variant is stream-captured once and replayed: a step costs ~6 graph launches on
+// the host instead of ~90 kernel launches (the host was the bottleneck at 0.75 ms of launch overhead per 0.78 ms step).
+template <typename F>
+static int run_stage(Engine* e, Session* s, int key, cudaStream_t st, F&& body) {
+  if (!s->use_graphs) return body();
+  StageGraph& g = s->graphs[key];
+  if (!g.exec) {
+    long long before = e->launches;
+    cudaGraph_t graph = nullptr;
+    RYK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = body();
+    cudaError_t err = cudaStreamEndCapture(st, &graph);
+    if (rc) return rc;
+    RYK_CUDA(err);
+    RYK_CUDA(cudaGraphInstantiate(&g.exec, graph, 0));
+    RYK_CUDA(cudaGraphDestroy(graph));
+    g.launches = e->launches - before;
+    e->launches = before;
+  }
+  RYK_CUDA(cudaGraphLaunch(g.exec, st));
+  e->launches += g.launches;
+  return 0;
+}
+
+enum { G_E1 = 0, G_E2 = 2, G_S1 = 4 /* + 2 * bucket + parity, bucket 0..15 */, G_S2A = 40, G_S2B = 42, G_S2C = 44, G_D = 46 };
+
+// Enqueue step k = s->step on the four streams. d_chunk: n_wave samples (device); results land in s->d_out_fixed[b] / s->d_n_fixed[b].
+static int session_enqueue(Engine* e, Session* s, const float* d_chunk_user) {
   const long long k = s->step;
   const int b = (int)(k & 1), f = b, g = b ^ 1;           // windows: read [f], write [g]; inter-stage sets: [b]
   const int r = (int)(k % kRing);
   const ryk_session_config& c = s->cfg;
   const int pe = s->e_enc_frames, pc = s->e_conv;
+  const bool was_profiling = e->profile;
+  e->profile = false;                                      // the session places its own timing events (between graph launches)
 
   // ================= stream E: gate + WORLD analysis =================
-  if (slide<float>(s->wave_win[f], d_chunk, s->wave_win[g], s->Lw, s->n_wave, 1, s->sE)) return -1;
-  if (slide<float>(s->cw_wave[f], s->wave_win[g] + (size_t)pe * s->hop, s->cw_wave[g], (size_t)s->Tw * s->hop, (size_t)s->n_feat * s->hop, 1, s->sE)) return -1;
+  RYK_CUDA(cudaMemcpyAsync(s->d_chunk_fixed, d_chunk_user, sizeof(float) * s->n_wave, cudaMemcpyDeviceToDevice, s->sE));
   if (k >= 2) RYK_CUDA(cudaStreamWaitEvent(s->sE, s->ev_conv[(k - 2) % kRing], 0));     // mask/index/count[b] free again
-  if (gate_mask_run(e, s->cw_wave[g], s->Tw * s->hop, c.fft_length, s->hop, c.threshold_db, s->Tw, s->d_mse, s->d_mask[b], s->d_index[b],
-                    s->d_count[b], s->sE)) return -1;
+  if (run_stage(e, s, G_E1 + b, s->sE, [&]() -> int {
+        if (slide<float>(s->wave_win[f], s->d_chunk_fixed, s->wave_win[g], s->Lw, s->n_wave, 1, s->sE)) return -1;
+        if (slide<float>(s->cw_wave[f], s->wave_win[g] + (size_t)pe * s->hop, s->cw_wave[g], (size_t)s->Tw * s->hop, (size_t)s->n_feat * s->hop, 1, s->sE)) return -1;
+        e->launches += 2;
+        return gate_mask_run(e, s->cw_wave[g], s->Tw * s->hop, c.fft_length, s->hop, c.threshold_db, s->Tw, s->d_mse, s->d_mask[b], s->d_index[b],
+                             s->d_count[b], s->sE);
+      })) return -1;
   RYK_CUDA(cudaMemcpyAsync(s->h_count[r], s->d_count[b], sizeof(int) * 2, cudaMemcpyDeviceToHost, s->sE));
   RYK_CUDA(cudaEventRecord(s->ev_count[r], s->sE));
-  if (k >= 2) RYK_CUDA(cudaStreamWaitEvent(s->sE, s->ev_cslide[(k - 2) % kRing], 0));   // enc_*[b] consumed by convert k-2
-  if (dio_stonemask_run(e, s->dio, s->wave_win[g], s->sE)) return -1;
-  const int n_enc = s->Lw / s->hop;
-  if (spectral_analysis_run(e, s->wave_win[g], s->Lw, c.fs, c.frame_period_ms, dio_plan_f0(s->dio), n_enc, c.fft_length, c.order,
-                            s->enc_sp[b], s->enc_ap[b], s->enc_mc[b], s->enc_f0[b], s->enc_voiced[b], s->sE)) return -1;
+  if (k >= 2) RYK_CUDA(cudaStreamWaitEvent(s->sE, s->ev_cslide[(k - 2) % kRing], 0));   // enc_*[b] consumed by stage 1 of k-2
+  if (run_stage(e, s, G_E2 + b, s->sE, [&]() -> int {
+        if (dio_stonemask_run(e, s->dio, s->wave_win[g], s->sE)) return -1;
+        const int n_enc = s->Lw / s->hop;
+        e->launches += 13;
+        return spectral_analysis_run(e, s->wave_win[g], s->Lw, c.fs, c.frame_period_ms, dio_plan_f0(s->dio), n_enc, c.fft_length, c.order,
+                                     s->enc_sp[b], s->enc_ap[b], s->enc_mc[b], s->enc_f0[b], s->enc_voiced[b], s->sE);
+      })) return -1;
   RYK_CUDA(cudaEventRecord(s->ev_enc[r], s->sE));
-  e->launches += 15;
 
-  // ================= stream C: stage 1 + stage 2 =================
+  // ================= stream C: stage 1 (+ f0 map, mc2sp) =================
   RYK_CUDA(cudaStreamWaitEvent(s->sC, s->ev_enc[r], 0));
-  if (slide<float>(s->cw_f0[f], s->enc_f0[b] + pe, s->cw_f0[g], s->Tw, s->n_feat, 1, s->sC)) return -1;
-  if (slide<float>(s->cw_ap[f], s->enc_ap[b] + (size_t)pe * s->nb, s->cw_ap[g], s->Tw, s->n_feat, s->nb, s->sC)) return -1;
-  if (slide<float>(s->cw_mc[f], s->enc_mc[b] + (size_t)pe * s->C, s->cw_mc[g], s->Tw, s->n_feat, s->C, s->sC)) return -1;
-  if (slide<uint8_t>(s->cw_voiced[f], s->enc_voiced[b] + pe, s->cw_voiced[g], s->Tw, s->n_feat, 1, s->sC)) return -1;
-  RYK_CUDA(cudaEventRecord(s->ev_cslide[r], s->sC));
-  if (k >= 2) RYK_CUDA(cudaStreamWaitEvent(s->sC, s->ev_dslide[(k - 2) % kRing], 0));   // cv_*[b] consumed by decode k-2
-  RYK_CUDA(cudaEventSynchronize(s->ev_count[r]));                                        // effective-frame count of THIS step
-  const int t_eff = s->h_count[r][0], tp1 = s->h_count[r][1];
-  const float* d_y = nullptr;
-  if (t_eff > 0) {      // voice_changer.py:32-35: stage 1 is skipped when no frame is effective
-    UNetPlan* p1 = nullptr;
-    if (unet_get_plan(e, e->stage1, 1, 1, tp1, e->precision, &p1)) return -1;
-    if (stage1_prologue_run(e, s->cw_mc[g], s->d_index[b], s->d_count[b], s->C, (float*)p1->d_in, tp1, s->sC)) return -1;
-    if (unet_forward(e, p1, s->sC)) return -1;
-    d_y = (const float*)p1->d_out;
+  if (k >= 2) {
+    RYK_CUDA(cudaStreamWaitEvent(s->sC, s->ev_dslide[(k - 2) % kRing], 0));   // cv_{f0,ap,voiced}_out[b] consumed by decode k-2
+    RYK_CUDA(cudaStreamWaitEvent(s->sC, s->ev_conv[(k - 2) % kRing], 0));     // cv_sp_mid[b] consumed by stage 2 of k-2
   }
-  if (stage1_epilogue_run(e, d_y, s->d_index[b], s->d_mask[b], s->d_count[b], s->Tw, s->C, s->cw_f0[g], s->cw_ap[g], s->cw_voiced[g], s->nb,
-                          kSilentMc0, s->cv_mc_out[b], s->cv_f0_out[b], s->cv_ap_out[b], s->cv_voiced_out[b], s->sC)) return -1;
-  if (mc2sp_run(e, s->cv_mc_out[b], s->Tw, c.order, c.fft_length, 1e-16, s->cv_sp_mid, nullptr, s->sC)) return -1;
+  RYK_CUDA(cudaEventSynchronize(s->ev_count[r]));                              // effective-frame count of THIS step
+  const int t_eff = s->h_count[r][0], tp1 = s->h_count[r][1];
+  RYK_CHECK(tp1 / 128 < 16, "window too long for the stage-1 graph table");
+  if (run_stage(e, s, G_S1 + 2 * (tp1 / 128) + b, s->sC, [&]() -> int {
+        SlideBatch sb; sb.n = 0;
+        slide_add<float>(sb, s->cw_f0[f], s->enc_f0[b] + pe, s->cw_f0[g], s->Tw, s->n_feat, 1);
+        slide_add<float>(sb, s->cw_ap[f], s->enc_ap[b] + (size_t)pe * s->nb, s->cw_ap[g], s->Tw, s->n_feat, s->nb);
+        slide_add<float>(sb, s->cw_mc[f], s->enc_mc[b] + (size_t)pe * s->C, s->cw_mc[g], s->Tw, s->n_feat, s->C);
+        slide_add<uint8_t>(sb, s->cw_voiced[f], s->enc_voiced[b] + pe, s->cw_voiced[g], s->Tw, s->n_feat, 1);
+        if (slide_batch(sb, s->sC)) return -1;
+        e->launches += 1;
+        const float* d_y = nullptr;
+        if (t_eff > 0) {      // voice_changer.py:32-35: stage 1 is skipped when no frame is effective
+          UNetPlan* p1 = nullptr;
+          if (unet_get_plan(e, e->stage1, 1, 1, tp1, e->precision, &p1)) return -1;
+          if (stage1_prologue_run(e, s->cw_mc[g], s->d_index[b], s->d_count[b], s->C, (float*)p1->d_in, tp1, s->sC)) return -1;
+          if (unet_forward(e, p1, s->sC)) return -1;
+          d_y = (const float*)p1->d_out;
+        }
+        if (stage1_epilogue_run(e, d_y, s->d_index[b], s->d_mask[b], s->d_count[b], s->Tw, s->C, s->cw_f0[g], s->cw_ap[g], s->cw_voiced[g], s->nb,
+                                kSilentMc0, s->cv_mc_out[b], s->cv_f0_out[b], s->cv_ap_out[b], s->cv_voiced_out[b], s->sC)) return -1;
+        return mc2sp_run(e, s->cv_mc_out[b], s->Tw, c.order, c.fft_length, 1e-16, s->cv_sp_mid[b], nullptr, s->sC);
+      })) return -1;
+  // NB: enc_*[b] may be overwritten by encode k+2 once this stage's slides ran; the stage-1 graph is short, so the
+  // guard event is simply the end of the stage.
+  RYK_CUDA(cudaEventRecord(s->ev_cslide[r], s->sC));
+  RYK_CUDA(cudaEventRecord(s->ev_s1[r], s->sC));
+
+  // ================= stream C2: stage 2 =================
+  RYK_CUDA(cudaStreamWaitEvent(s->sC2, s->ev_s1[r], 0));
+  if (k >= 2) RYK_CUDA(cudaStreamWaitEvent(s->sC2, s->ev_dslide[(k - 2) % kRing], 0));  // cv_sp_out[b] consumed by decode k-2
   const int Tp = s->Tw + (128 - s->Tw % 128);
   UNetPlan* p2 = nullptr;
   if (unet_get_plan(e, e->stage2, 1, Tp, 512, e->precision, &p2)) return -1;
-  if (sr_prologue_run(e, s->cv_sp_mid, s->Tw, Tp, s->nb, (float*)p2->d_in, s->sC)) return -1;
-  if (unet_forward(e, p2, s->sC)) return -1;
-  if (sr_epilogue_run(e, (const float*)p2->d_out, s->Tw, s->nb, s->cv_sp_out[b], s->sC)) return -1;
-  RYK_CUDA(cudaEventRecord(s->ev_conv[r], s->sC));
-  e->launches += 4;
+  if (run_stage(e, s, G_S2A + b, s->sC2, [&]() -> int {
+        if (sr_prologue_run(e, s->cv_sp_mid[b], s->Tw, Tp, s->nb, (float*)p2->d_in, s->sC2)) return -1;
+        return unet_forward(e, p2, s->sC2, 0, 0);
+      })) return -1;
+  cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+  if (was_profiling) { RYK_CUDA(cudaEventCreate(&pe0)); RYK_CUDA(cudaEventCreate(&pe1)); RYK_CUDA(cudaEventRecord(pe0, s->sC2)); }
+  if (run_stage(e, s, G_S2B + b, s->sC2, [&]() -> int { return unet_forward(e, p2, s->sC2, 1, 14); })) return -1;
+  if (was_profiling) { RYK_CUDA(cudaEventRecord(pe1, s->sC2)); e->prof_events.emplace_back(pe0, pe1); }
+  if (run_stage(e, s, G_S2C + b, s->sC2, [&]() -> int {
+        if (unet_forward(e, p2, s->sC2, 15, 15)) return -1;
+        return sr_epilogue_run(e, (const float*)p2->d_out, s->Tw, s->nb, s->cv_sp_out[b], s->sC2);
+      })) return -1;
+  RYK_CUDA(cudaEventRecord(s->ev_conv[r], s->sC2));
 
   // ================= stream D: realtime synthesizer =================
   RYK_CUDA(cudaStreamWaitEvent(s->sD, s->ev_conv[r], 0));
-  if (slide<float>(s->dw_f0[f], s->cv_f0_out[b] + pc, s->dw_f0[g], s->Td, s->n_feat, 1, s->sD)) return -1;
-  if (slide<float>(s->dw_ap[f], s->cv_ap_out[b] + (size_t)pc * s->nb, s->dw_ap[g], s->Td, s->n_feat, s->nb, s->sD)) return -1;
-  if (slide<float>(s->dw_sp[f], s->cv_sp_out[b] + (size_t)pc * s->nb, s->dw_sp[g], s->Td, s->n_feat, s->nb, s->sD)) return -1;
+  if (synth_host_advance(e, s->synth, s->Td, s->sD)) return -1;
+  const int max_blocks = s->max_blocks;
+  if (run_stage(e, s, G_D + b, s->sD, [&]() -> int {
+        SlideBatch sb; sb.n = 0;
+        slide_add<float>(sb, s->dw_f0[f], s->cv_f0_out[b] + pc, s->dw_f0[g], s->Td, s->n_feat, 1);
+        slide_add<float>(sb, s->dw_ap[f], s->cv_ap_out[b] + (size_t)pc * s->nb, s->dw_ap[g], s->Td, s->n_feat, s->nb);
+        slide_add<float>(sb, s->dw_sp[f], s->cv_sp_out[b] + (size_t)pc * s->nb, s->dw_sp[g], s->Td, s->n_feat, s->nb);
+        if (slide_batch(sb, s->sD)) return -1;
+        k_f32_to_f64<<<(s->Td + 127) / 128, 128, 0, s->sD>>>(s->dw_f0[g], s->dec_f0_f64, s->Td);
+        if (synth_add_kernel(e, s->synth, s->dec_f0_f64, s->Td, s->dw_sp[g], s->dw_ap[g], s->sD)) return -1;
+        if (synth_drain_async(e, s->synth, s->d_out_fixed[b], max_blocks, s->sD)) return -1;
+        k_scrub<<<8, 256, 0, s->sD>>>(s->d_out_fixed[b], s->synth->dev.state, c.vocoder_buffer_size, max_blocks * c.vocoder_buffer_size, s->d_n_fixed[b]);
+        e->launches += 3;
+        RYK_CUDA(cudaGetLastError());
+        return 0;
+      })) return -1;
+  // the decode graph both consumes cv_*[b] and produces the output: one event guards both
   RYK_CUDA(cudaEventRecord(s->ev_dslide[r], s->sD));
-  k_f32_to_f64<<<(s->Td + 127) / 128, 128, 0, s->sD>>>(s->dw_f0[g], s->dec_f0_f64, s->Td);
-  if (synth_add_async(e, s->synth, s->dec_f0_f64, s->Td, s->dw_sp[g], s->dw_ap[g], s->sD)) return -1;
-  int max_blocks = out_capacity / c.vocoder_buffer_size;
-  if (max_blocks > s->max_blocks) max_blocks = s->max_blocks;
-  RYK_CHECK(max_blocks > 0, "output capacity is smaller than one synthesizer block");
-  if (synth_drain_async(e, s->synth, d_out, max_blocks, s->sD)) return -1;
-  k_scrub<<<8, 256, 0, s->sD>>>(d_out, s->synth->dev.state, c.vocoder_buffer_size, max_blocks * c.vocoder_buffer_size, d_n_out);
-  e->launches += 5;
-  RYK_CUDA(cudaGetLastError());
-  // ev_dec[r] is recorded by the caller after any device->host copies it appends to stream D
+  e->profile = was_profiling;
+  // ev_dec[r] is recorded by the caller after the copies it appends to stream D
   s->step++;
   return 0;
 }
@@ -230,7 +336,7 @@ int ryk_session_create(ryk_engine* h, const ryk_session_config* cfg, int* sessio
   RYK_CHECK(e->stage1 && e->stage2, "load both models before creating a session");
   Session* s = new Session();
   memset(s->ev_count, 0, sizeof(s->ev_count)); memset(s->ev_enc, 0, sizeof(s->ev_enc)); memset(s->ev_cslide, 0, sizeof(s->ev_cslide));
-  memset(s->ev_conv, 0, sizeof(s->ev_conv)); memset(s->ev_dslide, 0, sizeof(s->ev_dslide)); memset(s->ev_dec, 0, sizeof(s->ev_dec));
+  memset(s->ev_s1, 0, sizeof(s->ev_s1)); memset(s->ev_conv, 0, sizeof(s->ev_conv)); memset(s->ev_dslide, 0, sizeof(s->ev_dslide)); memset(s->ev_dec, 0, sizeof(s->ev_dec));
   s->cfg = *cfg;
   s->hop = (int)(cfg->fs * cfg->frame_period_ms / 1000.0);
   s->rate = (int)lround(1000.0 / cfg->frame_period_ms);
@@ -251,9 +357,10 @@ int ryk_session_create(ryk_engine* h, const ryk_session_config* cfg, int* sessio
   if (sptk_prepare(e, cfg->order, cfg->alpha, cfg->fft_length)) return -1;
   RYK_CUDA(cudaStreamCreateWithFlags(&s->sE, cudaStreamNonBlocking));
   RYK_CUDA(cudaStreamCreateWithFlags(&s->sC, cudaStreamNonBlocking));
+  RYK_CUDA(cudaStreamCreateWithFlags(&s->sC2, cudaStreamNonBlocking));
   RYK_CUDA(cudaStreamCreateWithFlags(&s->sD, cudaStreamNonBlocking));
   for (int i = 0; i < kRing; ++i) {
-    cudaEvent_t* evs[] = {&s->ev_count[i], &s->ev_enc[i], &s->ev_cslide[i], &s->ev_conv[i], &s->ev_dslide[i], &s->ev_dec[i]};
+    cudaEvent_t* evs[] = {&s->ev_count[i], &s->ev_enc[i], &s->ev_cslide[i], &s->ev_s1[i], &s->ev_conv[i], &s->ev_dslide[i], &s->ev_dec[i]};
     for (cudaEvent_t* ev : evs) RYK_CUDA(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
   }
   auto A = [&](void** p, size_t bytes) -> int { RYK_CUDA(cudaMalloc(p, bytes ? bytes : 16)); RYK_CUDA(cudaMemset(*p, 0, bytes ? bytes : 16)); s->allocs.push_back(*p); return 0; };
@@ -284,12 +391,18 @@ int ryk_session_create(ryk_engine* h, const ryk_session_config* cfg, int* sessio
     if (A((void**)&s->cv_ap_out[i], sizeof(float) * (size_t)s->Tw * s->nb)) return -1;
     if (A((void**)&s->cv_sp_out[i], sizeof(float) * (size_t)s->Tw * s->nb)) return -1;
     if (A((void**)&s->cv_voiced_out[i], (size_t)s->Tw)) return -1;
+    if (A((void**)&s->cv_sp_mid[i], sizeof(float) * (size_t)s->Tw * s->nb)) return -1;
   }
   if (A((void**)&s->d_mse, sizeof(double) * s->Tw)) return -1;
-  if (A((void**)&s->cv_sp_mid, sizeof(float) * (size_t)s->Tw * s->nb)) return -1;
   if (A((void**)&s->dec_f0_f64, sizeof(double) * s->Td)) return -1;
+  if (A((void**)&s->d_chunk_fixed, sizeof(float) * s->n_wave)) return -1;
+  { const char* ng = getenv("RYK_NO_GRAPH"); s->use_graphs = !(ng && atoi(ng) != 0); }
   s->max_blocks = (s->Td * s->hop) / cfg->vocoder_buffer_size + 4;
   const size_t out_samples = (size_t)s->max_blocks * cfg->vocoder_buffer_size;
+  for (int i = 0; i < 2; ++i) {
+    if (A((void**)&s->d_out_fixed[i], sizeof(double) * out_samples)) return -1;
+    if (A((void**)&s->d_n_fixed[i], sizeof(int))) return -1;
+  }
   for (int i = 0; i < kRing; ++i) {
     if (A((void**)&s->d_chunk[i], sizeof(float) * s->n_wave)) return -1;
     if (A((void**)&s->d_out[i], sizeof(double) * out_samples)) return -1;
@@ -336,9 +449,10 @@ int ryk_session_submit(ryk_engine* h, int id, const float* wave, int n, long lon
   memcpy(s->h_in[r], wave, sizeof(float) * n);
   RYK_CUDA(cudaMemcpyAsync(s->d_chunk[r], s->h_in[r], sizeof(float) * n, cudaMemcpyHostToDevice, s->sE));
   const int cap = s->max_blocks * s->cfg.vocoder_buffer_size;
-  if (session_enqueue(e, s, s->d_chunk[r], s->d_out[r], cap, s->d_n_out[r])) return -1;
-  RYK_CUDA(cudaMemcpyAsync(s->h_n[r], s->d_n_out[r], sizeof(int), cudaMemcpyDeviceToHost, s->sD));
-  RYK_CUDA(cudaMemcpyAsync(s->h_out[r], s->d_out[r], sizeof(double) * (size_t)cap, cudaMemcpyDeviceToHost, s->sD));
+  const int b = (int)(k & 1);
+  if (session_enqueue(e, s, s->d_chunk[r])) return -1;
+  RYK_CUDA(cudaMemcpyAsync(s->h_n[r], s->d_n_fixed[b], sizeof(int), cudaMemcpyDeviceToHost, s->sD));
+  RYK_CUDA(cudaMemcpyAsync(s->h_out[r], s->d_out_fixed[b], sizeof(double) * (size_t)cap, cudaMemcpyDeviceToHost, s->sD));
   RYK_CUDA(cudaEventRecord(s->ev_dec[r], s->sD));
   if (ticket) *ticket = k;
   return 0;
@@ -374,8 +488,12 @@ int ryk_session_push_device(ryk_engine* h, int id, const float* wave_dev, int n,
   Session* s = get_session(e, id);
   RYK_CHECK(s != nullptr, "no such session");
   RYK_CHECK(n == s->n_wave, "chunk length must be round(fs * buffer_time)");
-  const int r = (int)(s->step % kRing);
-  if (session_enqueue(e, s, wave_dev, out_dev, out_capacity, n_out_dev)) return -1;
+  const int r = (int)(s->step % kRing), b = (int)(s->step & 1);
+  const int cap = s->max_blocks * s->cfg.vocoder_buffer_size;
+  RYK_CHECK(out_capacity >= cap, "out_capacity must hold (frames * hop / block + 4) synthesizer blocks");
+  if (session_enqueue(e, s, wave_dev)) return -1;
+  RYK_CUDA(cudaMemcpyAsync(out_dev, s->d_out_fixed[b], sizeof(double) * (size_t)cap, cudaMemcpyDeviceToDevice, s->sD));
+  RYK_CUDA(cudaMemcpyAsync(n_out_dev, s->d_n_fixed[b], sizeof(int), cudaMemcpyDeviceToDevice, s->sD));
   RYK_CUDA(cudaEventRecord(s->ev_dec[r], s->sD));
   s->collected = s->step;         // device-resident steps are not collected through the host API
   return 0;

@@ -46,6 +46,8 @@ struct Synth {
 
 int synth_create(Engine* e, int fs, double frame_period_ms, int fft_size, int buffer_size, int ring_frames, Synth** out);
 void synth_destroy(Synth* s);
+int synth_host_advance(Engine* e, Synth* s, int n, cudaStream_t st);
+int synth_add_kernel(Engine* e, Synth* s, const double* d_f0, int n, const float* d_sp, const float* d_ap, cudaStream_t st);
 int synth_add_async(Engine* e, Synth* s, const double* d_f0, int n, const float* d_sp, const float* d_ap, cudaStream_t st);
 int synth_drain_async(Engine* e, Synth* s, double* d_out, int max_blocks, cudaStream_t st);
 

@@ -463,11 +463,11 @@ void synth_destroy(Synth* s) {
 }
 
 // Stream-ordered: append n frames (device pointers). Also tops up the noise ring to the new end sample.
-int synth_add_async(Engine* e, Synth* s, const double* d_f0, int n, const float* d_sp, const float* d_ap, cudaStream_t st) {
+// Host-side bookkeeping of an AddParameters call (frame counter) + the rare bulk noise top-up; never captured in a graph.
+int synth_host_advance(Engine* e, Synth* s, int n, cudaStream_t st) {
   SynthDev& D = s->dev;
   RYK_CHECK((long long)n * D.frame_period * D.fs + 2 < D.max_samples_per_add, "too many frames in one AddParameters call");
   static_assert((1 << 17) / 256 <= 1024, "block totals must fit the scan scratch");
-  k_synth_add<<<1, 1024, 0, st>>>(D, d_f0, n, d_sp, d_ap);
   s->host_cum_frames += n;
   long long need = (long long)ceil((double)(s->host_cum_frames < 0 ? 0 : s->host_cum_frames) * D.frame_period * D.fs) + D.fft_size + 2;
   if (need > s->host_noise_generated) {
@@ -478,10 +478,23 @@ int synth_add_async(Engine* e, Synth* s, const double* d_f0, int n, const float*
     s->host_noise_generated += (long long)tiles * kNoiseTile;
     s->host_noise_slot ^= 1;
     e->launches++;
+    RYK_CUDA(cudaGetLastError());
   }
+  return 0;
+}
+
+// The device side of AddParameters (graph-capturable: fixed arguments, no host state).
+int synth_add_kernel(Engine* e, Synth* s, const double* d_f0, int n, const float* d_sp, const float* d_ap, cudaStream_t st) {
+  k_synth_add<<<1, 1024, 0, st>>>(s->dev, d_f0, n, d_sp, d_ap);
   e->launches++;
   RYK_CUDA(cudaGetLastError());
   return 0;
+}
+
+// Stream-ordered: append n frames (device pointers). Also tops up the noise ring to the new end sample.
+int synth_add_async(Engine* e, Synth* s, const double* d_f0, int n, const float* d_sp, const float* d_ap, cudaStream_t st) {
+  if (synth_host_advance(e, s, n, st)) return -1;
+  return synth_add_kernel(e, s, d_f0, n, d_sp, d_ap, st);
 }
 
 // Stream-ordered: emit up to max_blocks blocks into d_out (doubles); the count lands in state->blocks_out.

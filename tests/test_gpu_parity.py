@@ -217,14 +217,16 @@ def test_device_session_matches_oracle_stream(engine, small_models):
     from realtime_yukarin_b200.engine import SessionConfig
     ac, sr, f0c = _load(engine, small_models)
     p1, p2 = onets.load_npz(small_models['stage1_model_path']), onets.load_npz(small_models['stage2_model_path'])
-    for T, extra in ((0.3, (0.0, 0.5, 0.0)), (0.1, (0.1, 0.2, 0.0))):
+    # BASELINE.json configs: [1] 0.3 s / (0,0.5,0); [2] buffer sweep 0.1 / 0.3 / 1.0 s with overlaps; [0] check.py's 1 s chunks with (0,1,0)
+    for T, extra in ((0.3, (0.0, 0.5, 0.0)), (0.1, (0.1, 0.2, 0.0)), (0.1, (0.0, 0.5, 0.0)), (1.0, (0.0, 0.5, 0.0)), (1.0, (0.0, 1.0, 0.0)),
+                     (0.3, (0.1, 0.5, 0.1))):
         engine.set_precision('fp32')
         cfg = SessionConfig(fs=24000, frame_period_ms=5.0, f0_floor=71.0, f0_ceil=800.0, fft_length=1024, order=8, alpha=0.466,
                             buffer_time=T, encode_extra_time=extra[0], convert_extra_time=extra[1], decode_extra_time=extra[2],
                             threshold_db=60.0, vocoder_buffer_size=1024)
         sid = engine.session_create(cfg)
         orc = opipe.StreamOracle(CFG, p1, p2, f0c.stats(), buffer_time=T, extra=extra, backend='torch')
-        x = _speech(2.4, 33)
+        x = _speech(2.4 if T < 1.0 else 5.0, 33)
         n = round(T * 24000)
         outs, refs = [], []
         for k in range(len(x) // n):
