@@ -158,38 +158,48 @@ static int conv_direct_generic(const ConvLayer& L, cudaStream_t st) {
 // (25 MB written / 50 MB read at 384x512); the generic 64x64 tile above would waste 16-64x of its math on
 // them, so they get dedicated kernels: coalesced 16-byte accesses, weights in shared memory.
 
-// Cin = 1, fp32 input -> Cout (multiple of 8, <= 64) channels. One thread = one pixel x 8 output channels.
+// Cin = 1, fp32 input -> Cout (multiple of 8, <= 64) channels.  Block = 32 pixels (x) x Cout/8 channel groups, walking
+// kRows rows of the image with a 3-row register window: every input value is loaded once per thread column, every
+// store is a full 16-byte piece of a 128-byte pixel (4 pixels per warp instruction), no integer divisions.
 template <typename TOut>
 __global__ void __launch_bounds__(256) k_conv3x3_cin1(const float* __restrict__ in, const float* __restrict__ w /*[9][1][Cout]*/,
                                                      const float* __restrict__ scale, const float* __restrict__ shift, int act,
                                                      int B, int H, int W, int Cout, TOut* __restrict__ out) {
-  __shared__ float ws[9 * 64], sc[64], sh[64];
-  for (int i = threadIdx.x; i < 9 * Cout; i += blockDim.x) ws[i] = w[i];
-  for (int i = threadIdx.x; i < Cout; i += blockDim.x) { sc[i] = scale[i]; sh[i] = shift[i]; }
-  __syncthreads();
-  const int groups = Cout / 8;
-  const long long total = (long long)B * H * W * groups;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    int g = idx % groups; long long pix = idx / groups;
-    int x = pix % W; long long r = pix / W; int y = r % H; int b = r / H;
-    float v[9];
+  constexpr int kRows = 8;
+  const int groups = Cout >> 3;                   // blockDim.x = 32 * groups  (<= 256)
+  const int g = threadIdx.x % groups, xl = threadIdx.x / groups;
+  const int x = blockIdx.x * 32 + xl;
+  const int y0 = blockIdx.y * kRows;
+  const int b = blockIdx.z;
+  float wr[9][8], sc[8], sh[8];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      int iy = y + t / 3 - 1, ix = x + t % 3 - 1;
-      v[t] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(in + ((long long)b * H + iy) * W + ix) : 0.f;
-    }
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wr[t][j] = __ldg(w + t * Cout + g * 8 + j);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = __ldg(scale + g * 8 + j); sh[j] = __ldg(shift + g * 8 + j); }
+  if (x >= W) return;
+  const float* base = in + (size_t)b * H * W;
+  auto ld = [&](int yy, int xx) -> float { return (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(base + (size_t)yy * W + xx) : 0.f; };
+  float r0[3], r1[3], r2[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) { r0[d] = ld(y0 - 1, x + d - 1); r1[d] = ld(y0, x + d - 1); }
+  for (int yy = 0; yy < kRows; ++yy) {
+    const int y = y0 + yy;
+    if (y >= H) break;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) r2[d] = ld(y + 1, x + d - 1);
     float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      int n = g * 8 + j;
       float a = 0.f;
 #pragma unroll
-      for (int t = 0; t < 9; ++t) a = fmaf(v[t], ws[t * Cout + n], a);
-      a = a * sc[n] + sh[n];
+      for (int d = 0; d < 3; ++d) { a = fmaf(r0[d], wr[d][j], a); a = fmaf(r1[d], wr[3 + d][j], a); a = fmaf(r2[d], wr[6 + d][j], a); }
+      a = a * sc[j] + sh[j];
       if (act == ACT_LEAKY) a = a > 0.f ? a : 0.2f * a; else if (act == ACT_RELU) a = fmaxf(a, 0.f);
       o[j] = a;
     }
-    TOut* dst = out + pix * Cout + g * 8;
+    TOut* dst = out + (((size_t)b * H + y) * W + x) * Cout + g * 8;
     if constexpr (sizeof(TOut) == 2) {
       __half2 h0 = __floats2half2_rn(o[0], o[1]), h1 = __floats2half2_rn(o[2], o[3]), h2 = __floats2half2_rn(o[4], o[5]), h3 = __floats2half2_rn(o[6], o[7]);
       *reinterpret_cast<uint4*>(dst) = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
@@ -198,47 +208,69 @@ __global__ void __launch_bounds__(256) k_conv3x3_cin1(const float* __restrict__ 
       *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
       *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
     }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { r0[d] = r1[d]; r1[d] = r2[d]; }
   }
 }
 
-// Cout = 1 from two fp16 sources of 64 channels each (skip concat) -> fp32. One warp = one pixel at a time:
-// lanes 0-15 read 4 channels each of source 0, lanes 16-31 of source 1 (8-byte loads, 256 B per tap), warp-shuffle sum.
+// Cout = 1 from two fp16 sources of 64 channels each (skip concat) -> fp32.  One warp = 8 consecutive pixels of a row:
+// lanes 0-15 own 4 channels each of source 0, lanes 16-31 of source 1; the 3 x 10 input pixels are loaded once
+// (30 independent 8-byte loads in flight per lane) and feed all 8 outputs, which are then reduced across the warp.
 __global__ void __launch_bounds__(256) k_conv3x3_cout1_h(const __half* __restrict__ in0, const __half* __restrict__ in1,
                                                         const float* __restrict__ w /*[9][128][1]*/, float scale, float shift, int act,
                                                         int B, int H, int W, float* __restrict__ out) {
-  __shared__ float ws[9 * 128];
-  for (int i = threadIdx.x; i < 9 * 128; i += blockDim.x) ws[i] = w[i];
-  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // block tile: 4 rows x 16 columns of pixels, 8 warps x 8 pixels
-  const int tiles_x = (W + 15) / 16, tiles_y = (H + 3) / 4;
-  int t = blockIdx.x;
-  const int tx = t % tiles_x; t /= tiles_x;
-  const int ty = t % tiles_y; const int b = t / tiles_y;
+  const int x0 = (blockIdx.x * 8 + warp) * 8;          // 8 warps x 8 pixels = 64 pixels of a row per block
+  const int y = blockIdx.y, b = blockIdx.z;
+  if (x0 >= W) return;
   const __half* src = lane < 16 ? in0 : in1;
   const int c = (lane & 15) * 4;
-  const float* wl = ws + (lane < 16 ? 0 : 64) + c;
-  for (int q = 0; q < 8; ++q) {
-    int pl = warp * 8 + q;
-    int y = ty * 4 + pl / 16, x = tx * 16 + pl % 16;
-    if (y >= H || x >= W) continue;
-    float a = 0.f;
+  float wt[9][4];
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      int iy = y + tap / 3 - 1, ix = x + tap % 3 - 1;
-      if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
-      uint2 raw = __ldg(reinterpret_cast<const uint2*>(src + (((long long)b * H + iy) * W + ix) * 64 + c));
-      __half2 h01 = *reinterpret_cast<__half2*>(&raw.x), h23 = *reinterpret_cast<__half2*>(&raw.y);
-      float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-      const float* wt = wl + tap * 128;
-      a = fmaf(f01.x, wt[0], a); a = fmaf(f01.y, wt[1], a); a = fmaf(f23.x, wt[2], a); a = fmaf(f23.y, wt[3], a);
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) wt[t][j] = __ldg(w + t * 128 + (lane < 16 ? 0 : 64) + c + j);
+  float acc[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+    const int iy = y + dy - 1;
+    if (iy < 0 || iy >= H) continue;
+    uint2 raw[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      const int ix = x0 + i - 1;
+      raw[i] = (ix >= 0 && ix < W) ? __ldg(reinterpret_cast<const uint2*>(src + (((size_t)b * H + iy) * W + ix) * 64 + c)) : make_uint2(0u, 0u);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == 0) {
+    for (int i = 0; i < 10; ++i) {
+      const float2 f01 = __half22float2(*reinterpret_cast<__half2*>(&raw[i].x)), f23 = __half22float2(*reinterpret_cast<__half2*>(&raw[i].y));
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int q = i - dx;                    // output pixel fed by input column i through tap dx
+        if (q < 0 || q >= 8) continue;
+        const float* wv = wt[dy * 3 + dx];
+        acc[q] = fmaf(f01.x, wv[0], acc[q]); acc[q] = fmaf(f01.y, wv[1], acc[q]);
+        acc[q] = fmaf(f23.x, wv[2], acc[q]); acc[q] = fmaf(f23.y, wv[3], acc[q]);
+      }
+    }
+  }
+  // warp reduction of 8 values: fold pairs so that lane l ends up owning pixel (l & 7)
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+  }
+  if (lane < 8) {
+    float a = acc[0];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) a = lane == q ? acc[q] : a;
+    const int x = x0 + lane;
+    if (x < W) {
       a = a * scale + shift;
       if (act == ACT_LEAKY) a = a > 0.f ? a : 0.2f * a; else if (act == ACT_RELU) a = fmaxf(a, 0.f);
-      out[((long long)b * H + y) * W + x] = a;
+      out[((size_t)b * H + y) * W + x] = a;
     }
   }
 }
@@ -249,17 +281,17 @@ int conv_direct_run(const ConvLayer& L, cudaStream_t st) {
   // dedicated kernels for the stage-2 edge layers
   if (!L.transposed && L.KH == 3 && L.KW == 3 && L.SH == 1 && L.SW == 1 && L.PH == 1 && L.PW == 1) {
     if (L.C0 == 1 && L.C1 == 0 && L.in_dtype == DT_F32 && L.Cout % 8 == 0 && L.Cout <= 64) {
-      long long total = (long long)L.B * L.Hin * L.Win * (L.Cout / 8);
-      int blocks = (int)((total + 255) / 256);
+      dim3 grid((L.Win + 31) / 32, (L.Hin + 7) / 8, L.B);
+      int threads = 32 * (L.Cout / 8);
       if (L.out_dtype == DT_F16)
-        k_conv3x3_cin1<__half><<<blocks, 256, 0, st>>>((const float*)L.in0, L.w_direct, L.scale, L.shift, L.act, L.B, L.Hin, L.Win, L.Cout, (__half*)L.out);
+        k_conv3x3_cin1<__half><<<grid, threads, 0, st>>>((const float*)L.in0, L.w_direct, L.scale, L.shift, L.act, L.B, L.Hin, L.Win, L.Cout, (__half*)L.out);
       else
-        k_conv3x3_cin1<float><<<blocks, 256, 0, st>>>((const float*)L.in0, L.w_direct, L.scale, L.shift, L.act, L.B, L.Hin, L.Win, L.Cout, (float*)L.out);
+        k_conv3x3_cin1<float><<<grid, threads, 0, st>>>((const float*)L.in0, L.w_direct, L.scale, L.shift, L.act, L.B, L.Hin, L.Win, L.Cout, (float*)L.out);
       RYK_CUDA(cudaGetLastError());
       return 0;
     }
     if (L.Cout == 1 && L.C0 == 64 && L.C1 == 64 && L.in_dtype == DT_F16 && L.out_dtype == DT_F32 && L.host_scale_valid) {
-      int blocks = L.B * ((L.Hin + 3) / 4) * ((L.Win + 15) / 16);
+      dim3 blocks((L.Win + 63) / 64, L.Hin, L.B);
       k_conv3x3_cout1_h<<<blocks, 256, 0, st>>>((const __half*)L.in0, (const __half*)L.in1, L.w_direct, L.host_scale, L.host_shift, L.act,
                                                 L.B, L.Hin, L.Win, (float*)L.out);
       RYK_CUDA(cudaGetLastError());

@@ -97,6 +97,7 @@ struct TcParams {
   __half* out;
   float* ws;                     // split-K workspace [ksplit][pixels][Cout] or nullptr
   size_t out_pixels;             // B * Hout * Wout
+  int debug;                     // RYK_TC_DEBUG bit 1 (perf experiments only): skip the output stores
 };
 
 template <int BLOCK_N, int kStages, int kMinBlocks>
@@ -251,6 +252,242 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
   }
 }
 
+// ------------------------------------------------------------------------------------ persistent variant
+// One CTA per SM loops over output tiles (tile = blockIdx.x + i * gridDim.x).  The smem ring keeps streaming across
+// tile boundaries and the accumulator is double-buffered in TMEM (2 x BLOCK_N columns), so the epilogue of tile i
+// (tcgen05.ld -> scale/shift/act -> FP16 stores) overlaps the TMA + MMA main loop of tile i + 1, and the per-tile
+// fixed costs (TMEM alloc, barrier init, tensor-map fetch, pipeline fill) are paid once per CTA.
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int BLOCK_N, int kStages, int MT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+k_conv_tc_persist(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO, const TcParams p,
+                  const int tiles_mn, const int n_tiles_n, const int total_tiles) {
+  // MT = pixel tiles (of 128) per CTA tile: MT = 2 makes a 256 x BLOCK_N CTA tile whose two halves share every B
+  // (weight) stage -- the k4 layers are bound by L2 -> shared-memory traffic (~10 TB/s), so bytes per FLOP matter.
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr uint32_t kAHalf = kBlockM * kBlockK * 2;
+  constexpr uint32_t kABytes = MT * kAHalf;
+  constexpr uint32_t kBBytes = BLOCK_N * kBlockK * 2;
+  constexpr int kAccStages = (2 * MT * BLOCK_N <= 512) ? 2 : 1;
+  constexpr uint32_t kTmemCols = kAccStages * MT * BLOCK_N;
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * kABytes;
+  // epilogue staging: BLOCK_N / 64 blocks of [128 pixels][64 channels] fp16 in the 128B-swizzled layout a TMA store reads
+  constexpr uint32_t kOutBytes = kBlockM * BLOCK_N * 2;
+  uint8_t* smem_out = smem_b + kStages * kBBytes;
+  uint64_t* full_bar = (uint64_t*)(smem_out + kOutBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;      // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;            // [2]
+  uint32_t* tmem_ptr_smem = (uint32_t*)(tempty_bar + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 128) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    if (p.chunks1 > 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
+  }
+  if (threadIdx.x == 160) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int chunks_per_tap = p.chunks0 + p.chunks1;
+  const int total_chunks = p.ntaps * chunks_per_tap;
+  const int super_mn = (tiles_mn + MT - 1) / MT;
+
+  // tile decode: t -> (first m-tile, n-tile, class, split); m fastest so that co-running CTAs share the same weight tiles in L2
+  auto decode = [&](int t, int& mt0, int& n0, int& cls, int& split) {
+    mt0 = (t % super_mn) * MT; t /= super_mn;
+    int nt = t % n_tiles_n; t /= n_tiles_n;
+    split = t % p.ksplit; cls = t / p.ksplit;
+    n0 = nt * BLOCK_N;
+  };
+  auto decode_m = [&](int mt, int& tw, int& th, int& b) {
+    tw = mt % p.tiles_w; mt /= p.tiles_w;
+    th = mt % p.tiles_h; b = mt / p.tiles_h;       // b >= B for the padding half of an odd tile count: TMA zero-fills, stores are masked
+  };
+
+  if (warp == 4 && lane == 0) {
+    // ===== TMA producer =====
+    int it = 0;                                    // global chunk counter across tiles -> stage / phase
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int mt0, n0, cls, split;
+      decode(t, mt0, n0, cls, split);
+      const int py = cls / p.classes_w, px = cls % p.classes_w;
+      const int kc_begin = split * p.chunks_per_split;
+      const int kc_end = min(total_chunks, kc_begin + p.chunks_per_split);
+      for (int kc = kc_begin; kc < kc_end; ++kc, ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        const int tap = kc / chunks_per_tap;
+        const int cc = kc - tap * chunks_per_tap;
+        const int ty = tap / p.taps_w, tx = tap - ty * p.taps_w;
+        mbar_expect_tx(&full_bar[s], kABytes + kBBytes);
+#pragma unroll
+        for (int h = 0; h < MT; ++h) {
+          int tw, th, b;
+          decode_m(mt0 + h, tw, th, b);
+          const int oy0 = th * p.tile_h, ox0 = tw * p.tile_w;
+          int ix, iy;
+          if (!p.transposed) { ix = ox0 * p.sw + tx - p.pw; iy = oy0 * p.sh + ty - p.ph; }
+          else { ix = p.sw == 2 ? ox0 + tx - 1 + px : ox0; iy = p.sh == 2 ? oy0 + ty - 1 + py : oy0; }
+          if (cc < p.chunks0) tma_load_4d(smem_a + s * kABytes + h * kAHalf, &tmA0, &full_bar[s], cc * kBlockK, ix, iy, b);
+          else tma_load_4d(smem_a + s * kABytes + h * kAHalf, &tmA1, &full_bar[s], (cc - p.chunks0) * kBlockK, ix, iy, b);
+        }
+        tma_load_2d(smem_b + s * kBBytes, &tmB, &full_bar[s], kc * kBlockK, cls * p.Cout + n0);
+      }
+    }
+  } else if (warp == 5 && lane == 0) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+    int it = 0, ti = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+      int mt0, n0, cls, split;
+      decode(t, mt0, n0, cls, split);
+      const int kc_begin = split * p.chunks_per_split;
+      const int kc_end = min(total_chunks, kc_begin + p.chunks_per_split);
+      const int as = ti % kAccStages;
+      const uint32_t aph = (ti / kAccStages) & 1;
+      mbar_wait(&tempty_bar[as], aph ^ 1);          // epilogue has drained this accumulator
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int kc = kc_begin; kc < kc_end; ++kc, ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t bdesc = make_sw128_desc(smem_u32(smem_b + s * kBBytes));
+#pragma unroll
+        for (int h = 0; h < MT; ++h) {
+          const uint64_t adesc = make_sw128_desc(smem_u32(smem_a + s * kABytes + h * kAHalf));
+          const uint32_t tmem_d = tmem_base + (uint32_t)((as * MT + h) * BLOCK_N);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            umma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc > kc_begin || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(&tfull_bar[as]);
+    }
+  } else if (warp < 4) {
+    // ===== epilogue =====
+    int ti = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+      int mt0, n0, cls, split;
+      decode(t, mt0, n0, cls, split);
+      const int py = cls / p.classes_w, px = cls % p.classes_w;
+      const int as = ti % kAccStages;
+      const uint32_t aph = (ti / kAccStages) & 1;
+      mbar_wait(&tfull_bar[as], aph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int row = warp * 32 + lane;
+#pragma unroll 1
+      for (int h = 0; h < MT; ++h) {
+        int tw, th, b;
+        decode_m(mt0 + h, tw, th, b);
+        const int oy0 = th * p.tile_h, ox0 = tw * p.tile_w;
+        const int hl = row / p.tile_w, wl = row - hl * p.tile_w;
+        const int my = oy0 + hl, mx = ox0 + wl;
+        const bool valid = (my < p.Hc) && (mx < p.Wc) && (b < p.B) && !(p.debug & 1);
+        int oy = my, ox = mx;
+        if (p.transposed) { oy = my * p.sh + py; ox = mx * p.sw + px; }
+        const size_t pix = ((size_t)(b * p.Hout + oy) * p.Wout + ox);
+        if (!p.ws) {
+          // the previous TMA store must have finished reading the staging buffer before it is overwritten
+          if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          uint32_t r[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((as * MT + h) * BLOCK_N + c0);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+              : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (h == MT - 1 && c0 + 32 >= BLOCK_N) {   // accumulator fully read: hand it back to the MMA warp before the stores
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+          }
+          const int n = n0 + c0;
+          if (p.ws) {
+            if (valid) {
+              float4* w = reinterpret_cast<float4*>(p.ws + ((size_t)split * p.out_pixels + pix) * p.Cout + n);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                w[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+            }
+          } else {
+            // scale/shift/activation -> FP16 -> swizzled staging tile (row = pixel, 8 x 16-byte chunks per 64-channel block)
+            uint8_t* blk = smem_out + (c0 >> 6) * (kBlockM * 128) + row * 128;
+            const int cbase = (c0 & 32) >> 3;          // first 16-byte chunk of this 32-channel half inside the block: 0 or 4
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float v0 = __uint_as_float(r[j + 2 * q]) * __ldg(p.scale + n + j + 2 * q) + __ldg(p.shift + n + j + 2 * q);
+                float v1 = __uint_as_float(r[j + 2 * q + 1]) * __ldg(p.scale + n + j + 2 * q + 1) + __ldg(p.shift + n + j + 2 * q + 1);
+                if (p.act == ACT_LEAKY) { v0 = v0 > 0.f ? v0 : 0.2f * v0; v1 = v1 > 0.f ? v1 : 0.2f * v1; }
+                else if (p.act == ACT_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+                __half2 h2 = __floats2half2_rn(v0, v1);
+                pk[q] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              const int chunk = cbase + (j >> 3);
+              *reinterpret_cast<uint4*>(blk + ((chunk ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+        }
+        if (!p.ws) {
+          // generic-proxy smem writes -> visible to the async proxy, then one thread hands the tile to the TMA unit:
+          // coalesced 128-byte rows, out-of-range pixels clipped by the tensor map (no masking needed)
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (threadIdx.x == 0 && !(p.debug & 1)) {
+            const int xs = p.transposed ? ox0 * p.sw + px : ox0;
+            const int ys = p.transposed ? oy0 * p.sh + py : oy0;
+#pragma unroll
+            for (int jb = 0; jb < BLOCK_N / 64; ++jb) {
+              asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                           ::"l"(&tmO), "r"(smem_u32(smem_out + jb * (kBlockM * 128))), "r"(n0 + jb * 64), "r"(xs), "r"(ys), "r"(b) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      }
+    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
 // split-K reduce + epilogue: out = act((sum over splits of ws[s]) * scale + shift) as fp16, 4 channels per thread
 __global__ void k_splitk_reduce(const float* __restrict__ ws, size_t total4, size_t slice_elems, int ksplit, int Cout,
                                 const float* __restrict__ scale, const float* __restrict__ shift, int act, __half* __restrict__ out) {
@@ -288,6 +525,10 @@ static int tc_variant() {
   return g_variant;
 }
 
+template <int BN, int ST, int MT> static constexpr size_t tcp_smem_bytes() {
+  return (size_t)ST * (MT * kBlockM * kBlockK * 2 + BN * kBlockK * 2) + (size_t)kBlockM * BN * 2 + (2 * ST + 4) * 8 + 16 + 1024;
+}
+
 int tc_init() {
   if (!g_encode) {
     void* fn = nullptr;
@@ -302,6 +543,12 @@ int tc_init() {
   RYK_CUDA(cudaFuncSetAttribute(k_conv_tc<64, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<64, 4>()));
   RYK_CUDA(cudaFuncSetAttribute(k_conv_tc<128, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<128, 3>()));
   RYK_CUDA(cudaFuncSetAttribute(k_conv_tc<256, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<256, 2>()));
+  RYK_CUDA(cudaFuncSetAttribute(k_conv_tc_persist<64, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcp_smem_bytes<64, 8, 1>()));
+  RYK_CUDA(cudaFuncSetAttribute(k_conv_tc_persist<128, 6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcp_smem_bytes<128, 6, 1>()));
+  RYK_CUDA(cudaFuncSetAttribute(k_conv_tc_persist<256, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcp_smem_bytes<256, 3, 1>()));
+  RYK_CUDA(cudaFuncSetAttribute(k_conv_tc_persist<64, 5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcp_smem_bytes<64, 5, 2>()));
+  RYK_CUDA(cudaFuncSetAttribute(k_conv_tc_persist<128, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcp_smem_bytes<128, 4, 2>()));
+  RYK_CUDA(cudaFuncSetAttribute(k_conv_tc_persist<256, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcp_smem_bytes<256, 2, 2>()));
   return 0;
 }
 
@@ -348,12 +595,15 @@ static void tc_geometry(const ConvLayer& L, int num_sms, int* tile_w, int* tile_
   int th = kBlockM / tw;
   int bn = L.Cout >= 256 ? 256 : (L.Cout >= 128 ? 128 : 64);
   if (tc_variant() == 1 && bn == 256) bn = 128;        // variant 1: N <= 128 tiles, 3 stages, 2 CTAs/SM
+  if (tc_variant() == 4 && bn == 256) bn = 128;        // variant 4: persistent with N <= 128
   int classes = L.transposed ? L.SH * L.SW : 1;
-  int tiles = L.B * ((Wc + tw - 1) / tw) * ((Hc + th - 1) / th) * (L.Cout / bn) * classes;
+  int tiles_mn_ = L.B * ((Wc + tw - 1) / tw) * ((Hc + th - 1) / th);
+  if (tc_variant() == 5) tiles_mn_ = (tiles_mn_ + 1) / 2;       // variant 5: 256-pixel CTA tiles
+  int tiles = tiles_mn_ * (L.Cout / bn) * classes;
   int ntaps = L.transposed ? (L.KH / L.SH) * (L.KW / L.SW) : L.KH * L.KW;
   int total_chunks = ntaps * (L.C0 + L.C1) / kBlockK;
   int ks = 1;
-  int slots = num_sms * (tc_variant() == 0 ? 1 : 2);
+  int slots = num_sms * ((tc_variant() == 0 || tc_variant() >= 3) ? 1 : 2);
   if (tiles < slots) {
     ks = slots / tiles;
     if (ks > total_chunks / 2) ks = total_chunks / 2;   // at least 2 chunks per split
@@ -383,6 +633,8 @@ int tc_layer_prepare(ConvLayer& L, int num_sms) {
   size_t K = (size_t)ntaps * (L.C0 + L.C1);
   size_t rows = (size_t)classes * L.Cout;
   if (make_weight_map(&L.tmB, L.w_tc, K, rows, L.block_n)) return -1;
+  // output map for the TMA-store epilogue: deconv classes write every other pixel (element strides = conv strides)
+  if (make_act_map(&L.tmO, L.out, L.Cout, L.Wout, L.Hout, L.B, L.tile_w, L.tile_h, L.transposed ? L.SW : 1, L.transposed ? L.SH : 1)) return -1;
   RYK_CHECK(L.ksplit == 1 || L.splitk_ws != nullptr, "split-K layer without a workspace");
   L.tc_ready = true;
   return 0;
@@ -407,10 +659,25 @@ int conv_tc_run(const ConvLayer& L, cudaStream_t st) {
   p.act = L.act; p.scale = L.scale; p.shift = L.shift; p.out = (__half*)L.out;
   p.ws = L.ksplit > 1 ? L.splitk_ws : nullptr;
   p.out_pixels = (size_t)L.B * L.Hout * L.Wout;
+  { static int dbg = -1; if (dbg < 0) { const char* v = getenv("RYK_TC_DEBUG"); dbg = v ? atoi(v) : 0; } p.debug = dbg; }
   size_t out_elems = (size_t)L.B * L.Hout * L.Wout * L.Cout;
   dim3 grid(L.B * p.tiles_w * p.tiles_h, L.Cout / L.block_n, classes * L.ksplit);
   const int variant = tc_variant();
-  if (variant == 0) {
+  if (variant >= 3) {
+    int num_sms = 148;
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, 0);
+    const int tiles_mn = L.B * p.tiles_w * p.tiles_h, n_tiles_n = L.Cout / L.block_n;
+    const int mt = variant == 5 ? 2 : 1;
+    const int total_tiles = ((tiles_mn + mt - 1) / mt) * n_tiles_n * classes * L.ksplit;
+    const int ctas = total_tiles < num_sms ? total_tiles : num_sms;
+    if (mt == 2) {
+      if (L.block_n == 256) k_conv_tc_persist<256, 2, 2><<<ctas, kTcThreads, tcp_smem_bytes<256, 2, 2>(), st>>>(L.tmA0, L.tmA1, L.tmB, L.tmO, p, tiles_mn, n_tiles_n, total_tiles);
+      else if (L.block_n == 128) k_conv_tc_persist<128, 4, 2><<<ctas, kTcThreads, tcp_smem_bytes<128, 4, 2>(), st>>>(L.tmA0, L.tmA1, L.tmB, L.tmO, p, tiles_mn, n_tiles_n, total_tiles);
+      else k_conv_tc_persist<64, 5, 2><<<ctas, kTcThreads, tcp_smem_bytes<64, 5, 2>(), st>>>(L.tmA0, L.tmA1, L.tmB, L.tmO, p, tiles_mn, n_tiles_n, total_tiles);
+    } else if (L.block_n == 256) k_conv_tc_persist<256, 3, 1><<<ctas, kTcThreads, tcp_smem_bytes<256, 3, 1>(), st>>>(L.tmA0, L.tmA1, L.tmB, L.tmO, p, tiles_mn, n_tiles_n, total_tiles);
+    else if (L.block_n == 128) k_conv_tc_persist<128, 6, 1><<<ctas, kTcThreads, tcp_smem_bytes<128, 6, 1>(), st>>>(L.tmA0, L.tmA1, L.tmB, L.tmO, p, tiles_mn, n_tiles_n, total_tiles);
+    else k_conv_tc_persist<64, 8, 1><<<ctas, kTcThreads, tcp_smem_bytes<64, 8, 1>(), st>>>(L.tmA0, L.tmA1, L.tmB, L.tmO, p, tiles_mn, n_tiles_n, total_tiles);
+  } else if (variant == 0) {
     if (L.block_n == 256) k_conv_tc<256, 4, 1><<<grid, kTcThreads, tc_smem_bytes<256, 4>(), st>>>(L.tmA0, L.tmA1, L.tmB, p);
     else if (L.block_n == 128) k_conv_tc<128, 6, 1><<<grid, kTcThreads, tc_smem_bytes<128, 6>(), st>>>(L.tmA0, L.tmA1, L.tmB, p);
     else k_conv_tc<64, 6, 1><<<grid, kTcThreads, tc_smem_bytes<64, 6>(), st>>>(L.tmA0, L.tmA1, L.tmB, p);

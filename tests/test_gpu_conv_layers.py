@@ -66,3 +66,34 @@ def test_conv_kernels(engine, case):
         err16 = np.abs(got16 - ref).max()
         print('tcgen05', case, 'max err', err16, 'ms', ms)
         assert err16 < 3e-2, err16
+
+
+EDGE_CASES = [
+    # the stage-2 edge layers as the fp16 plan runs them (mixed precision): B, H, W, Cin (1 -> 64) or (64 + 64 -> 1)
+    (1, 16, 32, 1, 64), (2, 37, 75, 1, 64), (1, 128, 512, 1, 64), (1, 5, 40, 1, 16),
+    (1, 16, 32, 128, 1), (2, 37, 75, 128, 1), (1, 128, 512, 128, 1), (1, 2, 9, 128, 1),
+]
+
+
+@pytest.mark.parametrize('case', EDGE_CASES)
+def test_edge_layer_kernels(engine, case):
+    """k_conv3x3_cin1 / k_conv3x3_cout1_h (conv_direct.cu) with ragged tile edges, against torch on fp16-rounded inputs."""
+    B, H, W, Cin, Cout = case
+    rng = np.random.default_rng(B * 1000 + H * 10 + W + Cin)
+    C0 = 1 if Cin == 1 else 64
+    C1 = Cin - C0
+    in0 = rng.standard_normal((B, H, W, C0)).astype(np.float32)
+    in1 = rng.standard_normal((B, H, W, C1)).astype(np.float32) if C1 else None
+    Wt = (rng.standard_normal((Cout, Cin, 3, 3)) / np.sqrt(Cin * 9)).astype(np.float32)
+    scale = rng.uniform(0.8, 1.2, Cout).astype(np.float32)
+    shift = (0.1 * rng.standard_normal(Cout)).astype(np.float32)
+    act = 1 if Cin == 1 else 0
+    if Cin > 1:   # the kernel reads fp16 activations: compare on the same rounded values
+        r0, r1 = in0.astype(np.float16).astype(np.float32), in1.astype(np.float16).astype(np.float32)
+    else:
+        r0, r1 = in0, None
+    ref = _ref(r0, r1, Wt, scale, shift, 0, 3, 1, 1, act)
+    got, _ = engine.test_conv_layer(in0, in1, Wt, scale, shift, 0, 3, 1, 1, act, use_tc=2)
+    err = np.abs(got - ref).max()
+    print('edge', case, 'max err', err)
+    assert err < (5e-3 if Cin == 1 else 1e-4), err     # Cin = 1 writes fp16 (|y| < 8 -> half ulp 2^-9 * 4)

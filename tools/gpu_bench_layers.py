@@ -26,3 +26,12 @@ for name, tr, H, W, C0, C1, Cout in layers:
     tot += ms; totf += fl
     print(f'{name}: in {H}x{W}x{Cin} -> {Cout}: {ms * 1e3:7.1f} us  {fl / ms / 1e9:7.1f} TFLOP/s')
 print(f'TOTAL variant={os.environ.get("RYK_TC_VARIANT", "default")}: {tot * 1e3:.1f} us, {totf / tot / 1e9:.1f} TFLOP/s')
+# edge layers (3x3): c0 = 1 -> 64 (fp32 in, fp16 out), out = 64 + 64 -> 1 (fp16 in, fp32 out)
+in0 = rng.standard_normal((1, Tp, 512, 1)).astype(np.float32)
+Wt = rng.standard_normal((64, 1, 3, 3)).astype(np.float32) / 3
+out, ms = eng.test_conv_layer(in0, None, Wt, np.ones(64, np.float32), np.zeros(64, np.float32), 0, 3, 1, 1, 1, use_tc=2, repeat=20)
+print(f'c0 (cin1): {ms * 1e3:7.1f} us   {Tp * 512 * 64 * 2 / ms / 1e6:7.1f} GB/s written')
+in0 = rng.standard_normal((1, Tp, 512, 64)).astype(np.float32); in1 = rng.standard_normal((1, Tp, 512, 64)).astype(np.float32)
+Wt = rng.standard_normal((1, 128, 3, 3)).astype(np.float32) / 30
+out, ms = eng.test_conv_layer(in0, in1, Wt, np.ones(1, np.float32), np.zeros(1, np.float32), 0, 3, 1, 1, 0, use_tc=2, repeat=20)
+print(f'out (cout1): {ms * 1e3:7.1f} us   {Tp * 512 * 128 * 2 / ms / 1e6:7.1f} GB/s read')
