@@ -201,16 +201,32 @@ def run_gpu(args):
     SuperResolution(create_sr_from_json(paths['stage2_config_path']), paths['stage2_model_path'], engine=eng)
     eng.set_precision('fp16')
 
+    T, B = args.buffer_time, args.streams_per_gpu
+    default_workload = (B == 1 and abs(T - BUFFER_TIME) < 1e-9)
+    Tw = round((T + 2 * EXTRA[1]) * 200)
+    Tp = Tw + (128 - Tw % 128)
+
     def new_session():
         cfg = SessionConfig(fs=FS, frame_period_ms=5.0, f0_floor=71.0, f0_ceil=800.0, fft_length=1024, order=8, alpha=0.466,
-                            buffer_time=BUFFER_TIME, encode_extra_time=EXTRA[0], convert_extra_time=EXTRA[1], decode_extra_time=EXTRA[2],
+                            buffer_time=T, encode_extra_time=EXTRA[0], convert_extra_time=EXTRA[1], decode_extra_time=EXTRA[2],
                             threshold_db=THRESHOLD_DB, vocoder_buffer_size=1024)
         return eng.session_create(cfg)
 
-    n = round(BUFFER_TIME * FS)
+    def new_streams():
+        """B sessions of this rank; B > 1: grouped so that stage 2 runs once per step at batch B (BASELINE config 5)."""
+        sids = [new_session() for _ in range(B)]
+        return sids, (eng.group_create(sids) if B > 1 else None)
+
+    def free_streams(sids, gid):
+        if gid is not None:
+            eng.group_destroy(gid)
+        for sid in sids:
+            eng.session_destroy(sid)
+
+    n = round(T * FS)
     total = args.warmup + args.steps
-    x = synthetic.synthetic_speech((total + 1) * BUFFER_TIME, stream=rank)
-    chunks = [np.ascontiguousarray(x[k * n:(k + 1) * n]) for k in range(total)]
+    xs = [synthetic.synthetic_speech((total + 1) * T, stream=rank * B + j) for j in range(B)]
+    chunks = [[np.ascontiguousarray(x[k * n:(k + 1) * n]) for x in xs] for k in range(total)]     # [step][stream]
 
     def barrier():
         if world > 1:
@@ -228,15 +244,20 @@ def run_gpu(args):
         return float(t.item())
 
     # ---- leg 1: device-resident ("value") ----
-    sid = new_session()
-    d_in = torch.from_numpy(np.stack(chunks)).cuda()
-    out_cap = 16 * 1024
+    sids, gid = new_streams()
+    d_in = torch.from_numpy(np.stack([np.stack(c) for c in chunks])).cuda()       # [step][stream][n]
+    out_cap = (n // 1024 + 5) * 1024 + 8192
     RING = 8                                     # distinct output slots: consecutive chunks are in flight together
-    d_out = torch.empty((RING, out_cap), dtype=torch.float64, device='cuda')
-    d_n = torch.zeros(RING, dtype=torch.int32, device='cuda')
+    d_out = torch.empty((RING, B, out_cap), dtype=torch.float64, device='cuda')
+    d_n = torch.zeros((RING, B), dtype=torch.int32, device='cuda')
 
     def push_dev(k):
-        eng.session_push_device(sid, d_in[k].data_ptr(), n, d_out[k % RING].data_ptr(), out_cap, d_n[k % RING:].data_ptr())
+        r = k % RING
+        if gid is None:
+            eng.session_push_device(sids[0], d_in[k, 0].data_ptr(), n, d_out[r, 0].data_ptr(), out_cap, d_n[r, 0:].data_ptr())
+        else:
+            eng.group_push_device(gid, [d_in[k, j].data_ptr() for j in range(B)], n, [d_out[r, j].data_ptr() for j in range(B)], out_cap,
+                                  [d_n[r, j:].data_ptr() for j in range(B)])
 
     for k in range(args.warmup):
         push_dev(k)
@@ -258,28 +279,37 @@ def run_gpu(args):
     clocks = sampler.stop()
     launches = eng.launch_count - launches0
     t_dev = max_over_ranks(t_dev)
-    eng.session_destroy(sid)
+    free_streams(sids, gid)
 
     # ---- leg 2: end to end with host buffers ("e2e") ----
-    sid = new_session()
-    host_out = np.empty(out_cap, dtype=np.float64)
+    sids, gid = new_streams()
+    host_out = [np.empty(out_cap, dtype=np.float64) for _ in range(B)]
     produced = 0
-    DEPTH = 3                                    # chunks in flight (submit k, collect k - DEPTH): host buffers both ways
+    DEPTH = 3                                    # steps in flight (submit k, collect k - DEPTH): host buffers both ways
+
+    def submit(k):
+        return eng.session_submit(sids[0], chunks[k][0]) if gid is None else eng.group_submit(gid, chunks[k])
+
+    def collect(t):
+        if gid is None:
+            return len(eng.session_collect(sids[0], t, host_out[0]))
+        return sum(len(o) for o in eng.group_collect(gid, t, host_out))
+
     for k in range(args.warmup):
-        eng.session_push(sid, chunks[k], host_out)
+        collect(submit(k))
     barrier()
     t0 = time.perf_counter()
     tickets = []
     for k in range(args.warmup, total):
-        tickets.append(eng.session_submit(sid, chunks[k]))
+        tickets.append(submit(k))
         if len(tickets) > DEPTH:
-            produced += len(eng.session_collect(sid, tickets.pop(0), host_out))
+            produced += collect(tickets.pop(0))
     while tickets:
-        produced += len(eng.session_collect(sid, tickets.pop(0), host_out))
+        produced += collect(tickets.pop(0))
     t_e2e = time.perf_counter() - t0
     barrier()
     t_e2e = max_over_ranks(t_e2e)
-    eng.session_destroy(sid)
+    free_streams(sids, gid)
 
     if world > 1:
         import torch.distributed as dist
@@ -287,28 +317,33 @@ def run_gpu(args):
         dist.destroy_process_group()
     if rank != 0:
         return
-    value = world * args.steps / t_dev
-    e2e = world * args.steps / t_e2e
+    value = world * B * args.steps / t_dev
+    e2e = world * B * args.steps / t_e2e
     peaks = measured_peaks()
-    fl = stage2_tc_flop()
+    fl = stage2_tc_flop(Tp) * B
     ach = fl * s2_runs / (s2_ms * 1e-3) / 1e12 if s2_ms > 0 else None
     cpu_rate = cores = None
-    if world == 1:                      # reported baseline: rank 0 at N = 1 only
+    if world == 1 and default_workload:                      # reported baseline: rank 0 at N = 1 only
         cpu = CpuPath(paths, n_chunks=8)
         cpu.step()
         cpu_rate, cores = cpu.rate(3), cpu.cores
+    metric = METRIC if default_workload else f'chunks_per_s_{T:g}s_24kHz_encode_stage1_stage2_vocode'
+    workload = WORKLOAD if default_workload else (
+        f'{B} stream(s) per GPU' + (' grouped: one batched stage-2 forward per step' if B > 1 else '') +
+        f', buffer_time={T:g} s, extras (0,0.5,0), frame_period 5 ms, 24 kHz in/out, convert window {Tw} -> {Tp} frames, '
+        f'stage-2 input ({B},1,{Tp},512), same models as the default workload; one step = one chunk of every stream')
     line = dict(
-        metric=METRIC, value=value, unit='chunks/s', rtf=value * BUFFER_TIME, n_gpus=world, steps=args.steps, warmup=args.warmup,
+        metric=metric, value=value, unit='chunks/s', rtf=value * T, n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=1000.0 * t_dev / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
         dtype='f64 (WORLD analysis/synthesis), f32 (stage 1), f16 in / f32 accumulate (stage 2 tcgen05)', data='synthetic',
-        config=dict(workload=WORKLOAD, timing='CUDA events on the engine stream (forked to / joined from the session streams) around the K pushes, max over ranks', pipeline='encode | convert | decode of consecutive chunks overlap on 3 CUDA streams (as the reference overlaps its 3 worker processes); e2e keeps 3 chunks in flight',
+        config=dict(workload=workload, timing='CUDA events on the engine stream (forked to / joined from the session streams) around the K pushes, max over ranks', pipeline='encode | convert | decode of consecutive chunks overlap on 4 CUDA streams per audio stream (as the reference overlaps its 3 worker processes); e2e keeps 3 steps in flight',
                     l2='per-step footprint (109 MB fp16 stage-2 weights + 54 MB stage-1 weights + ~100 MB activations) exceeds the 126 MB L2; no explicit flush',
-                    streams_per_gpu=1, silence_threshold_db=THRESHOLD_DB),
-        e2e=dict(value=e2e, unit='chunks/s', rtf=e2e * BUFFER_TIME, h2d_bytes_per_step=n * 4,
-                 d2h_bytes_per_step=int(produced / max(1, args.steps)) * 8 + 4 + 8),
+                    streams_per_gpu=B, silence_threshold_db=THRESHOLD_DB),
+        e2e=dict(value=e2e, unit='chunks/s', rtf=e2e * T, h2d_bytes_per_step=B * n * 4,
+                 d2h_bytes_per_step=int(produced / max(1, args.steps)) * 8 + B * (4 + 8)),
         gpu_launches=int(launches), host_enqueue_ms_per_step=1000.0 * t_host / args.steps,
         clocks=clocks,
-        roofline=dict(bound='tensor', kernel='k_conv_tc (stage-2 k4 layers 1..14, incl. split-K memset/finalize)', achieved=ach, peak=peaks['tflops'],
+        roofline=dict(bound='tensor', kernel='k_conv_tc (stage-2 k4 layers 1..14, incl. split-K memset/finalize)' + ('' if B == 1 else ' + the two 3x3 edge layers (group forward timed as a whole)'), achieved=ach, peak=peaks['tflops'],
                       unit='TFLOP/s', frac=(ach / peaks['tflops']) if ach else None, traffic=None, peak_source=peaks['source'],
                       flop_per_step=fl, ms_per_step_in_kernel=(s2_ms / s2_runs) if s2_runs else None),
     )
@@ -324,6 +359,8 @@ def main():
     ap.add_argument('--steps', type=int, default=None)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--streams-per-gpu', type=int, default=1, help='B > 1: BASELINE config 5 style, B grouped streams per GPU')
+    ap.add_argument('--buffer-time', type=float, default=BUFFER_TIME, help='seconds per chunk (default workload: 0.3)')
     args = ap.parse_args()
     if args.steps is None:
         args.steps = 20 if args.impl == 'b200' else 6

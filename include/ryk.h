@@ -139,6 +139,20 @@ int ryk_session_collect(ryk_engine* e, int session_id, long long ticket, double*
 int ryk_session_push_device(ryk_engine* e, int session_id, const float* wave_dev, int n, double* out_dev, int out_capacity,
                             int* n_out_dev);
 
+/* ---- session groups: several streams of one GPU sharing one batched stage-2 forward -------------------
+ * BASELINE config 5 / SURVEY 8(e) "per-GPU batch = streams resident on it": the reference would run one
+ * SuperResolution.convert (voice_changer.py:41) per stream; a group stacks the members' padded log-spectrograms into
+ * one (B, 1, Tp, 512) stage-2 input per step.  Analysis, gate, stage 1 and synthesis stay per stream (per-stream state,
+ * data-dependent lengths).  Members are fresh sessions with the same window length; member i of every call is
+ * session_ids[i].  Outputs per member are those of an ungrouped session up to the FP16 stage-2 rounding. */
+int ryk_group_create(ryk_engine* e, const int* session_ids, int n_sessions, int* group_id);
+int ryk_group_destroy(ryk_engine* e, int group_id);        /* members survive, ungrouped */
+int ryk_group_size(ryk_engine* e, int group_id);
+int ryk_group_submit(ryk_engine* e, int group_id, const float* const* waves, int n, long long* ticket);
+int ryk_group_collect(ryk_engine* e, int group_id, long long ticket, double* const* outs, int out_capacity, int* n_outs);
+int ryk_group_push_device(ryk_engine* e, int group_id, const float* const* waves_dev, int n, double* const* outs_dev,
+                          int out_capacity, int* const* n_outs_dev);
+
 /* ---- diagnostics -------------------------------------------------------------------------------------- */
 /* Synthesizer pulse ring entries [first, first+count) and state {n_pulses, next_pulse, last_location, synthesized_sample,
  * cumulative_frame, rng_generated, blocks_out}. */

@@ -14,6 +14,7 @@ namespace ryk {
 
 struct DioPlan;
 struct Session;
+struct Group;
 
 struct Engine {
   int device = 0;
@@ -39,6 +40,7 @@ struct Engine {
   // synthesizers
   std::vector<Synth*> synths;
   std::vector<Session*> sessions;
+  std::vector<Group*> groups;
   float* d_colmin = nullptr;         // stage-2 prologue column-minimum partials
   // scratch arena for the per-op host-pointer API (grown on demand)
   void* d_scratch = nullptr; size_t scratch_bytes = 0;

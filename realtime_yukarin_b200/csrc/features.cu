@@ -272,12 +272,15 @@ int stage1_epilogue_run(Engine* e, const float* d_y, const int* d_index, const u
   return 0;
 }
 
-int sr_prologue_run(Engine* e, const float* d_sp, int T, int Tp, int nb, float* d_x, cudaStream_t st) {
+int sr_prologue_run(Engine* e, const float* d_sp, int T, int Tp, int nb, float* d_x, cudaStream_t st, float* d_colmin) {
   const int rows_per_block = 32, nparts = (T + rows_per_block - 1) / rows_per_block;
-  RYK_CHECK((size_t)nparts * (nb - 1) * sizeof(float) <= sizeof(float) * 64 * 512, "window too long for the column-minimum scratch");
-  if (!e->d_colmin) RYK_CUDA(cudaMalloc(&e->d_colmin, sizeof(float) * 64 * 512));
-  k_sr_colmin<<<dim3((nb - 1 + 127) / 128, nparts), 128, 0, st>>>(d_sp, T, nb, rows_per_block, e->d_colmin);
-  k_sr_prologue<<<dim3((nb - 1 + 127) / 128, Tp), 128, 0, st>>>(d_sp, e->d_colmin, nparts, T, Tp, nb, d_x);
+  RYK_CHECK((size_t)nparts * (nb - 1) * sizeof(float) <= sizeof(float) * kColminFloats, "window too long for the column-minimum scratch");
+  if (!d_colmin) {                  // per-op API: the engine's scratch (calls are serialised on the engine stream)
+    if (!e->d_colmin) RYK_CUDA(cudaMalloc(&e->d_colmin, sizeof(float) * kColminFloats));
+    d_colmin = e->d_colmin;
+  }
+  k_sr_colmin<<<dim3((nb - 1 + 127) / 128, nparts), 128, 0, st>>>(d_sp, T, nb, rows_per_block, d_colmin);
+  k_sr_prologue<<<dim3((nb - 1 + 127) / 128, Tp), 128, 0, st>>>(d_sp, d_colmin, nparts, T, Tp, nb, d_x);
   RYK_CUDA(cudaGetLastError());
   e->launches += 2;
   return 0;

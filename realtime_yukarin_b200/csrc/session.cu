@@ -37,7 +37,12 @@ namespace ryk {
 constexpr int kRing = 8;          // event / output-slot ring (pipeline depth is bounded by the buffer guards below)
 
 struct StageGraph { cudaGraphExec_t exec = nullptr; long long launches = 0; };
+struct Group;
 struct Session {
+  int owner = 0;                               // plan-cache owner id (activation buffers are private to the session)
+  float* d_colmin = nullptr;
+  Group* group = nullptr; int slot = 0;        // member of a batched stage-2 group (config 5), else nullptr
+  cudaEvent_t ev_pro[kRing];                   // stage-2 prologue of step r done (group members only)
   ryk_session_config cfg;
   int hop, rate, n_wave, n_feat, e_wave, e_enc_frames, e_conv, e_dec;
   int Lw, Tw, Td, nb, C;
@@ -69,6 +74,19 @@ struct Session {
   Synth* synth = nullptr;
   DioPlan* dio = nullptr;
   std::vector<void*> allocs, pinned;
+};
+
+// Several sessions on one GPU sharing ONE batched stage-2 forward per step (BASELINE config 5: 8 streams per GPU,
+// stage-2 input (B, 1, Tp, 512)).  Everything else (analysis, gate, stage 1, synthesis) stays per stream: those
+// stages carry per-stream state and data-dependent lengths, and they are a small share of the SM time.
+struct Group {
+  std::vector<Session*> members;
+  int Tp = 0, owner = 0;
+  UNetPlan* p2 = nullptr;                      // stage-2 plan at batch = members.size()
+  cudaStream_t sG = nullptr;
+  cudaEvent_t ev_fwd[kRing];                   // batched forward of step r done
+  long long step = 0, collected = 0;
+  StageGraph fwd_graph;
 };
 
 // dst = [old[shift..L), new[0..shift)] row-wise (rows of `row` elements)
@@ -146,7 +164,7 @@ static void session_free(Session* s) {
   if (!s) return;
   for (cudaStream_t st : {s->sE, s->sC, s->sC2, s->sD}) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
   for (int i = 0; i < kRing; ++i)
-    for (cudaEvent_t ev : {s->ev_count[i], s->ev_enc[i], s->ev_cslide[i], s->ev_s1[i], s->ev_conv[i], s->ev_dslide[i], s->ev_dec[i]}) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : {s->ev_pro[i], s->ev_count[i], s->ev_enc[i], s->ev_cslide[i], s->ev_s1[i], s->ev_conv[i], s->ev_dslide[i], s->ev_dec[i]}) if (ev) cudaEventDestroy(ev);
   for (auto& kv : s->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   for (void* p : s->allocs) cudaFree(p);
   for (void* p : s->pinned) cudaFreeHost(p);
@@ -154,7 +172,24 @@ static void session_free(Session* s) {
   delete s;
 }
 
+static void group_free(Group* G) {
+  if (!G) return;
+  if (G->sG) { cudaStreamSynchronize(G->sG); cudaStreamDestroy(G->sG); }
+  for (int i = 0; i < kRing; ++i) if (G->ev_fwd[i]) cudaEventDestroy(G->ev_fwd[i]);
+  if (G->fwd_graph.exec) cudaGraphExecDestroy(G->fwd_graph.exec);
+  for (Session* m : G->members) {
+    m->group = nullptr;
+    for (int key = 40; key < 46; ++key) {          // the captured stage-2 prologue / epilogue graphs point into the group's plan
+      auto it = m->graphs.find(key);
+      if (it != m->graphs.end()) { if (it->second.exec) cudaGraphExecDestroy(it->second.exec); m->graphs.erase(it); }
+    }
+  }
+  delete G;
+}
+
 void session_destroy_all(Engine* e) {
+  for (Group* G : e->groups) group_free(G);
+  e->groups.clear();
   for (Session* s : e->sessions) session_free(s);
   e->sessions.clear();
 }
@@ -165,6 +200,7 @@ int session_streams_fork(Engine* e, cudaEvent_t ev) {
     if (!s) continue;
     for (cudaStream_t st : {s->sE, s->sC, s->sC2, s->sD}) RYK_CUDA(cudaStreamWaitEvent(st, ev, 0));
   }
+  for (Group* G : e->groups) if (G) RYK_CUDA(cudaStreamWaitEvent(G->sG, ev, 0));
   return 0;
 }
 // make the engine's main stream wait for everything queued on the session streams
@@ -178,6 +214,14 @@ int session_streams_join(Engine* e) {
       RYK_CUDA(cudaStreamWaitEvent(e->stream, ev, 0));
       RYK_CUDA(cudaEventDestroy(ev));
     }
+  }
+  for (Group* G : e->groups) {
+    if (!G) continue;
+    cudaEvent_t ev;
+    RYK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    RYK_CUDA(cudaEventRecord(ev, G->sG));
+    RYK_CUDA(cudaStreamWaitEvent(e->stream, ev, 0));
+    RYK_CUDA(cudaEventDestroy(ev));
   }
   return 0;
 }
@@ -210,15 +254,20 @@ static int run_stage(Engine* e, Session* s, int key, cudaStream_t st, F&& body) 
 
 enum { G_E1 = 0, G_E2 = 2, G_S1 = 4 /* + 2 * bucket + parity, bucket 0..15 */, G_S2A = 40, G_S2B = 42, G_S2C = 44, G_D = 46 };
 
-// Enqueue step k = s->step on the four streams. d_chunk: n_wave samples (device); results land in s->d_out_fixed[b] / s->d_n_fixed[b].
-static int session_enqueue(Engine* e, Session* s, const float* d_chunk_user) {
-  const long long k = s->step;
-  const int b = (int)(k & 1), f = b, g = b ^ 1;           // windows: read [f], write [g]; inter-stage sets: [b]
-  const int r = (int)(k % kRing);
-  const ryk_session_config& c = s->cfg;
-  const int pe = s->e_enc_frames, pc = s->e_conv;
-  const bool was_profiling = e->profile;
-  e->profile = false;                                      // the session places its own timing events (between graph launches)
+// Step k = s->step is enqueued in three parts so that a group can interleave its members:
+//   front: streams E and C (analysis, gate, stage 1, mc2sp) and the stage-2 prologue
+//   mid:   the stage-2 U-Net forward (single session: on its own stream C2; group: one batched forward on the group stream)
+//   back:  stage-2 epilogue and stream D (synthesizer); results land in s->d_out_fixed[b] / s->d_n_fixed[b]; s->step advances.
+#define STEP_LOCALS                                                                                         \
+  const long long k = s->step;                                                                              \
+  const int b = (int)(k & 1), f = b, g = b ^ 1; /* windows: read [f], write [g]; inter-stage sets: [b] */    \
+  const int r = (int)(k % kRing);                                                                           \
+  const ryk_session_config& c = s->cfg;                                                                     \
+  const int pe = s->e_enc_frames, pc = s->e_conv;                                                           \
+  (void)f; (void)g; (void)r; (void)c; (void)pe; (void)pc;
+
+static int session_front(Engine* e, Session* s, const float* d_chunk_user) {
+  STEP_LOCALS
 
   // ================= stream E: gate + WORLD analysis =================
   RYK_CUDA(cudaMemcpyAsync(s->d_chunk_fixed, d_chunk_user, sizeof(float) * s->n_wave, cudaMemcpyDeviceToDevice, s->sE));
@@ -262,7 +311,7 @@ static int session_enqueue(Engine* e, Session* s, const float* d_chunk_user) {
         const float* d_y = nullptr;
         if (t_eff > 0) {      // voice_changer.py:32-35: stage 1 is skipped when no frame is effective
           UNetPlan* p1 = nullptr;
-          if (unet_get_plan(e, e->stage1, 1, 1, tp1, e->precision, &p1)) return -1;
+          if (unet_get_plan(e, e->stage1, 1, 1, tp1, e->precision, &p1, s->owner)) return -1;
           if (stage1_prologue_run(e, s->cw_mc[g], s->d_index[b], s->d_count[b], s->C, (float*)p1->d_in, tp1, s->sC)) return -1;
           if (unet_forward(e, p1, s->sC)) return -1;
           d_y = (const float*)p1->d_out;
@@ -276,24 +325,56 @@ static int session_enqueue(Engine* e, Session* s, const float* d_chunk_user) {
   RYK_CUDA(cudaEventRecord(s->ev_cslide[r], s->sC));
   RYK_CUDA(cudaEventRecord(s->ev_s1[r], s->sC));
 
-  // ================= stream C2: stage 2 =================
+  // ================= stream C2: stage-2 prologue =================
   RYK_CUDA(cudaStreamWaitEvent(s->sC2, s->ev_s1[r], 0));
   if (k >= 2) RYK_CUDA(cudaStreamWaitEvent(s->sC2, s->ev_dslide[(k - 2) % kRing], 0));  // cv_sp_out[b] consumed by decode k-2
   const int Tp = s->Tw + (128 - s->Tw % 128);
+  if (s->group) {
+    Group* G = s->group;
+    if (G->step >= 1) RYK_CUDA(cudaStreamWaitEvent(s->sC2, G->ev_fwd[(G->step - 1) % kRing], 0));   // batched input read by forward k-1
+    float* dst = (float*)G->p2->d_in + (size_t)s->slot * Tp * 512;
+    if (run_stage(e, s, G_S2A + b, s->sC2, [&]() -> int { return sr_prologue_run(e, s->cv_sp_mid[b], s->Tw, Tp, s->nb, dst, s->sC2, s->d_colmin); })) return -1;
+    RYK_CUDA(cudaEventRecord(s->ev_pro[r], s->sC2));
+  } else {
+    UNetPlan* p2 = nullptr;
+    if (unet_get_plan(e, e->stage2, 1, Tp, 512, e->precision, &p2, s->owner)) return -1;
+    if (run_stage(e, s, G_S2A + b, s->sC2, [&]() -> int {
+          if (sr_prologue_run(e, s->cv_sp_mid[b], s->Tw, Tp, s->nb, (float*)p2->d_in, s->sC2, s->d_colmin)) return -1;
+          return unet_forward(e, p2, s->sC2, 0, 0);
+        })) return -1;
+  }
+  return 0;
+}
+
+// single session: stage-2 layers 1..14 (the tcgen05 layers) on the session's own stream
+static int session_mid_single(Engine* e, Session* s, bool was_profiling) {
+  STEP_LOCALS
+  const int Tp = s->Tw + (128 - s->Tw % 128);
   UNetPlan* p2 = nullptr;
-  if (unet_get_plan(e, e->stage2, 1, Tp, 512, e->precision, &p2)) return -1;
-  if (run_stage(e, s, G_S2A + b, s->sC2, [&]() -> int {
-        if (sr_prologue_run(e, s->cv_sp_mid[b], s->Tw, Tp, s->nb, (float*)p2->d_in, s->sC2)) return -1;
-        return unet_forward(e, p2, s->sC2, 0, 0);
-      })) return -1;
+  if (unet_get_plan(e, e->stage2, 1, Tp, 512, e->precision, &p2, s->owner)) return -1;
   cudaEvent_t pe0 = nullptr, pe1 = nullptr;
   if (was_profiling) { RYK_CUDA(cudaEventCreate(&pe0)); RYK_CUDA(cudaEventCreate(&pe1)); RYK_CUDA(cudaEventRecord(pe0, s->sC2)); }
   if (run_stage(e, s, G_S2B + b, s->sC2, [&]() -> int { return unet_forward(e, p2, s->sC2, 1, 14); })) return -1;
   if (was_profiling) { RYK_CUDA(cudaEventRecord(pe1, s->sC2)); e->prof_events.emplace_back(pe0, pe1); }
-  if (run_stage(e, s, G_S2C + b, s->sC2, [&]() -> int {
-        if (unet_forward(e, p2, s->sC2, 15, 15)) return -1;
-        return sr_epilogue_run(e, (const float*)p2->d_out, s->Tw, s->nb, s->cv_sp_out[b], s->sC2);
-      })) return -1;
+  return 0;
+}
+
+static int session_back(Engine* e, Session* s) {
+  STEP_LOCALS
+  const int Tp = s->Tw + (128 - s->Tw % 128);
+  if (s->group) {
+    Group* G = s->group;
+    RYK_CUDA(cudaStreamWaitEvent(s->sC2, G->ev_fwd[G->step % kRing], 0));
+    const float* src = (const float*)G->p2->d_out + (size_t)s->slot * Tp * 512;
+    if (run_stage(e, s, G_S2C + b, s->sC2, [&]() -> int { return sr_epilogue_run(e, src, s->Tw, s->nb, s->cv_sp_out[b], s->sC2); })) return -1;
+  } else {
+    UNetPlan* p2 = nullptr;
+    if (unet_get_plan(e, e->stage2, 1, Tp, 512, e->precision, &p2, s->owner)) return -1;
+    if (run_stage(e, s, G_S2C + b, s->sC2, [&]() -> int {
+          if (unet_forward(e, p2, s->sC2, 15, 15)) return -1;
+          return sr_epilogue_run(e, (const float*)p2->d_out, s->Tw, s->nb, s->cv_sp_out[b], s->sC2);
+        })) return -1;
+  }
   RYK_CUDA(cudaEventRecord(s->ev_conv[r], s->sC2));
 
   // ================= stream D: realtime synthesizer =================
@@ -316,10 +397,68 @@ static int session_enqueue(Engine* e, Session* s, const float* d_chunk_user) {
       })) return -1;
   // the decode graph both consumes cv_*[b] and produces the output: one event guards both
   RYK_CUDA(cudaEventRecord(s->ev_dslide[r], s->sD));
-  e->profile = was_profiling;
   // ev_dec[r] is recorded by the caller after the copies it appends to stream D
   s->step++;
   return 0;
+}
+
+static int session_enqueue(Engine* e, Session* s, const float* d_chunk_user) {
+  const bool was_profiling = e->profile;
+  e->profile = false;                                      // the session places its own timing events (between graph launches)
+  int rc = session_front(e, s, d_chunk_user);
+  if (!rc) rc = session_mid_single(e, s, was_profiling);
+  if (!rc) rc = session_back(e, s);
+  e->profile = was_profiling;
+  return rc;
+}
+
+// One step of every member + the batched stage-2 forward between their front and back halves.
+static int group_enqueue_impl(Engine* e, Group* G, const float* const* d_chunks, bool was_profiling) {
+  const int r = (int)(G->step % kRing);
+  for (size_t i = 0; i < G->members.size(); ++i)
+    if (session_front(e, G->members[i], d_chunks[i])) return -1;
+  for (Session* m : G->members) {
+    RYK_CUDA(cudaStreamWaitEvent(G->sG, m->ev_pro[m->step % kRing], 0));
+    if (m->step >= 1) RYK_CUDA(cudaStreamWaitEvent(G->sG, m->ev_conv[(m->step - 1) % kRing], 0));   // batched output read by epilogue k-1
+  }
+  cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+  if (was_profiling) { RYK_CUDA(cudaEventCreate(&pe0)); RYK_CUDA(cudaEventCreate(&pe1)); RYK_CUDA(cudaEventRecord(pe0, G->sG)); }
+  {
+    StageGraph& g = G->fwd_graph;
+    const bool use_graphs = G->members[0]->use_graphs;
+    if (!use_graphs) {
+      if (unet_forward(e, G->p2, G->sG, 0, 15)) return -1;
+    } else {
+      if (!g.exec) {
+        long long before = e->launches;
+        cudaGraph_t graph = nullptr;
+        RYK_CUDA(cudaStreamBeginCapture(G->sG, cudaStreamCaptureModeThreadLocal));
+        int rc = unet_forward(e, G->p2, G->sG, 0, 15);
+        cudaError_t err = cudaStreamEndCapture(G->sG, &graph);
+        if (rc) return rc;
+        RYK_CUDA(err);
+        RYK_CUDA(cudaGraphInstantiate(&g.exec, graph, 0));
+        RYK_CUDA(cudaGraphDestroy(graph));
+        g.launches = e->launches - before;
+        e->launches = before;
+      }
+      RYK_CUDA(cudaGraphLaunch(g.exec, G->sG));
+      e->launches += g.launches;
+    }
+  }
+  if (was_profiling) { RYK_CUDA(cudaEventRecord(pe1, G->sG)); e->prof_events.emplace_back(pe0, pe1); }
+  RYK_CUDA(cudaEventRecord(G->ev_fwd[r], G->sG));
+  for (Session* m : G->members)
+    if (session_back(e, m)) return -1;
+  G->step++;
+  return 0;
+}
+static int group_enqueue(Engine* e, Group* G, const float* const* d_chunks) {
+  const bool was_profiling = e->profile;
+  e->profile = false;
+  int rc = group_enqueue_impl(e, G, d_chunks, was_profiling);
+  e->profile = was_profiling;
+  return rc;
 }
 
 }  // namespace ryk
@@ -336,7 +475,7 @@ int ryk_session_create(ryk_engine* h, const ryk_session_config* cfg, int* sessio
   RYK_CHECK(e->stage1 && e->stage2, "load both models before creating a session");
   Session* s = new Session();
   memset(s->ev_count, 0, sizeof(s->ev_count)); memset(s->ev_enc, 0, sizeof(s->ev_enc)); memset(s->ev_cslide, 0, sizeof(s->ev_cslide));
-  memset(s->ev_s1, 0, sizeof(s->ev_s1)); memset(s->ev_conv, 0, sizeof(s->ev_conv)); memset(s->ev_dslide, 0, sizeof(s->ev_dslide)); memset(s->ev_dec, 0, sizeof(s->ev_dec));
+  memset(s->ev_s1, 0, sizeof(s->ev_s1)); memset(s->ev_pro, 0, sizeof(s->ev_pro)); memset(s->ev_conv, 0, sizeof(s->ev_conv)); memset(s->ev_dslide, 0, sizeof(s->ev_dslide)); memset(s->ev_dec, 0, sizeof(s->ev_dec));
   s->cfg = *cfg;
   s->hop = (int)(cfg->fs * cfg->frame_period_ms / 1000.0);
   s->rate = (int)lround(1000.0 / cfg->frame_period_ms);
@@ -360,7 +499,7 @@ int ryk_session_create(ryk_engine* h, const ryk_session_config* cfg, int* sessio
   RYK_CUDA(cudaStreamCreateWithFlags(&s->sC2, cudaStreamNonBlocking));
   RYK_CUDA(cudaStreamCreateWithFlags(&s->sD, cudaStreamNonBlocking));
   for (int i = 0; i < kRing; ++i) {
-    cudaEvent_t* evs[] = {&s->ev_count[i], &s->ev_enc[i], &s->ev_cslide[i], &s->ev_s1[i], &s->ev_conv[i], &s->ev_dslide[i], &s->ev_dec[i]};
+    cudaEvent_t* evs[] = {&s->ev_pro[i], &s->ev_count[i], &s->ev_enc[i], &s->ev_cslide[i], &s->ev_s1[i], &s->ev_conv[i], &s->ev_dslide[i], &s->ev_dec[i]};
     for (cudaEvent_t* ev : evs) RYK_CUDA(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
   }
   auto A = [&](void** p, size_t bytes) -> int { RYK_CUDA(cudaMalloc(p, bytes ? bytes : 16)); RYK_CUDA(cudaMemset(*p, 0, bytes ? bytes : 16)); s->allocs.push_back(*p); return 0; };
@@ -394,6 +533,7 @@ int ryk_session_create(ryk_engine* h, const ryk_session_config* cfg, int* sessio
     if (A((void**)&s->cv_sp_mid[i], sizeof(float) * (size_t)s->Tw * s->nb)) return -1;
   }
   if (A((void**)&s->d_mse, sizeof(double) * s->Tw)) return -1;
+  if (A((void**)&s->d_colmin, sizeof(float) * kColminFloats)) return -1;
   if (A((void**)&s->dec_f0_f64, sizeof(double) * s->Td)) return -1;
   if (A((void**)&s->d_chunk_fixed, sizeof(float) * s->n_wave)) return -1;
   { const char* ng = getenv("RYK_NO_GRAPH"); s->use_graphs = !(ng && atoi(ng) != 0); }
@@ -417,8 +557,9 @@ int ryk_session_create(ryk_engine* h, const ryk_session_config* cfg, int* sessio
   if (synth_create(e, cfg->fs, cfg->frame_period_ms, cheaptrick_fft_size(cfg->fs, 71.0), cfg->vocoder_buffer_size, 4096, &s->synth)) return -1;
   // build the U-Net plans this session can need up front (allocation + tensor maps), not on the first chunk
   UNetPlan* p = nullptr;
-  for (int Tp = 128; Tp <= s->Tw + 128; Tp += 128) if (unet_get_plan(e, e->stage1, 1, 1, Tp, e->precision, &p)) return -1;
-  if (unet_get_plan(e, e->stage2, 1, s->Tw + (128 - s->Tw % 128), 512, e->precision, &p)) return -1;
+  s->owner = (int)e->sessions.size() + 1;
+  for (int Tp = 128; Tp <= s->Tw + 128; Tp += 128) if (unet_get_plan(e, e->stage1, 1, 1, Tp, e->precision, &p, s->owner)) return -1;
+  // (the stage-2 plan is created on first use: a session that joins a group never needs its own)
   RYK_CUDA(cudaStreamSynchronize(e->stream));
   RYK_CUDA(cudaDeviceSynchronize());
   e->sessions.push_back(s);
@@ -430,8 +571,12 @@ int ryk_session_destroy(ryk_engine* h, int id) {
   Engine* e = &h->impl;
   Session* s = get_session(e, id);
   RYK_CHECK(s != nullptr, "no such session");
+  RYK_CHECK(s->group == nullptr, "session belongs to a group: destroy the group first");
   RYK_CUDA(cudaStreamSynchronize(e->stream));
-  session_free(s);
+  const int owner = s->owner;
+  session_free(s);                         // synchronises the session's streams
+  unet_release_owner(e->stage1, owner);
+  unet_release_owner(e->stage2, owner);
   e->sessions[id] = nullptr;
   return 0;
 }
@@ -443,6 +588,7 @@ int ryk_session_submit(ryk_engine* h, int id, const float* wave, int n, long lon
   Session* s = get_session(e, id);
   RYK_CHECK(s != nullptr, "no such session");
   RYK_CHECK(n == s->n_wave, "chunk length must be round(fs * buffer_time)");
+  RYK_CHECK(s->group == nullptr, "session belongs to a group: use ryk_group_submit");
   RYK_CHECK(s->step - s->collected < kRing - 2, "too many chunks in flight: collect before submitting more");
   const long long k = s->step;
   const int r = (int)(k % kRing);
@@ -488,6 +634,7 @@ int ryk_session_push_device(ryk_engine* h, int id, const float* wave_dev, int n,
   Session* s = get_session(e, id);
   RYK_CHECK(s != nullptr, "no such session");
   RYK_CHECK(n == s->n_wave, "chunk length must be round(fs * buffer_time)");
+  RYK_CHECK(s->group == nullptr, "session belongs to a group: use ryk_group_push_device");
   const int r = (int)(s->step % kRing), b = (int)(s->step & 1);
   const int cap = s->max_blocks * s->cfg.vocoder_buffer_size;
   RYK_CHECK(out_capacity >= cap, "out_capacity must hold (frames * hop / block + 4) synthesizer blocks");
@@ -496,6 +643,126 @@ int ryk_session_push_device(ryk_engine* h, int id, const float* wave_dev, int n,
   RYK_CUDA(cudaMemcpyAsync(n_out_dev, s->d_n_fixed[b], sizeof(int), cudaMemcpyDeviceToDevice, s->sD));
   RYK_CUDA(cudaEventRecord(s->ev_dec[r], s->sD));
   s->collected = s->step;         // device-resident steps are not collected through the host API
+  return 0;
+}
+
+// ---- groups: several sessions of one GPU sharing one batched stage-2 forward per step (BASELINE config 5) ----
+static Group* get_group(Engine* e, int id) { return (id >= 0 && id < (int)e->groups.size()) ? e->groups[id] : nullptr; }
+
+int ryk_group_create(ryk_engine* h, const int* session_ids, int n_sessions, int* group_id) {
+  Engine* e = &h->impl;
+  RYK_CUDA(cudaSetDevice(e->device));
+  RYK_CHECK(session_ids && group_id && n_sessions >= 1 && n_sessions <= 64, "a group holds 1..64 sessions");
+  Group* G = new Group();
+  G->owner = 1000000 + (int)e->groups.size();
+  memset(G->ev_fwd, 0, sizeof(G->ev_fwd));
+  for (int i = 0; i < n_sessions; ++i) {
+    Session* s = get_session(e, session_ids[i]);
+    if (!s || s->group || s->step != 0 || (i > 0 && s->Tw != G->members[0]->Tw)) {
+      for (Session* m : G->members) m->group = nullptr;
+      delete G;
+      RYK_CHECK(false, "group members must be distinct fresh sessions (no chunk pushed yet) with the same window length");
+    }
+    s->group = G; s->slot = i;
+    G->members.push_back(s);
+  }
+  G->Tp = G->members[0]->Tw + (128 - G->members[0]->Tw % 128);
+  if (unet_get_plan(e, e->stage2, n_sessions, G->Tp, 512, e->precision, &G->p2, G->owner)) { group_free(G); return -1; }
+  RYK_CUDA(cudaStreamCreateWithFlags(&G->sG, cudaStreamNonBlocking));
+  for (int i = 0; i < kRing; ++i) RYK_CUDA(cudaEventCreateWithFlags(&G->ev_fwd[i], cudaEventDisableTiming));
+  RYK_CUDA(cudaDeviceSynchronize());
+  e->groups.push_back(G);
+  *group_id = (int)e->groups.size() - 1;
+  return 0;
+}
+
+int ryk_group_destroy(ryk_engine* h, int group_id) {
+  Engine* e = &h->impl;
+  Group* G = get_group(e, group_id);
+  RYK_CHECK(G != nullptr, "no such group");
+  RYK_CUDA(cudaDeviceSynchronize());
+  const int owner = G->owner;
+  group_free(G);                     // the member sessions survive (ungrouped) and are destroyed separately
+  unet_release_owner(e->stage2, owner);
+  e->groups[group_id] = nullptr;
+  return 0;
+}
+
+int ryk_group_size(ryk_engine* h, int group_id) {
+  Group* G = get_group(&h->impl, group_id);
+  return G ? (int)G->members.size() : -1;
+}
+
+// Queue one chunk per member (host samples; waves[i] belongs to member i in creation order).
+int ryk_group_submit(ryk_engine* h, int group_id, const float* const* waves, int n, long long* ticket) {
+  Engine* e = &h->impl;
+  RYK_CUDA(cudaSetDevice(e->device));
+  Group* G = get_group(e, group_id);
+  RYK_CHECK(G != nullptr, "no such group");
+  RYK_CHECK(G->step - G->collected < kRing - 2, "too many chunks in flight: collect before submitting more");
+  const long long k = G->step;
+  const int r = (int)(k % kRing), b = (int)(k & 1);
+  std::vector<const float*> d_chunks(G->members.size());
+  for (size_t i = 0; i < G->members.size(); ++i) {
+    Session* s = G->members[i];
+    RYK_CHECK(n == s->n_wave, "chunk length must be round(fs * buffer_time)");
+    memcpy(s->h_in[r], waves[i], sizeof(float) * n);
+    RYK_CUDA(cudaMemcpyAsync(s->d_chunk[r], s->h_in[r], sizeof(float) * n, cudaMemcpyHostToDevice, s->sE));
+    d_chunks[i] = s->d_chunk[r];
+  }
+  if (group_enqueue(e, G, d_chunks.data())) return -1;
+  for (Session* s : G->members) {
+    const int cap = s->max_blocks * s->cfg.vocoder_buffer_size;
+    RYK_CUDA(cudaMemcpyAsync(s->h_n[r], s->d_n_fixed[b], sizeof(int), cudaMemcpyDeviceToHost, s->sD));
+    RYK_CUDA(cudaMemcpyAsync(s->h_out[r], s->d_out_fixed[b], sizeof(double) * (size_t)cap, cudaMemcpyDeviceToHost, s->sD));
+    RYK_CUDA(cudaEventRecord(s->ev_dec[r], s->sD));
+  }
+  if (ticket) *ticket = k;
+  return 0;
+}
+
+// Wait for step `ticket` of every member; outs[i] receives member i's samples, n_outs[i] their count.
+int ryk_group_collect(ryk_engine* h, int group_id, long long ticket, double* const* outs, int out_capacity, int* n_outs) {
+  Engine* e = &h->impl;
+  Group* G = get_group(e, group_id);
+  RYK_CHECK(G != nullptr, "no such group");
+  RYK_CHECK(ticket == G->collected && ticket < G->step, "tickets are collected in submission order");
+  const int r = (int)(ticket % kRing);
+  for (size_t i = 0; i < G->members.size(); ++i) {
+    Session* s = G->members[i];
+    RYK_CUDA(cudaEventSynchronize(s->ev_dec[r]));
+    const int produced = *s->h_n[r];
+    RYK_CHECK(produced <= out_capacity, "output buffer too small for the produced blocks");
+    memcpy(outs[i], s->h_out[r], sizeof(double) * produced);
+    n_outs[i] = produced;
+    s->collected++;
+  }
+  G->collected++;
+  return 0;
+}
+
+// Device-resident group step, asynchronous (see ryk_session_push_device).
+int ryk_group_push_device(ryk_engine* h, int group_id, const float* const* waves_dev, int n, double* const* outs_dev, int out_capacity,
+                          int* const* n_outs_dev) {
+  Engine* e = &h->impl;
+  RYK_CUDA(cudaSetDevice(e->device));
+  Group* G = get_group(e, group_id);
+  RYK_CHECK(G != nullptr, "no such group");
+  const int r = (int)(G->step % kRing), b = (int)(G->step & 1);
+  for (Session* s : G->members) {
+    RYK_CHECK(n == s->n_wave, "chunk length must be round(fs * buffer_time)");
+    RYK_CHECK(out_capacity >= s->max_blocks * s->cfg.vocoder_buffer_size, "out_capacity must hold (frames * hop / block + 4) synthesizer blocks");
+  }
+  if (group_enqueue(e, G, waves_dev)) return -1;
+  for (size_t i = 0; i < G->members.size(); ++i) {
+    Session* s = G->members[i];
+    const int cap = s->max_blocks * s->cfg.vocoder_buffer_size;
+    RYK_CUDA(cudaMemcpyAsync(outs_dev[i], s->d_out_fixed[b], sizeof(double) * (size_t)cap, cudaMemcpyDeviceToDevice, s->sD));
+    RYK_CUDA(cudaMemcpyAsync(n_outs_dev[i], s->d_n_fixed[b], sizeof(int), cudaMemcpyDeviceToDevice, s->sD));
+    RYK_CUDA(cudaEventRecord(s->ev_dec[r], s->sD));
+    s->collected = s->step;
+  }
+  G->collected = G->step;
   return 0;
 }
 

@@ -57,6 +57,15 @@ void unet_destroy(UNet* n) {
   delete n;
 }
 
+// Drop every plan a destroyed session / group owned (call with its streams idle).
+void unet_release_owner(UNet* n, int owner) {
+  if (!n || owner == 0) return;
+  for (auto it = n->plans.begin(); it != n->plans.end();) {
+    if (std::get<4>(it->first) == owner) { free_plan(it->second); it = n->plans.erase(it); }
+    else ++it;
+  }
+}
+
 // W in the model file's (Chainer) layout: conv (Cout, Cin, k[, k]), deconv (Cin, Cout, k[, k]); host pointers.
 int unet_set_layer(Engine* e, UNet* n, int idx, const float* W, const float* scale, const float* shift) {
   RYK_CHECK(idx >= 0 && idx < 16, "layer index out of range");
@@ -85,9 +94,9 @@ int unet_set_layer(Engine* e, UNet* n, int idx, const float* W, const float* sca
 }
 
 // Plan for a (batch, H, W) input; H = 1 for 1-D nets. precision: 0 = FP32 everywhere, 1 = FP16 activations + tcgen05.
-int unet_get_plan(Engine* e, UNet* n, int B, int H, int W, int precision, UNetPlan** out) {
+int unet_get_plan(Engine* e, UNet* n, int B, int H, int W, int precision, UNetPlan** out, int owner) {
   for (auto& L : n->layers) RYK_CHECK(L.loaded, "U-Net layer weights not loaded");
-  auto key = std::make_tuple(B, H, W, precision);
+  auto key = std::make_tuple(B, H, W, precision, owner);
   auto it = n->plans.find(key);
   if (it != n->plans.end()) { *out = it->second; return 0; }
   RYK_CHECK(W % 128 == 0 && (n->ndim == 1 || H % 128 == 0), "U-Net input extent must be a multiple of 128");

@@ -31,13 +31,16 @@ struct UNetPlan {
 struct UNet {
   int ndim = 2, in_ch = 1, out_ch = 1, base = 64;
   std::vector<UNetLayerW> layers;                                  // 0..7 encoder, 8..15 decoder
-  std::map<std::tuple<int, int, int, int>, UNetPlan*> plans;       // (B, H, W, precision)
+  std::map<std::tuple<int, int, int, int, int>, UNetPlan*> plans;  // (B, H, W, precision, owner)
 };
 
 UNet* unet_create(int ndim, int in_ch, int out_ch, int base);
 void unet_destroy(UNet* n);
 int unet_set_layer(Engine* e, UNet* n, int idx, const float* W, const float* scale, const float* shift);
-int unet_get_plan(Engine* e, UNet* n, int B, int H, int W, int precision, UNetPlan** out);
+// owner: 0 = the engine's shared plans (per-op host API, serialised on the engine stream); every session / group passes its own
+// id so that concurrently running streams never share activation buffers.
+int unet_get_plan(Engine* e, UNet* n, int B, int H, int W, int precision, UNetPlan** out, int owner = 0);
+void unet_release_owner(UNet* n, int owner);
 int unet_forward(Engine* e, UNetPlan* p, cudaStream_t st, int first_layer = 0, int last_layer = 15);
 
 }  // namespace ryk

@@ -6,7 +6,7 @@ import ctypes
 import os
 import threading
 from pathlib import Path
-from typing import Dict, Optional
+from typing import Dict, List, Optional, Sequence
 
 import numpy
 
@@ -46,7 +46,8 @@ EXPORTED_SYMBOLS = [
     'ryk_stage1_set_stats', 'ryk_f0_set_stats', 'ryk_stage1_convert', 'ryk_f0_convert', 'ryk_mc2sp',
     'ryk_stage2_convert', 'ryk_convert_window', 'ryk_synth_create', 'ryk_synth_destroy', 'ryk_synth_add_parameters',
     'ryk_synth_synthesis2', 'ryk_synth_decode', 'ryk_session_create', 'ryk_session_destroy', 'ryk_session_push',
-    'ryk_session_push_device', 'ryk_session_submit', 'ryk_session_collect', 'ryk_test_conv_layer', 'ryk_debug_dio', 'ryk_debug_synth_pulses', 'ryk_debug_synth_timebase', 'ryk_engine_profile', 'ryk_engine_profile_read', 'ryk_engine_timer_start', 'ryk_engine_timer_stop',
+    'ryk_session_push_device', 'ryk_session_submit', 'ryk_session_collect', 'ryk_group_create', 'ryk_group_destroy',
+    'ryk_group_size', 'ryk_group_submit', 'ryk_group_collect', 'ryk_group_push_device', 'ryk_test_conv_layer', 'ryk_debug_dio', 'ryk_debug_synth_pulses', 'ryk_debug_synth_timebase', 'ryk_engine_profile', 'ryk_engine_profile_read', 'ryk_engine_timer_start', 'ryk_engine_timer_stop',
 ]
 
 
@@ -355,6 +356,45 @@ class Engine(object):
     def session_push_device(self, sid: int, wave_dev_ptr: int, n: int, out_dev_ptr: int, out_capacity: int, n_out_dev_ptr: int):
         self._check(self.lib.ryk_session_push_device(self._h, sid, ctypes.c_void_p(wave_dev_ptr), int(n), ctypes.c_void_p(out_dev_ptr),
                                                      int(out_capacity), ctypes.c_void_p(n_out_dev_ptr)))
+
+    # ---- groups (several streams per GPU, one batched stage-2 forward per step) ----
+    def group_create(self, session_ids: Sequence[int]) -> int:
+        ids = (ctypes.c_int * len(session_ids))(*[int(i) for i in session_ids])
+        gid = ctypes.c_int()
+        self._check(self.lib.ryk_group_create(self._h, ids, len(session_ids), ctypes.byref(gid)))
+        return gid.value
+
+    def group_destroy(self, gid: int):
+        self._check(self.lib.ryk_group_destroy(self._h, gid))
+
+    def group_size(self, gid: int) -> int:
+        return self._check(self.lib.ryk_group_size(self._h, gid))
+
+    def group_submit(self, gid: int, waves: Sequence) -> int:
+        ws = [_f32(w) for w in waves]
+        ptrs = (ctypes.POINTER(ctypes.c_float) * len(ws))(*[_fp(w) for w in ws])
+        ticket = ctypes.c_longlong()
+        self._check(self.lib.ryk_group_submit(self._h, gid, ptrs, len(ws[0]), ctypes.byref(ticket)))
+        return ticket.value
+
+    def group_collect(self, gid: int, ticket: int, outs: Sequence[numpy.ndarray]) -> List[numpy.ndarray]:
+        ptrs = (ctypes.POINTER(ctypes.c_double) * len(outs))(*[_dp(o) for o in outs])
+        n_outs = (ctypes.c_int * len(outs))()
+        self._check(self.lib.ryk_group_collect(self._h, gid, ctypes.c_longlong(ticket), ptrs, min(len(o) for o in outs), n_outs))
+        return [o[:n] for o, n in zip(outs, n_outs)]
+
+    def group_push(self, gid: int, waves: Sequence) -> List[numpy.ndarray]:
+        outs = [numpy.empty(len(waves[0]) * 2 + 8192, dtype=numpy.float64) for _ in waves]
+        return self.group_collect(gid, self.group_submit(gid, waves), outs)
+
+    def group_push_device(self, gid: int, wave_dev_ptrs: Sequence[int], n: int, out_dev_ptrs: Sequence[int], out_capacity: int,
+                          n_out_dev_ptrs: Sequence[int]):
+        B = len(wave_dev_ptrs)
+        w = (ctypes.c_void_p * B)(*[int(p) for p in wave_dev_ptrs])
+        o = (ctypes.c_void_p * B)(*[int(p) for p in out_dev_ptrs])
+        c = (ctypes.c_void_p * B)(*[int(p) for p in n_out_dev_ptrs])
+        self._check(self.lib.ryk_group_push_device(self._h, gid, w, int(n), o, int(out_capacity), c))
+
 
 
 _default: Optional[Engine] = None

@@ -275,3 +275,54 @@ def test_pipelined_submit_collect_equals_sequential(engine, small_models):
     assert rmse < 1e-3
     engine.session_destroy(sid)
     engine.set_precision('fp16')
+
+
+def test_group_batched_stage2_matches_oracle_streams(engine, small_models):
+    """BASELINE config 5 shape: several streams on one GPU share ONE batched stage-2 forward per step (ryk_group_*).
+    Each member must still reproduce the oracle's chunked stream for ITS audio (fp32), with chunks kept in flight,
+    and the fp16 (tcgen05) group must stay within the end-to-end tolerance."""
+    from realtime_yukarin_b200.engine import SessionConfig
+    ac, sr, f0c = _load(engine, small_models)
+    p1, p2 = onets.load_npz(small_models['stage1_model_path']), onets.load_npz(small_models['stage2_model_path'])
+    T, extra, B = 0.3, (0.0, 0.5, 0.0), 3
+    cfg = SessionConfig(fs=24000, frame_period_ms=5.0, f0_floor=71.0, f0_ceil=800.0, fft_length=1024, order=8, alpha=0.466,
+                        buffer_time=T, encode_extra_time=extra[0], convert_extra_time=extra[1], decode_extra_time=extra[2],
+                        threshold_db=60.0, vocoder_buffer_size=1024)
+    n = round(T * 24000)
+    xs = [_speech(2.4, 70 + i) for i in range(B)]
+    xs[1] = xs[1] * np.concatenate([np.zeros(12000), np.ones(len(xs[1]) - 12000)]).astype(np.float32)   # a stream that starts silent
+    nchunks = len(xs[0]) // n
+    refs = []
+    for i in range(B):
+        orc = opipe.StreamOracle(CFG, p1, p2, f0c.stats(), buffer_time=T, extra=extra, backend='torch')
+        refs.append([orc.push(xs[i][k * n:(k + 1) * n]) for k in range(nchunks)])
+    for precision, tol in (('fp32', 1e-3), ('fp16', 1e-3)):
+        engine.set_precision(precision)
+        sids = [engine.session_create(cfg) for _ in range(B)]
+        gid = engine.group_create(sids)
+        assert engine.group_size(gid) == B
+        with pytest.raises(Exception):
+            engine.session_push(sids[0], xs[0][:n])            # members are driven through the group only
+        bufs = [[np.empty(32768) for _ in range(B)] for _ in range(8)]
+        tickets, outs = [], [[] for _ in range(B)]
+
+        def collect():
+            t = tickets.pop(0)
+            for i, o in enumerate(engine.group_collect(gid, t, bufs[t % 8])):
+                outs[i].append(o.copy())
+        for k in range(nchunks):
+            tickets.append(engine.group_submit(gid, [x[k * n:(k + 1) * n] for x in xs]))
+            if len(tickets) > 3:
+                collect()
+        while tickets:
+            collect()
+        for i in range(B):
+            assert [len(o) for o in outs[i]] == [len(r) for r in refs[i]], i
+            y, r = np.concatenate(outs[i]), np.concatenate(refs[i])
+            rmse = float(np.sqrt(np.mean((y - r) ** 2)))
+            print(f'group {precision} member {i}: {len(y)} samples rmse {rmse:.3e} signal rms {float(np.sqrt(np.mean(r ** 2))):.3e}')
+            assert rmse < tol
+        engine.group_destroy(gid)
+        for sid in sids:
+            engine.session_destroy(sid)
+    engine.set_precision('fp16')

@@ -1,2 +1,1 @@
-timeout 600 python -m pytest tests/test_gpu_conv_layers.py -x -q 2>&1 | tail -5
-timeout 300 python tools/gpu_bench_layers.py 2>&1 | tail -4
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "group or pipelined or device_session" 2>&1 | tail -15
