@@ -651,9 +651,22 @@ int ryk_test_conv_layer(ryk_engine* h, int transposed, int k, int stride, int pa
     if (ws) L.splitk_ws = (float*)A(ws);
     if (tc_layer_prepare(L, num_sms)) return -1;
     rc = conv_tc_run(L, st);
-    RYK_CUDA(cudaEventRecord(ev0, st));
-    for (int i = 0; i < repeat && !rc; ++i) rc = conv_tc_run(L, st);
-    RYK_CUDA(cudaEventRecord(ev1, st));
+    if (!rc && repeat > 0) {
+      // time `repeat` runs replayed from a CUDA graph (as the session runs them): no host launch overhead in the figure
+      cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+      RYK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      for (int i = 0; i < repeat && !rc; ++i) rc = conv_tc_run(L, st);
+      cudaError_t err = cudaStreamEndCapture(st, &graph);
+      if (rc) return rc;
+      RYK_CUDA(err);
+      RYK_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+      RYK_CUDA(cudaGraphLaunch(exec, st));
+      RYK_CUDA(cudaEventRecord(ev0, st));
+      RYK_CUDA(cudaGraphLaunch(exec, st));
+      RYK_CUDA(cudaEventRecord(ev1, st));
+      RYK_CUDA(cudaStreamSynchronize(st));
+      cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+    }
     k_f16_to_f32<<<1184, 256, 0, st>>>(d_ho, d_out, no);
   } else if (use_tc == 2) {
     // mixed-precision edge layers as the fp16 U-Net plan runs them: Cin = 1 reads fp32 / writes fp16, Cout = 1 reads fp16 / writes fp32

@@ -3,7 +3,7 @@
 set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -Wno-unused-variable --expt-relaxed-constexpr"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -Wno-unused-variable --expt-relaxed-constexpr $RYK_NVCC_EXTRA"
 mkdir -p _obj
 SRCS="api conv_direct conv_tc unet world_analysis world_synth features convert session"
 pids=""
@@ -15,5 +15,7 @@ for s in $SRCS; do
 done
 for p in $pids; do wait $p; done
 OBJS=""; for s in $SRCS; do OBJS="$OBJS _obj/$s.o"; done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libryk.so $OBJS -L/usr/local/cuda/lib64 -lcufft -Xlinker -rpath -Xlinker /usr/local/cuda/lib64
-echo "built $(pwd)/libryk.so"
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ${RYK_LIB_OUT:-libryk.so} $OBJS -L/usr/local/cuda/lib64 -lcufft -Xlinker -rpath -Xlinker /usr/local/cuda/lib64
+OUT=${RYK_LIB_OUT:-libryk.so}
+
+echo "built $(pwd)/${RYK_LIB_OUT:-libryk.so}"

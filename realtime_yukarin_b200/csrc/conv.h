@@ -30,7 +30,7 @@ struct ConvLayer {
   const __half* w_tc = nullptr;           // conv: [Cout][KH*KW*Cin]; deconv: [4 classes][Cout][4*Cin]
   float* splitk_ws = nullptr;             // [pixels][Cout] fp32 when ksplit > 1
   int ksplit = 1;
-  CUtensorMap tmA0, tmA1, tmB, tmO;
+  CUtensorMap tmA0, tmA1, tmB, tmO, tmW;     // inputs, weights, fp16 output, fp32 split-K workspace
   int tile_w = 0, tile_h = 0;             // pixel tile = tile_w x tile_h = 128
   int block_n = 0;
   bool tc_ready = false;

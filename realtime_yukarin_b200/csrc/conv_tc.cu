@@ -24,6 +24,8 @@
 #include <cudaTypedefs.h>
 #include <stdlib.h>
 
+#include <vector>
+#include <stdio.h>
 #include "conv.h"
 
 namespace ryk {
@@ -100,10 +102,21 @@ struct TcParams {
   int debug;                     // RYK_TC_DEBUG bit 1 (perf experiments only): skip the output stores
 };
 
+#ifdef RYK_TC_TIMELINE
+// diagnostics build only (RYK_NVCC_EXTRA=-DRYK_TC_TIMELINE): per-CTA phase timestamps of the non-persistent kernel
+constexpr int kTlMaxCtas = 8192, kTlSlots = 10;
+__device__ unsigned long long g_tl[kTlMaxCtas * kTlSlots];
+__device__ __forceinline__ unsigned long long tl_now() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define TL(slot) do { int c_ = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z); if (c_ < kTlMaxCtas) g_tl[c_ * kTlSlots + (slot)] = tl_now(); } while (0)
+#else
+#define TL(slot) do {} while (0)
+#endif
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar);
 template <int BLOCK_N, int kStages, int kMinBlocks>
 __global__ void __launch_bounds__(kTcThreads, kMinBlocks)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-          const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+          const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmW,
+          const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
   constexpr uint32_t kBBytes = BLOCK_N * kBlockK * 2;
@@ -115,8 +128,19 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint32_t* tmem_ptr_smem = (uint32_t*)(tmem_full_bar + 1);
+  // per-channel scale / shift of this CTA's BLOCK_N output channels, staged once: the epilogue reads them as broadcast
+  // LDS.128 (reading them with __ldg per element cost 128 LSU instructions per 32 columns and made the epilogue
+  // longer than the MMA main loop)
+  float* s_scale = (float*)(((uintptr_t)(tmem_ptr_smem + 4) + 15) & ~(uintptr_t)15);
+  float* s_shift = s_scale + BLOCK_N;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    TL(0);
+#ifdef RYK_TC_TIMELINE
+    { unsigned sm; asm volatile("mov.u32 %0, %smid;" : "=r"(sm)); int c_ = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z); if (c_ < kTlMaxCtas) g_tl[c_ * kTlSlots + 9] = sm; }
+#endif
+  }
 
   // tile coordinates
   int mt = blockIdx.x;
@@ -137,11 +161,16 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     if (p.chunks1 > 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
+    if (!p.ws) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
+    else asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
   }
   if (threadIdx.x == 160) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp < 4 && !p.ws) {
+    for (int i = threadIdx.x; i < BLOCK_N; i += 128) { s_scale[i] = __ldg(p.scale + n0 + i); s_shift[i] = __ldg(p.shift + n0 + i); }
   }
   if (warp == 4) {   // TMEM allocation (whole warp), BLOCK_N fp32 accumulator columns
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)BLOCK_N) : "memory");
@@ -151,6 +180,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (threadIdx.x == 0) TL(1);
 
   if (warp == 4 && lane == 0) {
     // ===== TMA producer =====
@@ -168,10 +198,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
         ix = p.sw == 2 ? ox0 + tx - 1 + px : ox0;
         iy = p.sh == 2 ? oy0 + ty - 1 + py : oy0;
       }
-      mbar_expect_tx(&full_bar[s], kABytes + kBBytes);
+      const bool ldA = !(p.debug & 2) || i < kStages, ldB = !(p.debug & 4) || i < kStages;   // XXEXP
+      mbar_expect_tx(&full_bar[s], (ldA ? kABytes : 0) + (ldB ? kBBytes : 0));
+      if (ldA) {
       if (cc < p.chunks0) tma_load_4d(smem_a + s * kABytes, &tmA0, &full_bar[s], cc * kBlockK, ix, iy, b);
       else tma_load_4d(smem_a + s * kABytes, &tmA1, &full_bar[s], (cc - p.chunks0) * kBlockK, ix, iy, b);
-      tma_load_2d(smem_b + s * kBBytes, &tmB, &full_bar[s], kc * kBlockK, cls * p.Cout + n0);
+      }
+      if (ldB) tma_load_2d(smem_b + s * kBBytes, &tmB, &full_bar[s], kc * kBlockK, cls * p.Cout + n0);
     }
   } else if (warp == 5 && lane == 0) {
     // ===== MMA issuer =====
@@ -181,6 +214,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
       const int s = i % kStages;
       const uint32_t ph = (i / kStages) & 1;
       mbar_wait(&full_bar[s], ph);
+      if (i == 0) TL(2);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint64_t adesc = make_sw128_desc(smem_u32(smem_a + s * kABytes));
       const uint64_t bdesc = make_sw128_desc(smem_u32(smem_b + s * kBBytes));
@@ -192,9 +226,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
       umma_commit(&empty_bar[s]);
     }
     umma_commit(tmem_full_bar);
+    TL(3);
   } else if (warp < 4) {
     // ===== epilogue =====
     mbar_wait(tmem_full_bar, 0);
+    if (threadIdx.x == 0) TL(4);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int row = warp * 32 + lane;                 // accumulator row == TMEM lane == pixel of the tile
     const int hl = row / p.tile_w, wl = row - hl * p.tile_w;
@@ -217,38 +253,81 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
             "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (valid) {
+      {
         const int n = n0 + c0;
         if (p.ws) {
-          // split-K partial tile: plain (deterministic) stores into this split's slice; k_splitk_reduce sums the slices
-          float4* w = reinterpret_cast<float4*>(p.ws + ((size_t)split * p.out_pixels + pix) * p.Cout + n);
+          // split-K partial tile (raw FP32 sums) -> swizzled staging, one [128 pixels][32 channels] block per iteration;
+          // stored below by TMA into this split's slice of the workspace; k_splitk_reduce sums the slices
+          uint8_t* blk = smem + (c0 >> 5) * (kBlockM * 128) + row * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            w[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+            *reinterpret_cast<uint4*>(blk + ((j ^ (row & 7)) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
         } else {
-          __half* o = p.out + pix * p.Cout + n;
+          // scale/shift/activation -> FP16 -> 128B-swizzled staging tile in the (now idle) pipeline stage buffers:
+          // BLOCK_N / 64 blocks of [128 pixels][64 channels]; one TMA store per block writes full 128-byte rows
+          uint8_t* blk = smem + (c0 >> 6) * (kBlockM * 128) + row * 128;
+          const int cbase = (c0 & 32) >> 3;          // first 16-byte chunk of this 32-channel half inside the block: 0 or 4
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
+            const float4 sc0 = *reinterpret_cast<const float4*>(s_scale + c0 + j), sc1 = *reinterpret_cast<const float4*>(s_scale + c0 + j + 4);
+            const float4 sh0 = *reinterpret_cast<const float4*>(s_shift + c0 + j), sh1 = *reinterpret_cast<const float4*>(s_shift + c0 + j + 4);
+            const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+            const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
             uint32_t pk[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              float v0 = __uint_as_float(r[j + 2 * q]) * __ldg(p.scale + n + j + 2 * q) + __ldg(p.shift + n + j + 2 * q);
-              float v1 = __uint_as_float(r[j + 2 * q + 1]) * __ldg(p.scale + n + j + 2 * q + 1) + __ldg(p.shift + n + j + 2 * q + 1);
+              float v0 = fmaf(__uint_as_float(r[j + 2 * q]), sc[2 * q], sh[2 * q]);
+              float v1 = fmaf(__uint_as_float(r[j + 2 * q + 1]), sc[2 * q + 1], sh[2 * q + 1]);
               if (p.act == ACT_LEAKY) { v0 = v0 > 0.f ? v0 : 0.2f * v0; v1 = v1 > 0.f ? v1 : 0.2f * v1; }
               else if (p.act == ACT_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
               __half2 h = __floats2half2_rn(v0, v1);
               pk[q] = *reinterpret_cast<uint32_t*>(&h);
             }
-            *reinterpret_cast<uint4*>(o + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            const int chunk = cbase + (j >> 3);
+            *reinterpret_cast<uint4*>(blk + ((chunk ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
         }
       }
     }
+    if (!p.ws && my_chunks > 0) {
+      // generic-proxy smem writes -> visible to the async proxy; one thread hands the tile to the TMA unit
+      // (out-of-range pixels are clipped by the tensor map, so no masking is needed)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 0 && !(p.debug & 1)) {
+        const int xs = p.transposed ? ox0 * p.sw + px : ox0;
+        const int ys = p.transposed ? oy0 * p.sh + py : oy0;
+#pragma unroll
+        for (int jb = 0; jb < BLOCK_N / 64; ++jb) {
+          asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                       ::"l"(&tmO), "r"(smem_u32(smem + jb * (kBlockM * 128))), "r"(n0 + jb * 64), "r"(xs), "r"(ys), "r"(b) : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      }
+    }
+    if (p.ws && my_chunks > 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 0 && !(p.debug & 1)) {
+        const int xs = p.transposed ? ox0 * p.sw + px : ox0;
+        const int ys = p.transposed ? oy0 * p.sh + py : oy0;
+#pragma unroll
+        for (int jb = 0; jb < BLOCK_N / 32; ++jb) {
+          asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                       ::"l"(&tmW), "r"(smem_u32(smem + jb * (kBlockM * 128))), "r"(n0 + jb * 32), "r"(xs), "r"(ys), "r"(b), "r"(split) : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      }
+    }
   }
+  if (threadIdx.x == 0) TL(5);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 4) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BLOCK_N) : "memory");
+    if (lane == 0) TL(6);
   }
 }
 
@@ -285,6 +364,8 @@ k_conv_tc_persist(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   uint64_t* tfull_bar = empty_bar + kStages;      // [2]
   uint64_t* tempty_bar = tfull_bar + 2;            // [2]
   uint32_t* tmem_ptr_smem = (uint32_t*)(tempty_bar + 2);
+  float* s_scale = (float*)(((uintptr_t)(tmem_ptr_smem + 4) + 15) & ~(uintptr_t)15);    // scale / shift of the current tile's channels (see k_conv_tc)
+  float* s_shift = s_scale + BLOCK_N;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 128) {
@@ -411,6 +492,7 @@ k_conv_tc_persist(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         if (!p.ws) {
           // the previous TMA store must have finished reading the staging buffer before it is overwritten
           if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          if (h == 0) for (int i = threadIdx.x; i < BLOCK_N; i += 128) { s_scale[i] = __ldg(p.scale + n0 + i); s_shift[i] = __ldg(p.shift + n0 + i); }
           asm volatile("bar.sync 1, 128;" ::: "memory");
         }
 #pragma unroll 1
@@ -446,11 +528,15 @@ k_conv_tc_persist(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             const int cbase = (c0 & 32) >> 3;          // first 16-byte chunk of this 32-channel half inside the block: 0 or 4
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
+              const float4 sc0 = *reinterpret_cast<const float4*>(s_scale + c0 + j), sc1 = *reinterpret_cast<const float4*>(s_scale + c0 + j + 4);
+              const float4 sh0 = *reinterpret_cast<const float4*>(s_shift + c0 + j), sh1 = *reinterpret_cast<const float4*>(s_shift + c0 + j + 4);
+              const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+              const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
               uint32_t pk[4];
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                float v0 = __uint_as_float(r[j + 2 * q]) * __ldg(p.scale + n + j + 2 * q) + __ldg(p.shift + n + j + 2 * q);
-                float v1 = __uint_as_float(r[j + 2 * q + 1]) * __ldg(p.scale + n + j + 2 * q + 1) + __ldg(p.shift + n + j + 2 * q + 1);
+                float v0 = fmaf(__uint_as_float(r[j + 2 * q]), sc[2 * q], sh[2 * q]);
+                float v1 = fmaf(__uint_as_float(r[j + 2 * q + 1]), sc[2 * q + 1], sh[2 * q + 1]);
                 if (p.act == ACT_LEAKY) { v0 = v0 > 0.f ? v0 : 0.2f * v0; v1 = v1 > 0.f ? v1 : 0.2f * v1; }
                 else if (p.act == ACT_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
                 __half2 h2 = __floats2half2_rn(v0, v1);
@@ -488,23 +574,58 @@ k_conv_tc_persist(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   }
 }
 
-// split-K reduce + epilogue: out = act((sum over splits of ws[s]) * scale + shift) as fp16, 4 channels per thread
-__global__ void k_splitk_reduce(const float* __restrict__ ws, size_t total4, size_t slice_elems, int ksplit, int Cout,
+// split-K reduce + epilogue: out = act((sum over splits of ws[s]) * scale + shift) as fp16, 4 channels per thread.
+// Block = G warps x 32 lanes: lane = one float4 of the output (512 contiguous bytes per warp load), warp g sums the
+// slices g, g + G, g + 2G, ... ; the G partial sums are combined through shared memory in a fixed order, so the result
+// is deterministic (same summation tree every run) while G x more loads are in flight than with one thread per output.
+__global__ void __launch_bounds__(256) k_splitk_reduce(const float* __restrict__ ws, size_t total4, size_t slice_elems, int ksplit, int Cout,
                                 const float* __restrict__ scale, const float* __restrict__ shift, int act, __half* __restrict__ out) {
+  __shared__ float4 part[8][32];
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5, G = blockDim.x >> 5;
+  const size_t i = (size_t)blockIdx.x * 32 + lane;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < total4) {
+    const float4* p = reinterpret_cast<const float4*>(ws) + i;
+    const size_t stride4 = slice_elems / 4;
+#pragma unroll 4
+    for (int s = g; s < ksplit; s += G) {
+      const float4 b = __ldg(p + (size_t)s * stride4);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+  }
+  part[g][lane] = a;
+  __syncthreads();
+  if (g != 0 || i >= total4) return;
+  for (int k = 1; k < G; ++k) { const float4 b = part[k][lane]; a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+  const int n = (int)((i * 4) % Cout);
+  const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + n)), sh = __ldg(reinterpret_cast<const float4*>(shift + n));
+  float v[4] = {fmaf(a.x, sc.x, sh.x), fmaf(a.y, sc.y, sh.y), fmaf(a.z, sc.z, sh.z), fmaf(a.w, sc.w, sh.w)};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (act == ACT_LEAKY) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j]; else if (act == ACT_RELU) v[j] = fmaxf(v[j], 0.f);
+  }
+  __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+  reinterpret_cast<uint2*>(out)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+}
+
+// few splits, large outputs (c3 / c4 / d3): one thread per float4 of the output, grid-stride, all slices summed in order
+__global__ void __launch_bounds__(256) k_splitk_reduce_few(const float* __restrict__ ws, size_t total4, size_t slice_elems, int ksplit, int Cout,
+                                    const float* __restrict__ scale, const float* __restrict__ shift, int act, __half* __restrict__ out) {
+  const size_t stride4 = slice_elems / 4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
     const float4* p = reinterpret_cast<const float4*>(ws) + i;
     float4 a = __ldg(p);
+#pragma unroll 4
     for (int s = 1; s < ksplit; ++s) {
-      float4 b = __ldg(p + (size_t)s * (slice_elems / 4));
+      const float4 b = __ldg(p + (size_t)s * stride4);
       a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
     }
-    int n = (int)((i * 4) % Cout);
-    float v[4] = {a.x, a.y, a.z, a.w};
+    const int n = (int)((i * 4) % Cout);
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + n)), sh = __ldg(reinterpret_cast<const float4*>(shift + n));
+    float v[4] = {fmaf(a.x, sc.x, sh.x), fmaf(a.y, sc.y, sh.y), fmaf(a.z, sc.z, sh.z), fmaf(a.w, sc.w, sh.w)};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float t = v[j] * __ldg(scale + n + j) + __ldg(shift + n + j);
-      if (act == ACT_LEAKY) t = t > 0.f ? t : 0.2f * t; else if (act == ACT_RELU) t = fmaxf(t, 0.f);
-      v[j] = t;
+      if (act == ACT_LEAKY) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j]; else if (act == ACT_RELU) v[j] = fmaxf(v[j], 0.f);
     }
     __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
     reinterpret_cast<uint2*>(out)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
@@ -515,7 +636,7 @@ __global__ void k_splitk_reduce(const float* __restrict__ ws, size_t total4, siz
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 
 template <int BN, int ST> static constexpr size_t tc_smem_bytes() {
-  return (size_t)ST * (kBlockM * kBlockK * 2 + BN * kBlockK * 2) + (2 * ST + 1) * 8 + 16 + 1024;
+  return (size_t)ST * (kBlockM * kBlockK * 2 + BN * kBlockK * 2) + (2 * ST + 1) * 8 + 16 + 1024 + 2 * BN * 4 + 32;
 }
 
 // kernel variants: (BLOCK_N, stages, CTAs/SM). Two co-resident CTAs let one tile's epilogue overlap the other's main loop.
@@ -526,7 +647,7 @@ static int tc_variant() {
 }
 
 template <int BN, int ST, int MT> static constexpr size_t tcp_smem_bytes() {
-  return (size_t)ST * (MT * kBlockM * kBlockK * 2 + BN * kBlockK * 2) + (size_t)kBlockM * BN * 2 + (2 * ST + 4) * 8 + 16 + 1024;
+  return (size_t)ST * (MT * kBlockM * kBlockK * 2 + BN * kBlockK * 2) + (size_t)kBlockM * BN * 2 + (2 * ST + 4) * 8 + 16 + 1024 + 2 * BN * 4 + 32;
 }
 
 int tc_init() {
@@ -576,6 +697,20 @@ static int make_act_map(CUtensorMap* m, const void* ptr, int C, int W, int H, in
   return 0;
 }
 
+// split-K workspace [ksplit][B][Hout][Wout][Cout] fp32 as a 5-D map: box = (32 channels, tile_w, tile_h, 1, 1) with the same
+// W / H element strides as the output map (deconv parity classes write every other pixel)
+static int make_ws_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int B, int ksplit, int box_w, int box_h, int stride_w, int stride_h) {
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, (cuuint64_t)ksplit};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4, (cuuint64_t)B * H * W * C * 4};
+  cuuint32_t box[5] = {32, (cuuint32_t)(box_w * stride_w), (cuuint32_t)(box_h * stride_h), 1, 1};
+  cuuint32_t estr[5] = {1, (cuuint32_t)stride_w, (cuuint32_t)stride_h, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(split-K workspace) failed: " + std::to_string((int)r)); return -1; }
+  return 0;
+}
+
 static int make_weight_map(CUtensorMap* m, const void* ptr, size_t K, size_t rows, int block_n) {
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)K * 2};
@@ -594,7 +729,7 @@ static void tc_geometry(const ConvLayer& L, int num_sms, int* tile_w, int* tile_
   int tw = pow2_floor(Wc < kBlockM ? Wc : kBlockM);
   int th = kBlockM / tw;
   int bn = L.Cout >= 256 ? 256 : (L.Cout >= 128 ? 128 : 64);
-  if (tc_variant() == 1 && bn == 256) bn = 128;        // variant 1: N <= 128 tiles, 3 stages, 2 CTAs/SM
+  if ((tc_variant() == 1 || tc_variant() == 2) && bn == 256) bn = 128;   // non-persistent 2-CTAs/SM kernels: N <= 128 tiles (the epilogue staging must fit the stage buffers)
   if (tc_variant() == 4 && bn == 256) bn = 128;        // variant 4: persistent with N <= 128
   int classes = L.transposed ? L.SH * L.SW : 1;
   int tiles_mn_ = L.B * ((Wc + tw - 1) / tw) * ((Hc + th - 1) / th);
@@ -606,7 +741,9 @@ static void tc_geometry(const ConvLayer& L, int num_sms, int* tile_w, int* tile_
   int slots = num_sms * ((tc_variant() == 0 || tc_variant() >= 3) ? 1 : 2);
   if (tiles < slots) {
     ks = slots / tiles;
-    if (ks > total_chunks / 2) ks = total_chunks / 2;   // at least 2 chunks per split
+    static int min_chunks = -1;
+    if (min_chunks < 0) { const char* v = getenv("RYK_TC_MIN_CHUNKS"); min_chunks = v ? atoi(v) : 8; if (min_chunks < 1) min_chunks = 1; }
+    if (ks > total_chunks / min_chunks) ks = total_chunks / min_chunks;   // at least min_chunks chunks per split
     if (ks < 1) ks = 1;
     int cps = (total_chunks + ks - 1) / ks;
     ks = (total_chunks + cps - 1) / cps;                // every split owns at least one chunk
@@ -636,6 +773,9 @@ int tc_layer_prepare(ConvLayer& L, int num_sms) {
   // output map for the TMA-store epilogue: deconv classes write every other pixel (element strides = conv strides)
   if (make_act_map(&L.tmO, L.out, L.Cout, L.Wout, L.Hout, L.B, L.tile_w, L.tile_h, L.transposed ? L.SW : 1, L.transposed ? L.SH : 1)) return -1;
   RYK_CHECK(L.ksplit == 1 || L.splitk_ws != nullptr, "split-K layer without a workspace");
+  if (L.ksplit > 1) {
+    if (make_ws_map(&L.tmW, L.splitk_ws, L.Cout, L.Wout, L.Hout, L.B, L.ksplit, L.tile_w, L.tile_h, L.transposed ? L.SW : 1, L.transposed ? L.SH : 1)) return -1;
+  } else L.tmW = L.tmO;
   L.tc_ready = true;
   return 0;
 }
@@ -678,19 +818,38 @@ int conv_tc_run(const ConvLayer& L, cudaStream_t st) {
     else if (L.block_n == 128) k_conv_tc_persist<128, 6, 1><<<ctas, kTcThreads, tcp_smem_bytes<128, 6, 1>(), st>>>(L.tmA0, L.tmA1, L.tmB, L.tmO, p, tiles_mn, n_tiles_n, total_tiles);
     else k_conv_tc_persist<64, 8, 1><<<ctas, kTcThreads, tcp_smem_bytes<64, 8, 1>(), st>>>(L.tmA0, L.tmA1, L.tmB, L.tmO, p, tiles_mn, n_tiles_n, total_tiles);
   } else if (variant == 0) {
-    if (L.block_n == 256) k_conv_tc<256, 4, 1><<<grid, kTcThreads, tc_smem_bytes<256, 4>(), st>>>(L.tmA0, L.tmA1, L.tmB, p);
-    else if (L.block_n == 128) k_conv_tc<128, 6, 1><<<grid, kTcThreads, tc_smem_bytes<128, 6>(), st>>>(L.tmA0, L.tmA1, L.tmB, p);
-    else k_conv_tc<64, 6, 1><<<grid, kTcThreads, tc_smem_bytes<64, 6>(), st>>>(L.tmA0, L.tmA1, L.tmB, p);
+    if (L.block_n == 256) k_conv_tc<256, 4, 1><<<grid, kTcThreads, tc_smem_bytes<256, 4>(), st>>>(L.tmA0, L.tmA1, L.tmB, L.tmO, L.tmW, p);
+    else if (L.block_n == 128) k_conv_tc<128, 6, 1><<<grid, kTcThreads, tc_smem_bytes<128, 6>(), st>>>(L.tmA0, L.tmA1, L.tmB, L.tmO, L.tmW, p);
+    else k_conv_tc<64, 6, 1><<<grid, kTcThreads, tc_smem_bytes<64, 6>(), st>>>(L.tmA0, L.tmA1, L.tmB, L.tmO, L.tmW, p);
   } else {
-    if (L.block_n == 256) k_conv_tc<256, 2, 2><<<grid, kTcThreads, tc_smem_bytes<256, 2>(), st>>>(L.tmA0, L.tmA1, L.tmB, p);
-    else if (L.block_n == 128) k_conv_tc<128, 3, 2><<<grid, kTcThreads, tc_smem_bytes<128, 3>(), st>>>(L.tmA0, L.tmA1, L.tmB, p);
-    else k_conv_tc<64, 4, 2><<<grid, kTcThreads, tc_smem_bytes<64, 4>(), st>>>(L.tmA0, L.tmA1, L.tmB, p);
+    if (L.block_n == 256) k_conv_tc<256, 2, 2><<<grid, kTcThreads, tc_smem_bytes<256, 2>(), st>>>(L.tmA0, L.tmA1, L.tmB, L.tmO, L.tmW, p);
+    else if (L.block_n == 128) k_conv_tc<128, 3, 2><<<grid, kTcThreads, tc_smem_bytes<128, 3>(), st>>>(L.tmA0, L.tmA1, L.tmB, L.tmO, L.tmW, p);
+    else k_conv_tc<64, 4, 2><<<grid, kTcThreads, tc_smem_bytes<64, 4>(), st>>>(L.tmA0, L.tmA1, L.tmB, L.tmO, L.tmW, p);
   }
   RYK_CUDA(cudaGetLastError());
+#ifdef RYK_TC_TIMELINE
+  cudaStreamCaptureStatus cap_ = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cap_);
+  if (const char* path = cap_ == cudaStreamCaptureStatusNone ? getenv("RYK_TC_TIMELINE_FILE") : nullptr) {
+    cudaStreamSynchronize(st);
+    static std::vector<unsigned long long> h(kTlMaxCtas * kTlSlots);
+    cudaMemcpyFromSymbol(h.data(), g_tl, sizeof(unsigned long long) * h.size());
+    int n = grid.x * grid.y * grid.z; if (n > kTlMaxCtas) n = kTlMaxCtas;
+    if (FILE* f = fopen(path, "w")) {
+      fprintf(f, "# grid %d %d %d block_n %d ksplit %d\n", grid.x, grid.y, grid.z, L.block_n, L.ksplit);
+      for (int c = 0; c < n; ++c) { for (int k = 0; k < kTlSlots; ++k) fprintf(f, "%llu ", h[c * kTlSlots + k]); fprintf(f, "\n"); }
+      fclose(f);
+    }
+  }
+#endif
   if (p.ws) {
     size_t total4 = out_elems / 4;
-    int blocks = (int)((total4 + 255) / 256); if (blocks > 1184) blocks = 1184;
-    k_splitk_reduce<<<blocks, 256, 0, st>>>(p.ws, total4, out_elems, L.ksplit, L.Cout, L.scale, L.shift, L.act, (__half*)L.out);
+    if (L.ksplit <= 4) {
+      int blocks = (int)((total4 + 255) / 256); if (blocks > 2368) blocks = 2368;
+      k_splitk_reduce_few<<<blocks, 256, 0, st>>>(p.ws, total4, out_elems, L.ksplit, L.Cout, L.scale, L.shift, L.act, (__half*)L.out);
+    } else {
+      k_splitk_reduce<<<(unsigned)((total4 + 31) / 32), 256, 0, st>>>(p.ws, total4, out_elems, L.ksplit, L.Cout, L.scale, L.shift, L.act, (__half*)L.out);
+    }
     RYK_CUDA(cudaGetLastError());
   }
   return 0;
