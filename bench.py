@@ -269,8 +269,12 @@ def run_gpu(args):
     eng.profile(True)
     eng.timer_start()
     t_host0 = time.perf_counter()
+    trace = []
     for k in range(args.warmup, total):
         push_dev(k)
+        trace.append(time.perf_counter())
+    if os.environ.get('RYK_BENCH_TRACE') == '1':
+        print('host us per push:', [round((b - a) * 1e6) for a, b in zip([t_host0] + trace[:-1], trace)], file=sys.stderr)
     t_host = time.perf_counter() - t_host0          # host time to queue the K steps (launch overhead view)
     t_dev = eng.timer_stop() * 1e-3          # CUDA events on the stream the kernels are launched on
     barrier()
@@ -279,6 +283,11 @@ def run_gpu(args):
     clocks = sampler.stop()
     launches = eng.launch_count - launches0
     t_dev = max_over_ranks(t_dev)
+    stage_times = None
+    if os.environ.get('RYK_STAGE_TIMES') == '1':       # diagnostics: device time of each stage of the last pipelined step
+        st, en = eng.session_stage_times(sids[0])
+        stage_times = dict(stages=['gate_slides', 'world_analysis', 'stage1', 'stage2', 'synthesis'],
+                           start_ms=np.round(st, 3).tolist(), end_ms=np.round(en, 3).tolist())
     free_streams(sids, gid)
 
     # ---- leg 2: end to end with host buffers ("e2e") ----
@@ -347,6 +356,8 @@ def run_gpu(args):
                       unit='TFLOP/s', frac=(ach / peaks['tflops']) if ach else None, traffic=None, peak_source=peaks['source'],
                       flop_per_step=fl, ms_per_step_in_kernel=(s2_ms / s2_runs) if s2_runs else None),
     )
+    if stage_times is not None:
+        line['stage_timeline'] = stage_times
     if cpu_rate is not None:
         line['cpu_baseline'] = dict(value=cpu_rate, unit='chunks/s', cores=cores, kind='port',
                                     sample='3 chunks of 0.3 s after a warm-up chunk, C WORLD/SPTK restatement + torch-CPU U-Nets, same models/audio')

@@ -139,6 +139,10 @@ int ryk_session_collect(ryk_engine* e, int session_id, long long ticket, double*
 int ryk_session_push_device(ryk_engine* e, int session_id, const float* wave_dev, int n, double* out_dev, int out_capacity,
                             int* n_out_dev);
 
+/* Diagnostics: device timeline (ms) of the last <= 8 steps x 5 stages {gate, analysis, stage 1, stage 2, synthesis}; needs
+ * RYK_STAGE_TIMES=1 in the environment at session creation.  start/end hold 40 floats; returns the number of steps. */
+int ryk_session_stage_times(ryk_engine* e, int session_id, float* start, float* end);
+
 /* ---- session groups: several streams of one GPU sharing one batched stage-2 forward -------------------
  * BASELINE config 5 / SURVEY 8(e) "per-GPU batch = streams resident on it": the reference would run one
  * SuperResolution.convert (voice_changer.py:41) per stream; a group stacks the members' padded log-spectrograms into

@@ -39,6 +39,8 @@ constexpr int kRing = 8;          // event / output-slot ring (pipeline depth is
 struct StageGraph { cudaGraphExec_t exec = nullptr; long long launches = 0; };
 struct Group;
 struct Session {
+  // optional per-stage device timing (RYK_STAGE_TIMES=1): [stage E1,E2,S1,S2,D][begin/end][ring]
+  cudaEvent_t tev[5][2][kRing]; bool stage_times = false;
   int owner = 0;                               // plan-cache owner id (activation buffers are private to the session)
   float* d_colmin = nullptr;
   Group* group = nullptr; int slot = 0;        // member of a batched stage-2 group (config 5), else nullptr
@@ -48,7 +50,9 @@ struct Session {
   int Lw, Tw, Td, nb, C;
   long long step = 0;              // chunks submitted
   long long collected = 0;         // chunks collected through the host API
-  cudaStream_t sE = nullptr, sC = nullptr, sC2 = nullptr, sD = nullptr;     // encode | stage 1 | stage 2 | decode
+  cudaStream_t sE = nullptr, sC = nullptr, sC2 = nullptr, sD = nullptr;     // gate | stage 1 | stage 2 | decode
+  cudaStream_t sA[2] = {nullptr, nullptr};   // WORLD analysis of even / odd chunks: two chunks' analyses may be in flight
+  cudaEvent_t ev_gate[kRing];
   cudaEvent_t ev_count[kRing], ev_enc[kRing], ev_cslide[kRing], ev_s1[kRing], ev_conv[kRing], ev_dslide[kRing], ev_dec[kRing];
   // sliding windows, double-buffered by step parity
   float* wave_win[2];
@@ -72,7 +76,7 @@ struct Session {
   bool use_graphs = true;
   std::map<int, StageGraph> graphs;
   Synth* synth = nullptr;
-  DioPlan* dio = nullptr;
+  DioPlan* dio[2] = {nullptr, nullptr};     // one analysis plan per chunk parity
   std::vector<void*> allocs, pinned;
 };
 
@@ -162,10 +166,11 @@ static Session* get_session(Engine* e, int id) { return (id >= 0 && id < (int)e-
 
 static void session_free(Session* s) {
   if (!s) return;
-  for (cudaStream_t st : {s->sE, s->sC, s->sC2, s->sD}) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+  for (cudaStream_t st : {s->sE, s->sA[0], s->sA[1], s->sC, s->sC2, s->sD}) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
   for (int i = 0; i < kRing; ++i)
-    for (cudaEvent_t ev : {s->ev_pro[i], s->ev_count[i], s->ev_enc[i], s->ev_cslide[i], s->ev_s1[i], s->ev_conv[i], s->ev_dslide[i], s->ev_dec[i]}) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : {s->ev_gate[i], s->ev_pro[i], s->ev_count[i], s->ev_enc[i], s->ev_cslide[i], s->ev_s1[i], s->ev_conv[i], s->ev_dslide[i], s->ev_dec[i]}) if (ev) cudaEventDestroy(ev);
   for (auto& kv : s->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  if (s->stage_times) for (int a = 0; a < 5; ++a) for (int w = 0; w < 2; ++w) for (int i = 0; i < kRing; ++i) cudaEventDestroy(s->tev[a][w][i]);
   for (void* p : s->allocs) cudaFree(p);
   for (void* p : s->pinned) cudaFreeHost(p);
   synth_destroy(s->synth);
@@ -198,7 +203,7 @@ void session_destroy_all(Engine* e) {
 int session_streams_fork(Engine* e, cudaEvent_t ev) {
   for (Session* s : e->sessions) {
     if (!s) continue;
-    for (cudaStream_t st : {s->sE, s->sC, s->sC2, s->sD}) RYK_CUDA(cudaStreamWaitEvent(st, ev, 0));
+    for (cudaStream_t st : {s->sE, s->sA[0], s->sA[1], s->sC, s->sC2, s->sD}) RYK_CUDA(cudaStreamWaitEvent(st, ev, 0));
   }
   for (Group* G : e->groups) if (G) RYK_CUDA(cudaStreamWaitEvent(G->sG, ev, 0));
   return 0;
@@ -207,7 +212,7 @@ int session_streams_fork(Engine* e, cudaEvent_t ev) {
 int session_streams_join(Engine* e) {
   for (Session* s : e->sessions) {
     if (!s) continue;
-    for (cudaStream_t st : {s->sE, s->sC, s->sC2, s->sD}) {
+    for (cudaStream_t st : {s->sE, s->sA[0], s->sA[1], s->sC, s->sC2, s->sD}) {
       cudaEvent_t ev;
       RYK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
       RYK_CUDA(cudaEventRecord(ev, st));
@@ -230,8 +235,18 @@ int session_streams_join(Engine* e) {
 // Every stage of a step is a fixed kernel sequence over fixed buffers (selected by chunk parity, and for stage 1 by the
 // padded effective length), so each variant is stream-captured once and replayed: a step costs ~6 graph launches on
 // the host instead of ~90 kernel launches (the host was the bottleneck at 0.75 ms of launch overhead per 0.78 ms step).
+// RYK_SESSION_SKIP (timing experiments only; results are garbage): bit 0 analysis (E2), 1 stage 1, 2 stage-2 layers 1..14, 3 synthesis
+static int session_skip_mask() {
+  static int m = -1;
+  if (m < 0) { const char* v = getenv("RYK_SESSION_SKIP"); m = v ? atoi(v) : 0; }
+  return m;
+}
 template <typename F>
-static int run_stage(Engine* e, Session* s, int key, cudaStream_t st, F&& body) {
+static int run_stage(Engine* e, Session* s, int key, cudaStream_t st, F&& body, bool capture_only = false) {
+  if (const int m = session_skip_mask()) {
+    if (((m & 1) && (key == 2 || key == 3)) || ((m & 2) && key >= 4 && key < 40) || ((m & 4) && (key == 42 || key == 43)) || ((m & 8) && key >= 46 && key <= 49))
+      return 0;
+  }
   if (!s->use_graphs) return body();
   StageGraph& g = s->graphs[key];
   if (!g.exec) {
@@ -247,12 +262,42 @@ static int run_stage(Engine* e, Session* s, int key, cudaStream_t st, F&& body) 
     g.launches = e->launches - before;
     e->launches = before;
   }
+  if (capture_only) return 0;
   RYK_CUDA(cudaGraphLaunch(g.exec, st));
   e->launches += g.launches;
   return 0;
 }
 
-enum { G_E1 = 0, G_E2 = 2, G_S1 = 4 /* + 2 * bucket + parity, bucket 0..15 */, G_S2A = 40, G_S2B = 42, G_S2C = 44, G_D = 46 };
+enum { G_E1 = 0, G_E2 = 2, G_S1 = 4 /* + 2 * bucket + parity; bucket 0 = no effective frame, else padded length / 128 (1..15) */,
+       G_S2A = 40, G_S2B = 42, G_S2C = 44, G_D = 46, G_D1 = 48 };
+
+// Stage 1 of a chunk of parity b: slide the feature window, (gather ->) 1-D U-Net at padded length tp1 (0: no effective frame,
+// voice_changer.py:32-35 skips the net) -> scatter into the silent template + f0 map, mc2sp.  One graph per (tp1 bucket, parity);
+// all of them are captured when the session is created so that no chunk ever pays for a capture in the middle of a stream.
+static int stage1_enqueue(Engine* e, Session* s, int b, int tp1, bool capture_only) {
+  const int f = b, g = b ^ 1, pe = s->e_enc_frames;
+  const ryk_session_config& c = s->cfg;
+  return run_stage(e, s, G_S1 + 2 * (tp1 / 128) + b, s->sC, [&]() -> int {
+        SlideBatch sb; sb.n = 0;
+        slide_add<float>(sb, s->cw_f0[f], s->enc_f0[b] + pe, s->cw_f0[g], s->Tw, s->n_feat, 1);
+        slide_add<float>(sb, s->cw_ap[f], s->enc_ap[b] + (size_t)pe * s->nb, s->cw_ap[g], s->Tw, s->n_feat, s->nb);
+        slide_add<float>(sb, s->cw_mc[f], s->enc_mc[b] + (size_t)pe * s->C, s->cw_mc[g], s->Tw, s->n_feat, s->C);
+        slide_add<uint8_t>(sb, s->cw_voiced[f], s->enc_voiced[b] + pe, s->cw_voiced[g], s->Tw, s->n_feat, 1);
+        if (slide_batch(sb, s->sC)) return -1;
+        e->launches += 1;
+        const float* d_y = nullptr;
+        if (tp1 > 0) {
+          UNetPlan* p1 = nullptr;
+          if (unet_get_plan(e, e->stage1, 1, 1, tp1, e->precision, &p1, s->owner)) return -1;
+          if (stage1_prologue_run(e, s->cw_mc[g], s->d_index[b], s->d_count[b], s->C, (float*)p1->d_in, tp1, s->sC)) return -1;
+          if (unet_forward(e, p1, s->sC)) return -1;
+          d_y = (const float*)p1->d_out;
+        }
+        if (stage1_epilogue_run(e, d_y, s->d_index[b], s->d_mask[b], s->d_count[b], s->Tw, s->C, s->cw_f0[g], s->cw_ap[g], s->cw_voiced[g], s->nb,
+                                kSilentMc0, s->cv_mc_out[b], s->cv_f0_out[b], s->cv_ap_out[b], s->cv_voiced_out[b], s->sC)) return -1;
+        return mc2sp_run(e, s->cv_mc_out[b], s->Tw, c.order, c.fft_length, 1e-16, s->cv_sp_mid[b], nullptr, s->sC);
+      }, capture_only);
+}
 
 // Step k = s->step is enqueued in three parts so that a group can interleave its members:
 //   front: streams E and C (analysis, gate, stage 1, mc2sp) and the stage-2 prologue
@@ -266,12 +311,18 @@ enum { G_E1 = 0, G_E2 = 2, G_S1 = 4 /* + 2 * bucket + parity, bucket 0..15 */, G
   const int pe = s->e_enc_frames, pc = s->e_conv;                                                           \
   (void)f; (void)g; (void)r; (void)c; (void)pe; (void)pc;
 
+#define TSTAMP(stage, which, stream) do { if (s->stage_times) RYK_CUDA(cudaEventRecord(s->tev[stage][which][r], stream)); } while (0)
+
 static int session_front(Engine* e, Session* s, const float* d_chunk_user) {
   STEP_LOCALS
 
   // ================= stream E: gate + WORLD analysis =================
   RYK_CUDA(cudaMemcpyAsync(s->d_chunk_fixed, d_chunk_user, sizeof(float) * s->n_wave, cudaMemcpyDeviceToDevice, s->sE));
-  if (k >= 2) RYK_CUDA(cudaStreamWaitEvent(s->sE, s->ev_conv[(k - 2) % kRing], 0));     // mask/index/count[b] free again
+  if (k >= 2) {
+    RYK_CUDA(cudaStreamWaitEvent(s->sE, s->ev_s1[(k - 2) % kRing], 0));      // mask/index/count[b]: last read by stage 1 of k-2
+    RYK_CUDA(cudaStreamWaitEvent(s->sE, s->ev_enc[(k - 2) % kRing], 0));     // wave_win[g]: last read by the analysis of k-2
+  }
+  TSTAMP(0, 0, s->sE);
   if (run_stage(e, s, G_E1 + b, s->sE, [&]() -> int {
         if (slide<float>(s->wave_win[f], s->d_chunk_fixed, s->wave_win[g], s->Lw, s->n_wave, 1, s->sE)) return -1;
         if (slide<float>(s->cw_wave[f], s->wave_win[g] + (size_t)pe * s->hop, s->cw_wave[g], (size_t)s->Tw * s->hop, (size_t)s->n_feat * s->hop, 1, s->sE)) return -1;
@@ -279,17 +330,25 @@ static int session_front(Engine* e, Session* s, const float* d_chunk_user) {
         return gate_mask_run(e, s->cw_wave[g], s->Tw * s->hop, c.fft_length, s->hop, c.threshold_db, s->Tw, s->d_mse, s->d_mask[b], s->d_index[b],
                              s->d_count[b], s->sE);
       })) return -1;
+  TSTAMP(0, 1, s->sE);
   RYK_CUDA(cudaMemcpyAsync(s->h_count[r], s->d_count[b], sizeof(int) * 2, cudaMemcpyDeviceToHost, s->sE));
   RYK_CUDA(cudaEventRecord(s->ev_count[r], s->sE));
-  if (k >= 2) RYK_CUDA(cudaStreamWaitEvent(s->sE, s->ev_cslide[(k - 2) % kRing], 0));   // enc_*[b] consumed by stage 1 of k-2
-  if (run_stage(e, s, G_E2 + b, s->sE, [&]() -> int {
-        if (dio_stonemask_run(e, s->dio, s->wave_win[g], s->sE)) return -1;
+  RYK_CUDA(cudaEventRecord(s->ev_gate[r], s->sE));
+
+  // ================= stream A[b]: WORLD analysis (the chunks of one parity share a plan and a stream) =================
+  cudaStream_t sA = s->sA[b];
+  RYK_CUDA(cudaStreamWaitEvent(sA, s->ev_gate[r], 0));
+  if (k >= 2) RYK_CUDA(cudaStreamWaitEvent(sA, s->ev_cslide[(k - 2) % kRing], 0));   // enc_*[b] consumed by stage 1 of k-2
+  TSTAMP(1, 0, sA);
+  if (run_stage(e, s, G_E2 + b, sA, [&]() -> int {
+        if (dio_stonemask_run(e, s->dio[b], s->wave_win[g], sA)) return -1;
         const int n_enc = s->Lw / s->hop;
         e->launches += 13;
-        return spectral_analysis_run(e, s->wave_win[g], s->Lw, c.fs, c.frame_period_ms, dio_plan_f0(s->dio), n_enc, c.fft_length, c.order,
-                                     s->enc_sp[b], s->enc_ap[b], s->enc_mc[b], s->enc_f0[b], s->enc_voiced[b], s->sE);
+        return spectral_analysis_run(e, s->wave_win[g], s->Lw, c.fs, c.frame_period_ms, dio_plan_f0(s->dio[b]), n_enc, c.fft_length, c.order,
+                                     s->enc_sp[b], s->enc_ap[b], s->enc_mc[b], s->enc_f0[b], s->enc_voiced[b], sA);
       })) return -1;
-  RYK_CUDA(cudaEventRecord(s->ev_enc[r], s->sE));
+  TSTAMP(1, 1, sA);
+  RYK_CUDA(cudaEventRecord(s->ev_enc[r], sA));
 
   // ================= stream C: stage 1 (+ f0 map, mc2sp) =================
   RYK_CUDA(cudaStreamWaitEvent(s->sC, s->ev_enc[r], 0));
@@ -300,28 +359,11 @@ static int session_front(Engine* e, Session* s, const float* d_chunk_user) {
   RYK_CUDA(cudaEventSynchronize(s->ev_count[r]));                              // effective-frame count of THIS step
   const int t_eff = s->h_count[r][0], tp1 = s->h_count[r][1];
   RYK_CHECK(tp1 / 128 < 16, "window too long for the stage-1 graph table");
-  if (run_stage(e, s, G_S1 + 2 * (tp1 / 128) + b, s->sC, [&]() -> int {
-        SlideBatch sb; sb.n = 0;
-        slide_add<float>(sb, s->cw_f0[f], s->enc_f0[b] + pe, s->cw_f0[g], s->Tw, s->n_feat, 1);
-        slide_add<float>(sb, s->cw_ap[f], s->enc_ap[b] + (size_t)pe * s->nb, s->cw_ap[g], s->Tw, s->n_feat, s->nb);
-        slide_add<float>(sb, s->cw_mc[f], s->enc_mc[b] + (size_t)pe * s->C, s->cw_mc[g], s->Tw, s->n_feat, s->C);
-        slide_add<uint8_t>(sb, s->cw_voiced[f], s->enc_voiced[b] + pe, s->cw_voiced[g], s->Tw, s->n_feat, 1);
-        if (slide_batch(sb, s->sC)) return -1;
-        e->launches += 1;
-        const float* d_y = nullptr;
-        if (t_eff > 0) {      // voice_changer.py:32-35: stage 1 is skipped when no frame is effective
-          UNetPlan* p1 = nullptr;
-          if (unet_get_plan(e, e->stage1, 1, 1, tp1, e->precision, &p1, s->owner)) return -1;
-          if (stage1_prologue_run(e, s->cw_mc[g], s->d_index[b], s->d_count[b], s->C, (float*)p1->d_in, tp1, s->sC)) return -1;
-          if (unet_forward(e, p1, s->sC)) return -1;
-          d_y = (const float*)p1->d_out;
-        }
-        if (stage1_epilogue_run(e, d_y, s->d_index[b], s->d_mask[b], s->d_count[b], s->Tw, s->C, s->cw_f0[g], s->cw_ap[g], s->cw_voiced[g], s->nb,
-                                kSilentMc0, s->cv_mc_out[b], s->cv_f0_out[b], s->cv_ap_out[b], s->cv_voiced_out[b], s->sC)) return -1;
-        return mc2sp_run(e, s->cv_mc_out[b], s->Tw, c.order, c.fft_length, 1e-16, s->cv_sp_mid[b], nullptr, s->sC);
-      })) return -1;
+  TSTAMP(2, 0, s->sC);
+  if (stage1_enqueue(e, s, b, t_eff > 0 ? tp1 : 0, false)) return -1;
   // NB: enc_*[b] may be overwritten by encode k+2 once this stage's slides ran; the stage-1 graph is short, so the
   // guard event is simply the end of the stage.
+  TSTAMP(2, 1, s->sC);
   RYK_CUDA(cudaEventRecord(s->ev_cslide[r], s->sC));
   RYK_CUDA(cudaEventRecord(s->ev_s1[r], s->sC));
 
@@ -329,6 +371,7 @@ static int session_front(Engine* e, Session* s, const float* d_chunk_user) {
   RYK_CUDA(cudaStreamWaitEvent(s->sC2, s->ev_s1[r], 0));
   if (k >= 2) RYK_CUDA(cudaStreamWaitEvent(s->sC2, s->ev_dslide[(k - 2) % kRing], 0));  // cv_sp_out[b] consumed by decode k-2
   const int Tp = s->Tw + (128 - s->Tw % 128);
+  TSTAMP(3, 0, s->sC2);
   if (s->group) {
     Group* G = s->group;
     if (G->step >= 1) RYK_CUDA(cudaStreamWaitEvent(s->sC2, G->ev_fwd[(G->step - 1) % kRing], 0));   // batched input read by forward k-1
@@ -375,28 +418,36 @@ static int session_back(Engine* e, Session* s) {
           return sr_epilogue_run(e, (const float*)p2->d_out, s->Tw, s->nb, s->cv_sp_out[b], s->sC2);
         })) return -1;
   }
+  TSTAMP(3, 1, s->sC2);
   RYK_CUDA(cudaEventRecord(s->ev_conv[r], s->sC2));
 
   // ================= stream D: realtime synthesizer =================
   RYK_CUDA(cudaStreamWaitEvent(s->sD, s->ev_conv[r], 0));
+  TSTAMP(4, 0, s->sD);
   if (synth_host_advance(e, s->synth, s->Td, s->sD)) return -1;
   const int max_blocks = s->max_blocks;
-  if (run_stage(e, s, G_D + b, s->sD, [&]() -> int {
+  if (run_stage(e, s, G_D1 + b, s->sD, [&]() -> int {
         SlideBatch sb; sb.n = 0;
         slide_add<float>(sb, s->dw_f0[f], s->cv_f0_out[b] + pc, s->dw_f0[g], s->Td, s->n_feat, 1);
         slide_add<float>(sb, s->dw_ap[f], s->cv_ap_out[b] + (size_t)pc * s->nb, s->dw_ap[g], s->Td, s->n_feat, s->nb);
         slide_add<float>(sb, s->dw_sp[f], s->cv_sp_out[b] + (size_t)pc * s->nb, s->dw_sp[g], s->Td, s->n_feat, s->nb);
         if (slide_batch(sb, s->sD)) return -1;
         k_f32_to_f64<<<(s->Td + 127) / 128, 128, 0, s->sD>>>(s->dw_f0[g], s->dec_f0_f64, s->Td);
-        if (synth_add_kernel(e, s->synth, s->dec_f0_f64, s->Td, s->dw_sp[g], s->dw_ap[g], s->sD)) return -1;
-        if (synth_drain_async(e, s->synth, s->d_out_fixed[b], max_blocks, s->sD)) return -1;
-        k_scrub<<<8, 256, 0, s->sD>>>(s->d_out_fixed[b], s->synth->dev.state, c.vocoder_buffer_size, max_blocks * c.vocoder_buffer_size, s->d_n_fixed[b]);
-        e->launches += 3;
+        e->launches += 2;
         RYK_CUDA(cudaGetLastError());
         return 0;
       })) return -1;
-  // the decode graph both consumes cv_*[b] and produces the output: one event guards both
+  // the converted features of this parity are free again as soon as they sit in the decode window
   RYK_CUDA(cudaEventRecord(s->ev_dslide[r], s->sD));
+  if (run_stage(e, s, G_D + b, s->sD, [&]() -> int {
+        if (synth_add_kernel(e, s->synth, s->dec_f0_f64, s->Td, s->dw_sp[g], s->dw_ap[g], s->sD)) return -1;
+        if (synth_drain_async(e, s->synth, s->d_out_fixed[b], max_blocks, s->sD)) return -1;
+        k_scrub<<<8, 256, 0, s->sD>>>(s->d_out_fixed[b], s->synth->dev.state, c.vocoder_buffer_size, max_blocks * c.vocoder_buffer_size, s->d_n_fixed[b]);
+        e->launches += 1;
+        RYK_CUDA(cudaGetLastError());
+        return 0;
+      })) return -1;
+  TSTAMP(4, 1, s->sD);
   // ev_dec[r] is recorded by the caller after the copies it appends to stream D
   s->step++;
   return 0;
@@ -475,7 +526,7 @@ int ryk_session_create(ryk_engine* h, const ryk_session_config* cfg, int* sessio
   RYK_CHECK(e->stage1 && e->stage2, "load both models before creating a session");
   Session* s = new Session();
   memset(s->ev_count, 0, sizeof(s->ev_count)); memset(s->ev_enc, 0, sizeof(s->ev_enc)); memset(s->ev_cslide, 0, sizeof(s->ev_cslide));
-  memset(s->ev_s1, 0, sizeof(s->ev_s1)); memset(s->ev_pro, 0, sizeof(s->ev_pro)); memset(s->ev_conv, 0, sizeof(s->ev_conv)); memset(s->ev_dslide, 0, sizeof(s->ev_dslide)); memset(s->ev_dec, 0, sizeof(s->ev_dec));
+  memset(s->ev_s1, 0, sizeof(s->ev_s1)); memset(s->ev_gate, 0, sizeof(s->ev_gate)); memset(s->ev_pro, 0, sizeof(s->ev_pro)); memset(s->ev_conv, 0, sizeof(s->ev_conv)); memset(s->ev_dslide, 0, sizeof(s->ev_dslide)); memset(s->ev_dec, 0, sizeof(s->ev_dec));
   s->cfg = *cfg;
   s->hop = (int)(cfg->fs * cfg->frame_period_ms / 1000.0);
   s->rate = (int)lround(1000.0 / cfg->frame_period_ms);
@@ -494,14 +545,23 @@ int ryk_session_create(ryk_engine* h, const ryk_session_config* cfg, int* sessio
   RYK_CHECK(s->Lw / s->hop - 2 * s->e_enc_frames == s->n_feat, "encode window does not trim to one chunk of frames");
   RYK_CHECK(s->nb == 513 && e->stage1->in_ch == s->C, "session configuration does not match the loaded models");
   if (sptk_prepare(e, cfg->order, cfg->alpha, cfg->fft_length)) return -1;
-  RYK_CUDA(cudaStreamCreateWithFlags(&s->sE, cudaStreamNonBlocking));
-  RYK_CUDA(cudaStreamCreateWithFlags(&s->sC, cudaStreamNonBlocking));
-  RYK_CUDA(cudaStreamCreateWithFlags(&s->sC2, cudaStreamNonBlocking));
-  RYK_CUDA(cudaStreamCreateWithFlags(&s->sD, cudaStreamNonBlocking));
+  // The analysis, stage-1 and synthesis stages are chains of small, latency-bound kernels; stage 2 is bulk work that fills
+  // every SM.  Higher stream priority for the former lets their CTAs take freed SM slots first, so their latency does not
+  // inflate behind stage-2 waves (the analysis chain is what the host's per-step count sync waits on).
+  int prio_lo = 0, prio_hi = 0;
+  RYK_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));      // lo = least (numerically largest), hi = greatest
+  { const char* v = getenv("RYK_NO_PRIORITY"); if (v && atoi(v)) prio_hi = prio_lo; }
+  RYK_CUDA(cudaStreamCreateWithPriority(&s->sE, cudaStreamNonBlocking, prio_hi));
+  for (int i = 0; i < 2; ++i) RYK_CUDA(cudaStreamCreateWithPriority(&s->sA[i], cudaStreamNonBlocking, prio_hi));
+  RYK_CUDA(cudaStreamCreateWithPriority(&s->sC, cudaStreamNonBlocking, prio_hi));
+  RYK_CUDA(cudaStreamCreateWithPriority(&s->sC2, cudaStreamNonBlocking, prio_lo));
+  RYK_CUDA(cudaStreamCreateWithPriority(&s->sD, cudaStreamNonBlocking, prio_hi));
   for (int i = 0; i < kRing; ++i) {
-    cudaEvent_t* evs[] = {&s->ev_pro[i], &s->ev_count[i], &s->ev_enc[i], &s->ev_cslide[i], &s->ev_s1[i], &s->ev_conv[i], &s->ev_dslide[i], &s->ev_dec[i]};
+    cudaEvent_t* evs[] = {&s->ev_gate[i], &s->ev_pro[i], &s->ev_count[i], &s->ev_enc[i], &s->ev_cslide[i], &s->ev_s1[i], &s->ev_conv[i], &s->ev_dslide[i], &s->ev_dec[i]};
     for (cudaEvent_t* ev : evs) RYK_CUDA(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
   }
+  { const char* v = getenv("RYK_STAGE_TIMES"); s->stage_times = v && atoi(v) != 0; }
+  if (s->stage_times) for (int a = 0; a < 5; ++a) for (int w = 0; w < 2; ++w) for (int i = 0; i < kRing; ++i) RYK_CUDA(cudaEventCreate(&s->tev[a][w][i]));
   auto A = [&](void** p, size_t bytes) -> int { RYK_CUDA(cudaMalloc(p, bytes ? bytes : 16)); RYK_CUDA(cudaMemset(*p, 0, bytes ? bytes : 16)); s->allocs.push_back(*p); return 0; };
   auto P = [&](void** p, size_t bytes) -> int { RYK_CUDA(cudaMallocHost(p, bytes ? bytes : 16)); memset(*p, 0, bytes ? bytes : 16); s->pinned.push_back(*p); return 0; };
   const int n_enc = s->Lw / s->hop;
@@ -552,8 +612,10 @@ int ryk_session_create(ryk_engine* h, const ryk_session_config* cfg, int* sessio
     if (P((void**)&s->h_n[i], sizeof(int))) return -1;
     if (P((void**)&s->h_count[i], sizeof(int) * 2)) return -1;
   }
-  if (dio_plan_create(e, s->Lw, cfg->fs, cfg->frame_period_ms, cfg->f0_floor, cfg->f0_ceil, &s->dio)) return -1;
-  e->dio_plans[std::make_tuple(-(int)e->sessions.size() - 1, cfg->fs, 0, 0, 0)] = s->dio;   // owned by the engine's plan table
+  for (int i = 0; i < 2; ++i) {
+    if (dio_plan_create(e, s->Lw, cfg->fs, cfg->frame_period_ms, cfg->f0_floor, cfg->f0_ceil, &s->dio[i])) return -1;
+    e->dio_plans[std::make_tuple(-(int)e->sessions.size() - 1, cfg->fs, i, 0, 0)] = s->dio[i];   // owned by the engine's plan table
+  }
   if (synth_create(e, cfg->fs, cfg->frame_period_ms, cheaptrick_fft_size(cfg->fs, 71.0), cfg->vocoder_buffer_size, 4096, &s->synth)) return -1;
   // build the U-Net plans this session can need up front (allocation + tensor maps), not on the first chunk
   UNetPlan* p = nullptr;
@@ -562,6 +624,13 @@ int ryk_session_create(ryk_engine* h, const ryk_session_config* cfg, int* sessio
   // (the stage-2 plan is created on first use: a session that joins a group never needs its own)
   RYK_CUDA(cudaStreamSynchronize(e->stream));
   RYK_CUDA(cudaDeviceSynchronize());
+  if (s->use_graphs) {
+    const long long before = e->launches;
+    for (int b = 0; b < 2; ++b)
+      for (int tp1 = 0; tp1 <= s->Tw + (128 - s->Tw % 128); tp1 += 128)
+        if (stage1_enqueue(e, s, b, tp1, true)) return -1;
+    e->launches = before;
+  }
   e->sessions.push_back(s);
   *session_id = (int)e->sessions.size() - 1;
   return 0;
@@ -668,7 +737,7 @@ int ryk_group_create(ryk_engine* h, const int* session_ids, int n_sessions, int*
   }
   G->Tp = G->members[0]->Tw + (128 - G->members[0]->Tw % 128);
   if (unet_get_plan(e, e->stage2, n_sessions, G->Tp, 512, e->precision, &G->p2, G->owner)) { group_free(G); return -1; }
-  RYK_CUDA(cudaStreamCreateWithFlags(&G->sG, cudaStreamNonBlocking));
+  { int lo = 0, hi = 0; RYK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi)); RYK_CUDA(cudaStreamCreateWithPriority(&G->sG, cudaStreamNonBlocking, lo)); }
   for (int i = 0; i < kRing; ++i) RYK_CUDA(cudaEventCreateWithFlags(&G->ev_fwd[i], cudaEventDisableTiming));
   RYK_CUDA(cudaDeviceSynchronize());
   e->groups.push_back(G);
@@ -764,6 +833,26 @@ int ryk_group_push_device(ryk_engine* h, int group_id, const float* const* waves
   }
   G->collected = G->step;
   return 0;
+}
+
+// Diagnostics (RYK_STAGE_TIMES=1 at session creation): device timeline of the last min(steps, 8) steps.  start/end[i*5 + a] =
+// ms since the oldest listed step began, for stage a in {gate+slides, WORLD analysis, stage 1 (+mc2sp), stage 2
+// (prologue..epilogue), synthesis}; returns the number of steps listed (oldest first).
+int ryk_session_stage_times(ryk_engine* h, int id, float* start, float* end) {
+  Engine* e = &h->impl;
+  Session* s = get_session(e, id);
+  RYK_CHECK(s != nullptr && s->stage_times && s->step >= 1, "stage timing is not enabled for this session (RYK_STAGE_TIMES=1) or no step ran");
+  RYK_CUDA(cudaDeviceSynchronize());
+  const int n = s->step < kRing ? (int)s->step : kRing;
+  const int r0 = (int)((s->step - n) % kRing);
+  for (int i = 0; i < n; ++i) {
+    const int r = (int)((s->step - n + i) % kRing);
+    for (int a = 0; a < 5; ++a) {
+      RYK_CUDA(cudaEventElapsedTime(&start[i * 5 + a], s->tev[0][0][r0], s->tev[a][0][r]));
+      RYK_CUDA(cudaEventElapsedTime(&end[i * 5 + a], s->tev[0][0][r0], s->tev[a][1][r]));
+    }
+  }
+  return n;
 }
 
 }  // extern "C"

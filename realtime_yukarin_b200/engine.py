@@ -47,7 +47,7 @@ EXPORTED_SYMBOLS = [
     'ryk_stage2_convert', 'ryk_convert_window', 'ryk_synth_create', 'ryk_synth_destroy', 'ryk_synth_add_parameters',
     'ryk_synth_synthesis2', 'ryk_synth_decode', 'ryk_session_create', 'ryk_session_destroy', 'ryk_session_push',
     'ryk_session_push_device', 'ryk_session_submit', 'ryk_session_collect', 'ryk_group_create', 'ryk_group_destroy',
-    'ryk_group_size', 'ryk_group_submit', 'ryk_group_collect', 'ryk_group_push_device', 'ryk_test_conv_layer', 'ryk_debug_dio', 'ryk_debug_synth_pulses', 'ryk_debug_synth_timebase', 'ryk_engine_profile', 'ryk_engine_profile_read', 'ryk_engine_timer_start', 'ryk_engine_timer_stop',
+    'ryk_group_size', 'ryk_session_stage_times', 'ryk_group_submit', 'ryk_group_collect', 'ryk_group_push_device', 'ryk_test_conv_layer', 'ryk_debug_dio', 'ryk_debug_synth_pulses', 'ryk_debug_synth_timebase', 'ryk_engine_profile', 'ryk_engine_profile_read', 'ryk_engine_timer_start', 'ryk_engine_timer_stop',
 ]
 
 
@@ -356,6 +356,12 @@ class Engine(object):
     def session_push_device(self, sid: int, wave_dev_ptr: int, n: int, out_dev_ptr: int, out_capacity: int, n_out_dev_ptr: int):
         self._check(self.lib.ryk_session_push_device(self._h, sid, ctypes.c_void_p(wave_dev_ptr), int(n), ctypes.c_void_p(out_dev_ptr),
                                                      int(out_capacity), ctypes.c_void_p(n_out_dev_ptr)))
+
+    def session_stage_times(self, sid: int):
+        """(start, end) arrays of shape (steps, 5) in ms; see ryk_session_stage_times."""
+        st, en = (ctypes.c_float * 40)(), (ctypes.c_float * 40)()
+        n = self._check(self.lib.ryk_session_stage_times(self._h, sid, st, en))
+        return numpy.array(st[:n * 5]).reshape(n, 5), numpy.array(en[:n * 5]).reshape(n, 5)
 
     # ---- groups (several streams per GPU, one batched stage-2 forward per step) ----
     def group_create(self, session_ids: Sequence[int]) -> int:
