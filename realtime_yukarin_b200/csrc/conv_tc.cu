@@ -37,6 +37,14 @@ constexpr int kTcThreads = 192;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Programmatic dependent launch: every kernel of a U-Net forward is a dependent of the one before it in the stream.
+// pdl_trigger() lets the NEXT kernel's CTAs be scheduled as soon as all CTAs of this grid have started (they run their
+// prologue -- barrier init, TMEM allocation, tensor-map prefetch, scale/shift staging -- in the shadow of this grid's
+// tail); pdl_wait() blocks until the PREVIOUS grid has completed and its memory is visible, and must precede every
+// access to activations / workspaces.  Both are no-ops for launches without the programmatic attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -135,6 +143,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
   float* s_shift = s_scale + BLOCK_N;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
   if (threadIdx.x == 0) {
     TL(0);
 #ifdef RYK_TC_TIMELINE
@@ -180,6 +189,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();                       // the previous layer's outputs (our A operand) are complete from here on
   if (threadIdx.x == 0) TL(1);
 
   if (warp == 4 && lane == 0) {
@@ -198,13 +208,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
         ix = p.sw == 2 ? ox0 + tx - 1 + px : ox0;
         iy = p.sh == 2 ? oy0 + ty - 1 + py : oy0;
       }
-      const bool ldA = !(p.debug & 2) || i < kStages, ldB = !(p.debug & 4) || i < kStages;   // XXEXP
-      mbar_expect_tx(&full_bar[s], (ldA ? kABytes : 0) + (ldB ? kBBytes : 0));
-      if (ldA) {
+      mbar_expect_tx(&full_bar[s], kABytes + kBBytes);
       if (cc < p.chunks0) tma_load_4d(smem_a + s * kABytes, &tmA0, &full_bar[s], cc * kBlockK, ix, iy, b);
       else tma_load_4d(smem_a + s * kABytes, &tmA1, &full_bar[s], (cc - p.chunks0) * kBlockK, ix, iy, b);
-      }
-      if (ldB) tma_load_2d(smem_b + s * kBBytes, &tmB, &full_bar[s], kc * kBlockK, cls * p.Cout + n0);
+      tma_load_2d(smem_b + s * kBBytes, &tmB, &full_bar[s], kc * kBlockK, cls * p.Cout + n0);
     }
   } else if (warp == 5 && lane == 0) {
     // ===== MMA issuer =====
@@ -581,6 +588,8 @@ k_conv_tc_persist(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 __global__ void __launch_bounds__(256) k_splitk_reduce(const float* __restrict__ ws, size_t total4, size_t slice_elems, int ksplit, int Cout,
                                 const float* __restrict__ scale, const float* __restrict__ shift, int act, __half* __restrict__ out) {
   __shared__ float4 part[8][32];
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31, g = threadIdx.x >> 5, G = blockDim.x >> 5;
   const size_t i = (size_t)blockIdx.x * 32 + lane;
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -612,6 +621,8 @@ __global__ void __launch_bounds__(256) k_splitk_reduce(const float* __restrict__
 __global__ void __launch_bounds__(256) k_splitk_reduce_few(const float* __restrict__ ws, size_t total4, size_t slice_elems, int ksplit, int Cout,
                                     const float* __restrict__ scale, const float* __restrict__ shift, int act, __half* __restrict__ out) {
   const size_t stride4 = slice_elems / 4;
+  pdl_trigger();
+  pdl_wait();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
     const float4* p = reinterpret_cast<const float4*>(ws) + i;
     float4 a = __ldg(p);
@@ -780,6 +791,24 @@ int tc_layer_prepare(ConvLayer& L, int num_sms) {
   return 0;
 }
 
+// Launch with the programmatic-stream-serialization attribute (see pdl_trigger / pdl_wait); RYK_NO_PDL=1 falls back to
+// plain stream order (the device-side instructions are then no-ops).
+static bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("RYK_NO_PDL"); v = (e && atoi(e) != 0) ? 0 : 1; }
+  return v != 0;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 int conv_tc_run(const ConvLayer& L, cudaStream_t st) {
   RYK_CHECK(L.tc_ready, "tc layer not prepared");
   TcParams p;
@@ -818,13 +847,13 @@ int conv_tc_run(const ConvLayer& L, cudaStream_t st) {
     else if (L.block_n == 128) k_conv_tc_persist<128, 6, 1><<<ctas, kTcThreads, tcp_smem_bytes<128, 6, 1>(), st>>>(L.tmA0, L.tmA1, L.tmB, L.tmO, p, tiles_mn, n_tiles_n, total_tiles);
     else k_conv_tc_persist<64, 8, 1><<<ctas, kTcThreads, tcp_smem_bytes<64, 8, 1>(), st>>>(L.tmA0, L.tmA1, L.tmB, L.tmO, p, tiles_mn, n_tiles_n, total_tiles);
   } else if (variant == 0) {
-    if (L.block_n == 256) k_conv_tc<256, 4, 1><<<grid, kTcThreads, tc_smem_bytes<256, 4>(), st>>>(L.tmA0, L.tmA1, L.tmB, L.tmO, L.tmW, p);
-    else if (L.block_n == 128) k_conv_tc<128, 6, 1><<<grid, kTcThreads, tc_smem_bytes<128, 6>(), st>>>(L.tmA0, L.tmA1, L.tmB, L.tmO, L.tmW, p);
-    else k_conv_tc<64, 6, 1><<<grid, kTcThreads, tc_smem_bytes<64, 6>(), st>>>(L.tmA0, L.tmA1, L.tmB, L.tmO, L.tmW, p);
+    if (L.block_n == 256) RYK_CUDA(launch_pdl(k_conv_tc<256, 4, 1>, grid, dim3(kTcThreads), tc_smem_bytes<256, 4>(), st, L.tmA0, L.tmA1, L.tmB, L.tmO, L.tmW, p));
+    else if (L.block_n == 128) RYK_CUDA(launch_pdl(k_conv_tc<128, 6, 1>, grid, dim3(kTcThreads), tc_smem_bytes<128, 6>(), st, L.tmA0, L.tmA1, L.tmB, L.tmO, L.tmW, p));
+    else RYK_CUDA(launch_pdl(k_conv_tc<64, 6, 1>, grid, dim3(kTcThreads), tc_smem_bytes<64, 6>(), st, L.tmA0, L.tmA1, L.tmB, L.tmO, L.tmW, p));
   } else {
-    if (L.block_n == 256) k_conv_tc<256, 2, 2><<<grid, kTcThreads, tc_smem_bytes<256, 2>(), st>>>(L.tmA0, L.tmA1, L.tmB, L.tmO, L.tmW, p);
-    else if (L.block_n == 128) k_conv_tc<128, 3, 2><<<grid, kTcThreads, tc_smem_bytes<128, 3>(), st>>>(L.tmA0, L.tmA1, L.tmB, L.tmO, L.tmW, p);
-    else k_conv_tc<64, 4, 2><<<grid, kTcThreads, tc_smem_bytes<64, 4>(), st>>>(L.tmA0, L.tmA1, L.tmB, L.tmO, L.tmW, p);
+    if (L.block_n == 256) RYK_CUDA(launch_pdl(k_conv_tc<256, 2, 2>, grid, dim3(kTcThreads), tc_smem_bytes<256, 2>(), st, L.tmA0, L.tmA1, L.tmB, L.tmO, L.tmW, p));
+    else if (L.block_n == 128) RYK_CUDA(launch_pdl(k_conv_tc<128, 3, 2>, grid, dim3(kTcThreads), tc_smem_bytes<128, 3>(), st, L.tmA0, L.tmA1, L.tmB, L.tmO, L.tmW, p));
+    else RYK_CUDA(launch_pdl(k_conv_tc<64, 4, 2>, grid, dim3(kTcThreads), tc_smem_bytes<64, 4>(), st, L.tmA0, L.tmA1, L.tmB, L.tmO, L.tmW, p));
   }
   RYK_CUDA(cudaGetLastError());
 #ifdef RYK_TC_TIMELINE
@@ -846,9 +875,9 @@ int conv_tc_run(const ConvLayer& L, cudaStream_t st) {
     size_t total4 = out_elems / 4;
     if (L.ksplit <= 4) {
       int blocks = (int)((total4 + 255) / 256); if (blocks > 2368) blocks = 2368;
-      k_splitk_reduce_few<<<blocks, 256, 0, st>>>(p.ws, total4, out_elems, L.ksplit, L.Cout, L.scale, L.shift, L.act, (__half*)L.out);
+      RYK_CUDA(launch_pdl(k_splitk_reduce_few, dim3(blocks), dim3(256), 0, st, (const float*)p.ws, total4, out_elems, L.ksplit, L.Cout, L.scale, L.shift, L.act, (__half*)L.out));
     } else {
-      k_splitk_reduce<<<(unsigned)((total4 + 31) / 32), 256, 0, st>>>(p.ws, total4, out_elems, L.ksplit, L.Cout, L.scale, L.shift, L.act, (__half*)L.out);
+      RYK_CUDA(launch_pdl(k_splitk_reduce, dim3((unsigned)((total4 + 31) / 32)), dim3(256), 0, st, (const float*)p.ws, total4, out_elems, L.ksplit, L.Cout, L.scale, L.shift, L.act, (__half*)L.out));
     }
     RYK_CUDA(cudaGetLastError());
   }
