@@ -35,6 +35,11 @@ WORKLOAD = ('single stream per GPU, buffer_time=0.3 s, extras (0,0.5,0), frame_p
             'convert window 260 -> 384 frames, stage-1 1-D U-Net base 64 (13.6 M params), '
             'stage-2 2-D U-Net base 64 on 384x512 (54.4 M params, 142 GFLOP/chunk), WORLD DIO+StoneMask/CheapTrick/D4C + realtime synthesis')
 
+# DRAM traffic of one stage-2 k4 block (14 k_conv_tc + 9 split-K reduce launches, 384x512, batch 1) from the committed ncu
+# capture profiles/r01c_ncu_full_one_step.csv: 284.67 MB read + 0.11 MB written (algorithmic: 108.8 MB fp16 weights +
+# ~100 MB activations written/read once; under ncu every replay starts with cold caches, so activations are re-read).
+STAGE2_BLOCK_DRAM_BYTES = 284.77e6
+
 # algorithmic work of the stage-2 k4 layers (the tcgen05 kernel launches) for one 384x512 forward, base 64
 STAGE2_TC_FLOP = None
 
@@ -345,7 +350,7 @@ def run_gpu(args):
         metric=metric, value=value, unit='chunks/s', rtf=value * T, n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=1000.0 * t_dev / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
         dtype='f64 (WORLD analysis/synthesis), f32 (stage 1), f16 in / f32 accumulate (stage 2 tcgen05)', data='synthetic',
-        config=dict(workload=workload, timing='CUDA events on the engine stream (forked to / joined from the session streams) around the K pushes, max over ranks', pipeline='encode | convert | decode of consecutive chunks overlap on 4 CUDA streams per audio stream (as the reference overlaps its 3 worker processes); e2e keeps 3 steps in flight',
+        config=dict(workload=workload, timing='CUDA events on the engine stream (forked to / joined from the session streams) around the K pushes, max over ranks', pipeline='gate | analysis (2 chunks in flight) | stage 1 | stage 2 | synthesis of consecutive chunks overlap on 6 CUDA streams per audio stream, each stage a CUDA graph (the reference overlaps its 3 worker processes); e2e keeps 3 steps in flight',
                     l2='per-step footprint (109 MB fp16 stage-2 weights + 54 MB stage-1 weights + ~100 MB activations) exceeds the 126 MB L2; no explicit flush',
                     streams_per_gpu=B, silence_threshold_db=THRESHOLD_DB),
         e2e=dict(value=e2e, unit='chunks/s', rtf=e2e * T, h2d_bytes_per_step=B * n * 4,
@@ -353,7 +358,8 @@ def run_gpu(args):
         gpu_launches=int(launches), host_enqueue_ms_per_step=1000.0 * t_host / args.steps,
         clocks=clocks,
         roofline=dict(bound='tensor', kernel='k_conv_tc (stage-2 k4 layers 1..14, incl. split-K memset/finalize)' + ('' if B == 1 else ' + the two 3x3 edge layers (group forward timed as a whole)'), achieved=ach, peak=peaks['tflops'],
-                      unit='TFLOP/s', frac=(ach / peaks['tflops']) if ach else None, traffic=None, peak_source=peaks['source'],
+                      unit='TFLOP/s', frac=(ach / peaks['tflops']) if ach else None, traffic=STAGE2_BLOCK_DRAM_BYTES if default_workload else None,
+                      traffic_source='ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum summed over the 23 launches of one 384x512 stage-2 k4 block (cold caches per replay): profiles/r01c_ncu_full_one_step.csv', peak_source=peaks['source'],
                       flop_per_step=fl, ms_per_step_in_kernel=(s2_ms / s2_runs) if s2_runs else None),
     )
     if stage_times is not None:

@@ -639,6 +639,24 @@ int ryk_test_conv_layer(ryk_engine* h, int transposed, int k, int stride, int pa
   int rc = 0;
   cudaEvent_t ev0, ev1;
   RYK_CUDA(cudaEventCreate(&ev0)); RYK_CUDA(cudaEventCreate(&ev1));
+  // time `repeat` runs replayed from a CUDA graph (as the session runs them): no host launch overhead in the figure
+  auto timed_graph = [&](auto&& run) -> int {
+    cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+    int r = 0;
+    RYK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    for (int i = 0; i < repeat && !r; ++i) r = run();
+    cudaError_t err = cudaStreamEndCapture(st, &graph);
+    if (r) return r;
+    RYK_CUDA(err);
+    RYK_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+    RYK_CUDA(cudaGraphLaunch(exec, st));
+    RYK_CUDA(cudaEventRecord(ev0, st));
+    RYK_CUDA(cudaGraphLaunch(exec, st));
+    RYK_CUDA(cudaEventRecord(ev1, st));
+    RYK_CUDA(cudaStreamSynchronize(st));
+    cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+    return 0;
+  };
   if (use_tc == 1) {
     if (pack_weights_tc(d_w, transposed, Cin, Cout, L.KH, k, L.SH, stride, d_wt, st)) return -1;
     k_f32_to_f16<<<1184, 256, 0, st>>>(d_in0, d_h0, n0);
@@ -651,41 +669,23 @@ int ryk_test_conv_layer(ryk_engine* h, int transposed, int k, int stride, int pa
     if (ws) L.splitk_ws = (float*)A(ws);
     if (tc_layer_prepare(L, num_sms)) return -1;
     rc = conv_tc_run(L, st);
-    if (!rc && repeat > 0) {
-      // time `repeat` runs replayed from a CUDA graph (as the session runs them): no host launch overhead in the figure
-      cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
-      RYK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-      for (int i = 0; i < repeat && !rc; ++i) rc = conv_tc_run(L, st);
-      cudaError_t err = cudaStreamEndCapture(st, &graph);
-      if (rc) return rc;
-      RYK_CUDA(err);
-      RYK_CUDA(cudaGraphInstantiate(&exec, graph, 0));
-      RYK_CUDA(cudaGraphLaunch(exec, st));
-      RYK_CUDA(cudaEventRecord(ev0, st));
-      RYK_CUDA(cudaGraphLaunch(exec, st));
-      RYK_CUDA(cudaEventRecord(ev1, st));
-      RYK_CUDA(cudaStreamSynchronize(st));
-      cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
-    }
+    if (!rc && repeat > 0) rc = timed_graph([&]() { return conv_tc_run(L, st); });
     k_f16_to_f32<<<1184, 256, 0, st>>>(d_ho, d_out, no);
   } else if (use_tc == 2) {
-    // mixed-precision edge layers as the fp16 U-Net plan runs them: Cin = 1 reads fp32 / writes fp16, Cout = 1 reads fp16 / writes fp32
-    const bool in_h = Cin > 1, out_h = Cout > 1;
+    // mixed-precision edge layers as the fp16 U-Net plans run them: the first layer (Cin = 1) reads fp32 / writes fp16, the last
+    // layers (stage 2: Cout = 1, stage 1: 1-D k3 to `order + 1` channels) read fp16 / write fp32
+    const bool in_h = Cin > 1, out_h = Cin == 1;
     if (in_h) { k_f32_to_f16<<<1184, 256, 0, st>>>(d_in0, d_h0, n0); if (n1) k_f32_to_f16<<<1184, 256, 0, st>>>(d_in1, d_h1, n1); }
     L.in0 = in_h ? (const void*)d_h0 : (const void*)d_in0; L.in1 = n1 ? (in_h ? (const void*)d_h1 : (const void*)d_in1) : nullptr;
     L.in_dtype = in_h ? DT_F16 : DT_F32; L.out = out_h ? (void*)d_ho : (void*)d_out; L.out_dtype = out_h ? DT_F16 : DT_F32;
     if (Cout == 1) { L.host_scale_valid = true; L.host_scale = scale[0]; L.host_shift = shift[0]; }
     rc = conv_direct_run(L, st);
-    RYK_CUDA(cudaEventRecord(ev0, st));
-    for (int i = 0; i < repeat && !rc; ++i) rc = conv_direct_run(L, st);
-    RYK_CUDA(cudaEventRecord(ev1, st));
+    if (!rc && repeat > 0) rc = timed_graph([&]() { return conv_direct_run(L, st); });
     if (out_h) k_f16_to_f32<<<1184, 256, 0, st>>>(d_ho, d_out, no);
   } else {
     L.in0 = d_in0; L.in1 = n1 ? d_in1 : nullptr; L.in_dtype = DT_F32; L.out = d_out; L.out_dtype = DT_F32;
     rc = conv_direct_run(L, st);
-    RYK_CUDA(cudaEventRecord(ev0, st));
-    for (int i = 0; i < repeat && !rc; ++i) rc = conv_direct_run(L, st);
-    RYK_CUDA(cudaEventRecord(ev1, st));
+    if (!rc && repeat > 0) rc = timed_graph([&]() { return conv_direct_run(L, st); });
   }
   if (!rc) {
     cudaError_t err = cudaMemcpyAsync(out, d_out, no * 4, cudaMemcpyDeviceToHost, st);

@@ -275,6 +275,46 @@ __global__ void __launch_bounds__(256) k_conv3x3_cout1_h(const __half* __restric
   }
 }
 
+// Last layer of the stage-1 1-D U-Net: k3 s1 p1 over two fp16 sources of 64 channels -> Cout <= 16 channels, fp32.
+// One warp per output position: lane l owns channels 4l..4l+3 of the concatenated 128 (lanes 0-15 source 0, 16-31
+// source 1), 3 taps x 4 channels x Cout FMAs, warp-shuffle reduction per output channel.  (The generic 64x64x16 tile
+// kernel put this layer on 6 CTAs: 39 us for 0.3 MFLOP.)
+__global__ void __launch_bounds__(256) k_conv1d_k3_small(const __half* __restrict__ in0, const __half* __restrict__ in1,
+                                                        const float* __restrict__ w /*[3][128][Cout]*/, const float* __restrict__ scale,
+                                                        const float* __restrict__ shift, int act, int B, int W, int Cout, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int pos = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (pos >= B * W) return;
+  const int b = pos / W, x = pos - b * W;
+  const __half* src = lane < 16 ? in0 : in1;
+  const int c = (lane & 15) * 4, cg = lane * 4;       // channel inside the source / inside the concatenation
+  float xin[3][4];
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    const int ix = x + t - 1;
+    uint2 raw = make_uint2(0u, 0u);
+    if (ix >= 0 && ix < W) raw = __ldg(reinterpret_cast<const uint2*>(src + ((size_t)b * W + ix) * 64 + c));
+    const float2 f01 = __half22float2(*reinterpret_cast<__half2*>(&raw.x)), f23 = __half22float2(*reinterpret_cast<__half2*>(&raw.y));
+    xin[t][0] = f01.x; xin[t][1] = f01.y; xin[t][2] = f23.x; xin[t][3] = f23.y;
+  }
+  float mine = 0.f;
+  for (int co = 0; co < Cout; ++co) {
+    float a = 0.f;
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a = fmaf(xin[t][j], __ldg(w + ((size_t)t * 128 + cg + j) * Cout + co), a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == co) mine = a;
+  }
+  if (lane < Cout) {
+    float a = mine * __ldg(scale + lane) + __ldg(shift + lane);
+    if (act == ACT_LEAKY) a = a > 0.f ? a : 0.2f * a; else if (act == ACT_RELU) a = fmaxf(a, 0.f);
+    out[(size_t)pos * Cout + lane] = a;
+  }
+}
+
 __global__ void k_read2(const float* a, const float* b, float* out) { out[0] = a[0]; out[1] = b[0]; }
 
 int conv_direct_run(const ConvLayer& L, cudaStream_t st) {
@@ -297,6 +337,14 @@ int conv_direct_run(const ConvLayer& L, cudaStream_t st) {
       RYK_CUDA(cudaGetLastError());
       return 0;
     }
+  }
+  if (!L.transposed && L.KH == 1 && L.KW == 3 && L.SW == 1 && L.PW == 1 && L.Hin == 1 && L.C0 == 64 && L.C1 == 64 && L.Cout <= 16 &&
+      L.in_dtype == DT_F16 && L.out_dtype == DT_F32) {
+    const int npos = L.B * L.Win;
+    k_conv1d_k3_small<<<(npos + 7) / 8, 256, 0, st>>>((const __half*)L.in0, (const __half*)L.in1, L.w_direct, L.scale, L.shift, L.act, L.B, L.Win, L.Cout,
+                                                     (float*)L.out);
+    RYK_CUDA(cudaGetLastError());
+    return 0;
   }
   return conv_direct_generic(L, st);
 }

@@ -97,3 +97,21 @@ def test_edge_layer_kernels(engine, case):
     err = np.abs(got - ref).max()
     print('edge', case, 'max err', err)
     assert err < (5e-3 if Cin == 1 else 1e-4), err     # Cin = 1 writes fp16 (|y| < 8 -> half ulp 2^-9 * 4)
+
+
+@pytest.mark.parametrize('case', [(1, 384, 9), (2, 131, 9), (1, 40, 16)])
+def test_stage1_last_layer_kernel(engine, case):
+    """k_conv1d_k3_small (conv_direct.cu): the 1-D k3 output layer of the stage-1 net, fp16 inputs (64 + 64 channels) -> fp32."""
+    B, W, Cout = case
+    rng = np.random.default_rng(W + Cout)
+    in0 = rng.standard_normal((B, 1, W, 64)).astype(np.float32)
+    in1 = rng.standard_normal((B, 1, W, 64)).astype(np.float32)
+    Wt = (rng.standard_normal((Cout, 128, 1, 3)) / np.sqrt(128 * 3)).astype(np.float32)
+    scale = rng.uniform(0.8, 1.2, Cout).astype(np.float32)
+    shift = (0.1 * rng.standard_normal(Cout)).astype(np.float32)
+    r0, r1 = in0.astype(np.float16).astype(np.float32), in1.astype(np.float16).astype(np.float32)
+    ref = _ref(r0, r1, Wt, scale, shift, 0, 3, 1, 1, 0)
+    got, _ = engine.test_conv_layer(in0, in1, Wt, scale, shift, 0, 3, 1, 1, 0, use_tc=2)
+    err = np.abs(got - ref).max()
+    print('stage-1 last layer', case, 'max err', err)
+    assert err < 1e-4, err
