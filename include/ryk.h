@@ -110,6 +110,35 @@ int ryk_synth_synthesis2(ryk_engine* e, int synth_id, double* buffer);
 int ryk_synth_decode(ryk_engine* e, int synth_id, const double* f0, int n, const float* sp, const float* ap,
                      double* out, int max_blocks, int* n_blocks);
 
+/* ---- offline synthesis: Vocoder.decode = pyworld.synthesize ---------------------
+ * Replaces realtime_voice_conversion/yukarin_wrapper/vocoder.py:50-62 (pyworld.synthesize -> WORLD Synthesis()):
+ * whole-utterance time base, fractional pulse shift, Hanning dc-remover, overlap-add.  y receives
+ * ryk_world_synthesize_length(n_frames, frame_period_ms, fs) = (int)(n_frames * frame_period_ms * fs / 1000) doubles.
+ * pulse_index / pulse_shift / pulse_vuv (each may be NULL, max_pulses entries) expose the pulse plan for parity tests. */
+int ryk_world_synthesize_length(int n_frames, double frame_period_ms, int fs);
+int ryk_world_synthesize(ryk_engine* e, const double* f0, int n_frames, const float* sp, const float* ap, int fs,
+                         double frame_period_ms, int fft_size, double* y, int y_capacity, int* y_length,
+                         long long* pulse_index, double* pulse_shift, int* pulse_vuv, int max_pulses, int* n_pulses);
+
+/* ---- output silence gate and re-blocking ------------------------------------------
+ * Replaces realtime_voice_conversion/worker/decode_worker.py:38-59: the synthesizer's 1024-sample blocks are queued in a
+ * fragment, one out_audio_chunk is cut off its front per step when enough samples are queued, and the chunk is dropped
+ * when librosa.power_to_db(abs(librosa.stft(chunk)) ** 2).mean() < -output_silent_threshold
+ * (n_fft 2048, hop 512, periodic Hann, reflect-centred, amin 1e-10, top_db 80).
+ * ryk_output_gate: the gate alone on a host chunk; *pass = 1 keeps the chunk.
+ * ryk_reblock_*: device-resident fragment + gate.  push_device is stream-ordered and never syncs the host: with
+ * session_id >= 0 it is queued on that session's decode stream right behind its latest step (wave_dev == NULL consumes the
+ * step's blocks and count in place); results go to ring slot ticket % 8.  collect: *status 0 = no chunk this step,
+ * 1 = chunk copied to chunk_out, 2 = chunk was silent (the reference forwards None). */
+int ryk_output_gate(ryk_engine* e, const double* wave, int n, int n_fft, int hop, double threshold_db, double* power_db, int* pass);
+int ryk_reblock_create(ryk_engine* e, int out_audio_chunk, int max_in, int n_fft, int hop, double threshold_db, int* reblock_id);
+int ryk_reblock_destroy(ryk_engine* e, int reblock_id);
+int ryk_reblock_push(ryk_engine* e, int reblock_id, const double* wave, int n, double* chunk_out, int* status, double* power_db);
+int ryk_reblock_push_device(ryk_engine* e, int reblock_id, int session_id, const double* wave_dev, const int* n_dev, long long* ticket);
+int ryk_reblock_collect(ryk_engine* e, int reblock_id, long long ticket, double* chunk_out, int* status, double* power_db);
+int ryk_reblock_result_device(ryk_engine* e, int reblock_id, long long ticket, const double** chunk_dev, const int** status_dev,
+                              const double** power_dev);
+
 /* ---- device-resident streaming session (one audio stream) -------------------------------------- */
 typedef struct {
   int fs;                       /* 24000 */

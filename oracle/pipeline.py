@@ -11,7 +11,7 @@ PARITY UNPINNED (see oracle/world_oracle.c).  DECIDE points mirrored from DESIGN
   ref = max over the window, fp64; silent template mc0 = ln(1e-8); F0 conversion in fp64 -> fp32.
 """
 from dataclasses import dataclass
-from typing import Dict, Optional
+from typing import Dict, Optional, Tuple
 
 import numpy as np
 
@@ -176,3 +176,26 @@ class StreamOracle:
         self.k += 1
         self.last = dict(encoded=f, converted=conv)
         return y
+
+
+class OutputReblockOracle:
+    """decode_worker.py:38-59 restated: `wave_fragment` accumulation, one out_audio_chunk per step, and the output silence
+    gate power_to_db(abs(stft(chunk)) ** 2).mean() < -threshold (oracle/world.py: stft_power_db_mean)."""
+
+    def __init__(self, out_audio_chunk: int, output_silent_threshold: float):
+        self.chunk = int(out_audio_chunk)
+        self.threshold = float(output_silent_threshold)
+        self.fragment = np.empty(0)
+        self.last_power = None
+
+    def push(self, wave: np.ndarray) -> Tuple[int, Optional[np.ndarray]]:
+        """-> (status, chunk): 0 = not enough samples yet, 1 = chunk, 2 = silent chunk (the reference forwards None)."""
+        self.fragment = np.concatenate([self.fragment, np.asarray(wave, np.float64)])
+        if len(self.fragment) < self.chunk:
+            self.last_power = None
+            return 0, None
+        wave, self.fragment = self.fragment[:self.chunk], self.fragment[self.chunk:]
+        self.last_power = W.stft_power_db_mean(wave)
+        if self.last_power < -self.threshold:
+            return 2, None
+        return 1, wave

@@ -206,3 +206,39 @@ class RealtimeSynthesizer:
             lib().wo_synth_destroy(self._h)
         except Exception:
             pass
+
+
+def synthesize(f0, sp, ap, fs, frame_period=5.0, fft_size=None, return_pulses=False):
+    """pyworld.synthesize restated (WORLD synthesis.cpp Synthesis(); call site
+    realtime_voice_conversion/yukarin_wrapper/vocoder.py:50-62).  sp / ap enter as float32."""
+    f0 = _f64(np.asarray(f0).ravel())
+    sp = np.ascontiguousarray(sp, dtype=np.float32)
+    ap = np.ascontiguousarray(ap, dtype=np.float32)
+    if fft_size is None:
+        fft_size = (sp.shape[1] - 1) * 2
+    L = lib()
+    L.wo_synthesize_length.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_int]
+    n = L.wo_synthesize_length(len(f0), float(frame_period), int(fs))
+    y = np.zeros(max(n, 0))
+    cap = max(n, 1)
+    idx = np.zeros(cap, dtype=np.int64)
+    shift = np.zeros(cap)
+    vuv = np.zeros(cap, dtype=np.int32)
+    L.wo_synthesize.argtypes = [c_double_p, ctypes.c_int, c_float_p, c_float_p, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int,
+                                c_double_p, ctypes.c_int, c_ll_p, c_double_p, c_int_p]
+    L.wo_synthesize.restype = ctypes.c_int
+    npulse = L.wo_synthesize(_dp(f0), len(f0), sp.ctypes.data_as(c_float_p), ap.ctypes.data_as(c_float_p), int(fft_size), float(frame_period),
+                             int(fs), n, _dp(y), cap, idx.ctypes.data_as(c_ll_p), _dp(shift), vuv.ctypes.data_as(c_int_p))
+    if return_pulses:
+        return y, idx[:npulse], shift[:npulse], vuv[:npulse]
+    return y
+
+
+def stft_power_db_mean(wave, n_fft=2048, hop=512, amin=1e-10, top_db=80.0) -> float:
+    """librosa.core.power_to_db(numpy.abs(librosa.stft(wave)) ** 2).mean() restated
+    (realtime_voice_conversion/worker/decode_worker.py:56), fp64."""
+    w = _f64(np.asarray(wave).ravel())
+    L = lib()
+    L.wo_stft_power_db_mean.restype = ctypes.c_double
+    L.wo_stft_power_db_mean.argtypes = [c_double_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double]
+    return float(L.wo_stft_power_db_mean(_dp(w), len(w), int(n_fft), int(hop), float(amin), float(top_db)))

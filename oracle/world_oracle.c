@@ -1012,3 +1012,197 @@ void wo_synth_get_pulses(void *h, long long first, int count, long long *index, 
     index[i] = s->p_index[slot]; time[i] = s->p_time[slot]; vuv[i] = s->p_vuv[slot];
   }
 }
+
+/* ------------------------------------------------------------------ WORLD offline Synthesis()
+ * realtime_voice_conversion/yukarin_wrapper/vocoder.py:50-62 calls
+ * pyworld.synthesize(f0, spectrogram, aperiodicity, fs, frame_period) = WORLD synthesis.cpp
+ * Synthesis() with y_length = (int)(f0_length * frame_period * fs / 1000) (pyworld.pyx).
+ * Restated from WORLD v0.2.3+ (the version with the fractional pulse time shift):
+ * GetTimeBase / GetTemporalParametersForTimeBase / GetPulseLocationsForTimeBase, GetDCRemover
+ * (normalised Hanning over the whole fft_size), GetPeriodicResponse (+ linear-phase fractional
+ * shift) / GetAperiodicResponse / GetOneFrameSegment, overlap-add at index - fft/2 + 1.
+ * DECIDE (shared with the realtime synthesizer above): total phase summed in the fixed blocked
+ * order (256-sample blocks), randn addressed by absolute sample position (pulse at sample q
+ * uses draws [q, q + noise_size) of the canonical xorshift128 stream), features enter as float32.
+ * [UPSTREAM-UNVERIFIED] like the rest of this file. */
+int wo_synthesize_length(int f0_length, double frame_period_ms, int fs) {
+  return (int)((double)f0_length * frame_period_ms * fs / 1000.0);
+}
+
+int wo_synthesize(const double *f0, int f0_length, const float *sp, const float *ap, int fft_size,
+                  double frame_period_ms, int fs, int y_length, double *y,
+                  int max_pulses, long long *pulse_index, double *pulse_shift, int *pulse_vuv) {
+  const int n = fft_size, nb = n / 2 + 1;
+  const double frame_period = frame_period_ms / 1000.0;
+  const double lowest_f0 = (double)fs / fft_size + 1.0;
+  for (int i = 0; i < y_length; ++i) y[i] = 0.0;
+  if (y_length < 2 || f0_length < 1) return 0;
+  /* coarse axes with one extrapolated point */
+  int nc = f0_length + 1;
+  double *ct = (double *)malloc(sizeof(double) * nc), *cf = (double *)malloc(sizeof(double) * nc), *cv = (double *)malloc(sizeof(double) * nc);
+  for (int i = 0; i < f0_length; ++i) {
+    ct[i] = i * frame_period;
+    cf[i] = f0[i] < lowest_f0 ? 0.0 : f0[i];
+    cv[i] = cf[i] == 0.0 ? 0.0 : 1.0;
+  }
+  ct[f0_length] = f0_length * frame_period;
+  if (f0_length >= 2) {
+    cf[f0_length] = cf[f0_length - 1] * 2.0 - cf[f0_length - 2];
+    cv[f0_length] = cv[f0_length - 1] * 2.0 - cv[f0_length - 2];
+  } else { cf[f0_length] = cf[0]; cv[f0_length] = cv[0]; }
+  double *ta = (double *)malloc(sizeof(double) * y_length), *if0 = (double *)malloc(sizeof(double) * y_length), *ivuv = (double *)malloc(sizeof(double) * y_length);
+  for (int i = 0; i < y_length; ++i) ta[i] = (double)i / (double)fs;
+  wo_interp1(ct, cf, nc, ta, y_length, if0);
+  wo_interp1(ct, cv, nc, ta, y_length, ivuv);
+  for (int i = 0; i < y_length; ++i) {
+    ivuv[i] = ivuv[i] > 0.5 ? 1.0 : 0.0;
+    if0[i] = ivuv[i] == 0.0 ? WO_DEFAULT_F0 : if0[i];
+  }
+  /* total phase: blocked fixed-order prefix sum of 2 pi f0 / fs (inclusive: tp[0] = first increment) */
+  double *tp = (double *)malloc(sizeof(double) * y_length), *wp = (double *)malloc(sizeof(double) * y_length);
+  {
+    const int BLK = 256;
+    double base = 0.0;
+    for (int b0 = 0; b0 < y_length; b0 += BLK) {
+      int b1 = b0 + BLK < y_length ? b0 + BLK : y_length;
+      double local = 0.0;
+      for (int i = b0; i < b1; ++i) { local = local + 2.0 * WO_PI * if0[i] / fs; tp[i] = base + local; }
+      base = base + local;
+    }
+  }
+  for (int i = 0; i < y_length; ++i) wp[i] = fmod(tp[i], 2.0 * WO_PI);
+  int np_ = 0;
+  long long *pidx = (long long *)malloc(sizeof(long long) * y_length);
+  double *pshift = (double *)malloc(sizeof(double) * y_length);
+  for (int i = 0; i < y_length - 1; ++i) {
+    if (fabs(wp[i + 1] - wp[i]) > WO_PI) {
+      double y1 = wp[i] - 2.0 * WO_PI, y2 = wp[i + 1];
+      double x = -y1 / (y2 - y1);
+      pidx[np_] = i; pshift[np_] = x / fs; ++np_;
+    }
+  }
+  /* dc remover over the whole fft_size */
+  double *dcr = (double *)malloc(sizeof(double) * n);
+  {
+    double dc = 0.0;
+    for (int i = 0; i < n / 2; ++i) {
+      dcr[i] = 0.5 - 0.5 * cos(2.0 * WO_PI * (i + 1.0) / (1.0 + n));
+      dcr[n - i - 1] = dcr[i];
+      dc += dcr[i] * 2.0;
+    }
+    for (int i = 0; i < n / 2; ++i) { dcr[i] /= dc; dcr[n - i - 1] = dcr[i]; }
+  }
+  double *spec = (double *)malloc(sizeof(double) * nb), *apr = (double *)malloc(sizeof(double) * nb), *lg = (double *)malloc(sizeof(double) * nb);
+  double *re = (double *)malloc(sizeof(double) * n), *im = (double *)malloc(sizeof(double) * n);
+  double *nr = (double *)malloc(sizeof(double) * n), *ni = (double *)malloc(sizeof(double) * n);
+  double *periodic = (double *)malloc(sizeof(double) * n), *aperiodic = (double *)malloc(sizeof(double) * n), *tmp = (double *)malloc(sizeof(double) * n);
+  double *noise = (double *)malloc(sizeof(double) * n);
+  wo_rng rng; wo_rng_seed(&rng);
+  long long rng_pos = 0;
+  for (int p = 0; p < np_; ++p) {
+    long long idx = pidx[p];
+    int noise_size = (int)(pidx[p + 1 < np_ ? p + 1 : np_ - 1] - idx);
+    if (noise_size > n) noise_size = n;
+    double t = ta[idx];
+    int vuv = ivuv[idx] > 0.5 ? 1 : 0;
+    if (p < max_pulses) { if (pulse_index) pulse_index[p] = idx; if (pulse_shift) pulse_shift[p] = pshift[p]; if (pulse_vuv) pulse_vuv[p] = vuv; }
+    int fl = (int)floor(t / frame_period), ce = (int)ceil(t / frame_period);
+    if (fl > f0_length - 1) fl = f0_length - 1;
+    if (ce > f0_length - 1) ce = f0_length - 1;
+    double interp = t / frame_period - fl;
+    const float *sp0 = sp + (size_t)fl * nb, *sp1 = sp + (size_t)ce * nb, *ap0 = ap + (size_t)fl * nb, *ap1 = ap + (size_t)ce * nb;
+    for (int i = 0; i < nb; ++i) {
+      if (fl == ce) { spec[i] = fabs((double)sp0[i]); apr[i] = pow(safe_ap((double)ap0[i]), 2.0); }
+      else {
+        spec[i] = (1.0 - interp) * fabs((double)sp0[i]) + interp * fabs((double)sp1[i]);
+        apr[i] = pow((1.0 - interp) * safe_ap((double)ap0[i]) + interp * safe_ap((double)ap1[i]), 2.0);
+      }
+    }
+    if (vuv == 0 || apr[0] > 0.999) {
+      for (int i = 0; i < n; ++i) periodic[i] = 0.0;
+    } else {
+      for (int i = 0; i < nb; ++i) lg[i] = log(spec[i] * (1.0 - apr[i]) + WO_SAFE_MIN) / 2.0;
+      min_phase(lg, n, re, im);
+      double coef = 2.0 * WO_PI * pshift[p] * fs / n;
+      for (int i = 0; i < nb; ++i) {
+        double r = re[i], m = im[i];
+        double re2 = cos(coef * i), im2 = sqrt(1.0 - re2 * re2);
+        re[i] = r * re2 + m * im2;
+        im[i] = m * re2 - r * im2;
+      }
+      irfft_unnorm(re, im, n, tmp);
+      for (int i = 0; i < n / 2; ++i) { periodic[i] = tmp[i + n / 2]; periodic[i + n / 2] = tmp[i]; }
+      double dc = 0.0;
+      for (int i = n / 2; i < n; ++i) dc += periodic[i];
+      for (int i = 0; i < n / 2; ++i) periodic[i] = -dc * dcr[i];
+      for (int i = n / 2; i < n; ++i) periodic[i] -= dc * dcr[i];
+    }
+    if (noise_size > 0) {
+      while (rng_pos < idx) { wo_randn(&rng); rng_pos++; }      /* windows [idx, idx + noise_size) ascend and never overlap */
+      for (int i = 0; i < noise_size; ++i) noise[i] = wo_randn(&rng);
+      rng_pos += noise_size;
+      double avg = 0.0;
+      for (int i = 0; i < noise_size; ++i) avg += noise[i];
+      avg /= noise_size;
+      for (int i = 0; i < noise_size; ++i) tmp[i] = noise[i] - avg;
+    }
+    for (int i = noise_size; i < n; ++i) tmp[i] = 0.0;
+    rfft(tmp, n, nr, ni);
+    if (vuv != 0) for (int i = 0; i < nb; ++i) lg[i] = log(spec[i] * apr[i]) / 2.0;
+    else for (int i = 0; i < nb; ++i) lg[i] = log(spec[i]) / 2.0;
+    min_phase(lg, n, re, im);
+    for (int i = 0; i < nb; ++i) {
+      double a = re[i] * nr[i] - im[i] * ni[i], b = re[i] * ni[i] + im[i] * nr[i];
+      re[i] = a; im[i] = b;
+    }
+    irfft_unnorm(re, im, n, tmp);
+    for (int i = 0; i < n / 2; ++i) { aperiodic[i] = tmp[i + n / 2]; aperiodic[i + n / 2] = tmp[i]; }
+    double sq = sqrt((double)noise_size);
+    long long offset = idx - n / 2 + 1;
+    int lower = (int)(offset < 0 ? -offset : 0);
+    int upper = (int)(n < y_length - offset ? n : y_length - offset);
+    for (int i = lower; i < upper; ++i) y[i + offset] += (periodic[i] * sq + aperiodic[i]) / n;
+  }
+  free(ct); free(cf); free(cv); free(ta); free(if0); free(ivuv); free(tp); free(wp); free(pidx); free(pshift); free(dcr);
+  free(spec); free(apr); free(lg); free(re); free(im); free(nr); free(ni); free(periodic); free(aperiodic); free(tmp); free(noise);
+  return np_;
+}
+
+/* ------------------------------------------------------------------ output silence gate
+ * realtime_voice_conversion/worker/decode_worker.py:53-59:
+ *   power = librosa.core.power_to_db(numpy.abs(librosa.stft(wave)) ** 2).mean();  drop if power < -threshold
+ * librosa (0.6/0.7 era) defaults: n_fft 2048, hop 512, periodic Hann window, center=True with reflect
+ * padding, frames = 1 + len // hop; power_to_db(ref=1, amin=1e-10, top_db=80):
+ *   db = 10 log10(max(amin, S));  db = max(db, max(db) - top_db);  mean over bins and frames.
+ * DECIDE: fp64 throughout (librosa stores the STFT as complex64) so the decision is reproducible. */
+int wo_stft_frames(int n, int hop) { return 1 + n / hop; }
+
+double wo_stft_power_db_mean(const double *wave, int n, int n_fft, int hop, double amin, double top_db) {
+  int frames = wo_stft_frames(n, hop), nb = n_fft / 2 + 1, pad = n_fft / 2;
+  double *win = (double *)malloc(sizeof(double) * n_fft), *buf = (double *)malloc(sizeof(double) * n_fft);
+  double *re = (double *)malloc(sizeof(double) * n_fft), *im = (double *)malloc(sizeof(double) * n_fft);
+  double *db = (double *)malloc(sizeof(double) * (size_t)frames * nb);
+  for (int i = 0; i < n_fft; ++i) win[i] = 0.5 - 0.5 * cos(2.0 * WO_PI * i / n_fft);
+  double mx = -1e300;
+  for (int f = 0; f < frames; ++f) {
+    for (int j = 0; j < n_fft; ++j) {
+      int idx = f * hop + j - pad;
+      if (idx < 0) idx = -idx;
+      if (idx >= n) idx = 2 * (n - 1) - idx;
+      if (idx < 0) idx = 0;
+      if (idx >= n) idx = n - 1;
+      buf[j] = wave[idx] * win[j];
+    }
+    rfft(buf, n_fft, re, im);
+    for (int k = 0; k < nb; ++k) {
+      double pw = re[k] * re[k] + im[k] * im[k];
+      double d = 10.0 * log10(pw > amin ? pw : amin);
+      db[(size_t)f * nb + k] = d;
+      if (d > mx) mx = d;
+    }
+  }
+  double acc = 0.0;
+  for (size_t i = 0; i < (size_t)frames * nb; ++i) acc += db[i] > mx - top_db ? db[i] : mx - top_db;
+  free(win); free(buf); free(re); free(im); free(db);
+  return acc / ((double)frames * nb);
+}

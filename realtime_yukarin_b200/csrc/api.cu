@@ -564,6 +564,49 @@ int ryk_synth_decode(ryk_engine* h, int id, const double* f0, int n, const float
 }
 
 
+// ---- offline synthesis (pyworld.synthesize; vocoder.py:50-62) and the output silence gate (decode_worker.py:53-59) ----
+int ryk_world_synthesize_length(int n_frames, double frame_period_ms, int fs) {
+  return (int)((double)n_frames * frame_period_ms * fs / 1000.0);
+}
+
+int ryk_world_synthesize(ryk_engine* h, const double* f0, int n_frames, const float* sp, const float* ap, int fs, double frame_period_ms,
+                         int fft_size, double* y, int y_capacity, int* y_length, long long* pulse_index, double* pulse_shift, int* pulse_vuv,
+                         int max_pulses, int* n_pulses) {
+  Engine* e = E(h);
+  RYK_CUDA(cudaSetDevice(e->device));
+  RYK_CHECK(f0 && sp && ap && y && n_frames >= 1, "null or empty synthesis input");
+  const int ny = ryk_world_synthesize_length(n_frames, frame_period_ms, fs);
+  RYK_CHECK(ny <= y_capacity, "output buffer too small: ryk_world_synthesize_length samples are written");
+  const int np = world_synthesize_run(e, f0, n_frames, sp, ap, fs, frame_period_ms, fft_size, y, ny, pulse_index, pulse_shift, pulse_vuv, max_pulses);
+  if (np < 0) return -1;
+  if (y_length) *y_length = ny;
+  if (n_pulses) *n_pulses = np;
+  return 0;
+}
+
+int ryk_output_gate(ryk_engine* h, const double* wave, int n, int n_fft, int hop, double threshold_db, double* power_db, int* pass) {
+  Engine* e = E(h);
+  RYK_CUDA(cudaSetDevice(e->device));
+  RYK_CHECK(wave != nullptr && n > 0, "empty chunk");
+  const size_t scratch = output_gate_scratch_doubles(n, n_fft, hop);
+  void* buf = nullptr;
+  if (engine_scratch(e, sizeof(double) * (n + scratch + 2) + 64, &buf)) return -1;
+  double* d_wave = (double*)buf;
+  double* d_scr = d_wave + n;
+  double* d_power = d_scr + scratch;
+  int* d_status = (int*)(d_power + 1);
+  RYK_CUDA(cudaMemcpyAsync(d_wave, wave, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
+  if (output_gate_async(e, d_wave, nullptr, n, n_fft, hop, threshold_db, d_scr, d_power, d_status, e->stream)) return -1;
+  double pw = 0.0; int st = 0;
+  RYK_CUDA(cudaMemcpyAsync(&pw, d_power, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  RYK_CUDA(cudaMemcpyAsync(&st, d_status, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  RYK_CUDA(cudaStreamSynchronize(e->stream));
+  if (power_db) *power_db = pw;
+  if (pass) *pass = st == 1 ? 1 : 0;
+  return 0;
+}
+
+
 // ---- diagnostics: the synthesizer's pulse ring (index, time, vuv) and scalar state
 int ryk_debug_synth_pulses(ryk_engine* h, int id, long long first, int count, long long* index, double* time, int* vuv, long long* state7) {
   Engine* e = E(h);

@@ -15,6 +15,7 @@ namespace ryk {
 struct DioPlan;
 struct Session;
 struct Group;
+struct Reblock;
 
 struct Engine {
   int device = 0;
@@ -41,6 +42,7 @@ struct Engine {
   std::vector<Synth*> synths;
   std::vector<Session*> sessions;
   std::vector<Group*> groups;
+  std::vector<Reblock*> reblocks;     // output re-blockers + silence gates (decode_worker.py:38-59)
   float* d_colmin = nullptr;         // stage-2 prologue column-minimum partials
   // scratch arena for the per-op host-pointer API (grown on demand)
   void* d_scratch = nullptr; size_t scratch_bytes = 0;
@@ -69,6 +71,13 @@ int dio_plan_debug_copy(DioPlan* p, double* f0_raw, double* cand, double* score,
 int spectral_analysis_run(Engine* e, const float* d_x, int n, int fs, double frame_period, const double* d_f0, int n_out,
                           int fft_size, int order, float* d_sp, float* d_ap, float* d_mc, float* d_f0_out, uint8_t* d_voiced,
                           cudaStream_t st);
+
+// world_synth.cu: offline Synthesis() (pyworld.synthesize) and the output silence gate
+int world_synthesize_run(Engine* e, const double* f0, int n_frames, const float* sp, const float* ap, int fs, double frame_period_ms,
+                         int fft_size, double* y, int y_length, long long* pulse_index, double* pulse_shift, int* pulse_vuv, int max_pulses);
+int output_gate_async(Engine* e, const double* d_wave, const int* d_n_valid, int n, int n_fft, int hop, double threshold_db,
+                      double* d_scratch, double* d_power, int* d_status, cudaStream_t st);
+size_t output_gate_scratch_doubles(int n, int n_fft, int hop);
 
 // sptk.cu
 int sptk_prepare(Engine* e, int order, double alpha, int fft_size);                 // builds G and H on the device

@@ -21,6 +21,7 @@
 // plan (T_eff + 128 - T_eff % 128); the gate runs first in stream E so the count is on the host long before
 // stream C needs it.
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <map>
@@ -129,6 +130,59 @@ __global__ void k_f32_to_f64(const float* __restrict__ a, double* __restrict__ b
   if (i < n) b[i] = (double)a[i];
 }
 
+// ---- output re-blocker + silence gate (realtime_voice_conversion/worker/decode_worker.py:38-59) ----
+// The reference's decode worker concatenates the synthesizer blocks into `wave_fragment`, cuts one out_audio_chunk off its
+// front whenever enough samples are queued (at most one per step) and drops the chunk when its mean STFT power is below
+// -output_silent_threshold dB.  Here the fragment lives in HBM (ping-pong buffers), the sample count of a step is read from
+// device memory (no host sync) and the gate kernels (world_synth.cu) are predicated on the device-side "chunk emitted" flag.
+struct ReblockState { int len, sel, overflow; };
+struct Reblock {
+  int chunk = 0, max_in = 0, cap = 0, n_fft = 2048, hop = 512;
+  double threshold_db = 80.0;
+  ReblockState* d_state = nullptr;
+  double* d_frag[2] = {nullptr, nullptr};
+  double* d_scratch = nullptr;
+  double* d_chunk[kRing]; int* d_nvalid[kRing]; int* d_status[kRing]; double* d_power[kRing];
+  double* h_chunk[kRing]; int* h_status[kRing]; double* h_power[kRing];
+  cudaEvent_t ev[kRing];
+  double* d_stage_in = nullptr; int* d_stage_n = nullptr;     // staging for the host-buffer entry point
+  long long pushed = 0;
+  std::vector<void*> allocs, pinned;
+};
+
+static void reblock_free(Reblock* R) {
+  if (!R) return;
+  for (int i = 0; i < kRing; ++i) if (R->ev[i]) cudaEventDestroy(R->ev[i]);
+  for (void* p : R->allocs) cudaFree(p);
+  for (void* p : R->pinned) cudaFreeHost(p);
+  delete R;
+}
+
+__global__ void __launch_bounds__(1024) k_reblock(ReblockState* __restrict__ st, double* __restrict__ frag0, double* __restrict__ frag1, int cap,
+                                                 const double* __restrict__ in, const int* __restrict__ n_in_p, int max_in, int chunk,
+                                                 double* __restrict__ out, int* __restrict__ n_valid) {
+  __shared__ int sh_len, sh_sel;
+  if (threadIdx.x == 0) { sh_len = st->len; sh_sel = st->sel; }
+  __syncthreads();
+  const int len = sh_len, sel = sh_sel;
+  int n_in = *n_in_p;
+  if (n_in < 0) n_in = 0;
+  if (n_in > max_in) n_in = max_in;
+  double* cur = sel ? frag1 : frag0;
+  double* nxt = sel ? frag0 : frag1;
+  const int new_len = len + n_in;
+  if (new_len >= chunk) {
+    int rest = new_len - chunk, over = 0;
+    if (rest > cap) { rest = cap; over = 1; }
+    for (int i = threadIdx.x; i < chunk; i += blockDim.x) out[i] = i < len ? cur[i] : in[i - len];
+    for (int j = threadIdx.x; j < rest; j += blockDim.x) { const int i = chunk + j; nxt[j] = i < len ? cur[i] : in[i - len]; }
+    if (threadIdx.x == 0) { st->len = rest; st->sel = sel ^ 1; st->overflow |= over; *n_valid = chunk; }
+  } else {
+    for (int i = threadIdx.x; i < n_in; i += blockDim.x) cur[len + i] = in[i];
+    if (threadIdx.x == 0) { st->len = new_len; *n_valid = 0; }
+  }
+}
+
 // NaN -> 0 on the produced samples (decode_stream.py:38) and publish the sample count
 __global__ void k_scrub(double* __restrict__ y, const SynthState* __restrict__ st, int block, int max_samples, int* __restrict__ n_out) {
   int n = st->blocks_out * block;
@@ -193,6 +247,8 @@ static void group_free(Group* G) {
 }
 
 void session_destroy_all(Engine* e) {
+  for (Reblock* R : e->reblocks) reblock_free(R);
+  e->reblocks.clear();
   for (Group* G : e->groups) group_free(G);
   e->groups.clear();
   for (Session* s : e->sessions) session_free(s);
@@ -551,11 +607,15 @@ int ryk_session_create(ryk_engine* h, const ryk_session_config* cfg, int* sessio
   int prio_lo = 0, prio_hi = 0;
   RYK_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));      // lo = least (numerically largest), hi = greatest
   { const char* v = getenv("RYK_NO_PRIORITY"); if (v && atoi(v)) prio_hi = prio_lo; }
-  RYK_CUDA(cudaStreamCreateWithPriority(&s->sE, cudaStreamNonBlocking, prio_hi));
-  for (int i = 0; i < 2; ++i) RYK_CUDA(cudaStreamCreateWithPriority(&s->sA[i], cudaStreamNonBlocking, prio_hi));
-  RYK_CUDA(cudaStreamCreateWithPriority(&s->sC, cudaStreamNonBlocking, prio_hi));
-  RYK_CUDA(cudaStreamCreateWithPriority(&s->sC2, cudaStreamNonBlocking, prio_lo));
-  RYK_CUDA(cudaStreamCreateWithPriority(&s->sD, cudaStreamNonBlocking, prio_hi));
+  // RYK_PRIO="E,A,C,C2,D" (tuning experiments): priority level of each stream as steps above the lowest (0 .. lo - hi)
+  int lv[5] = {prio_lo - prio_hi, prio_lo - prio_hi, prio_lo - prio_hi, 0, prio_lo - prio_hi};
+  if (const char* v = getenv("RYK_PRIO")) sscanf(v, "%d,%d,%d,%d,%d", &lv[0], &lv[1], &lv[2], &lv[3], &lv[4]);
+  auto PR = [&](int i) { int l = lv[i] < 0 ? 0 : (lv[i] > prio_lo - prio_hi ? prio_lo - prio_hi : lv[i]); return prio_lo - l; };
+  RYK_CUDA(cudaStreamCreateWithPriority(&s->sE, cudaStreamNonBlocking, PR(0)));
+  for (int i = 0; i < 2; ++i) RYK_CUDA(cudaStreamCreateWithPriority(&s->sA[i], cudaStreamNonBlocking, PR(1)));
+  RYK_CUDA(cudaStreamCreateWithPriority(&s->sC, cudaStreamNonBlocking, PR(2)));
+  RYK_CUDA(cudaStreamCreateWithPriority(&s->sC2, cudaStreamNonBlocking, PR(3)));
+  RYK_CUDA(cudaStreamCreateWithPriority(&s->sD, cudaStreamNonBlocking, PR(4)));
   for (int i = 0; i < kRing; ++i) {
     cudaEvent_t* evs[] = {&s->ev_gate[i], &s->ev_pro[i], &s->ev_count[i], &s->ev_enc[i], &s->ev_cslide[i], &s->ev_s1[i], &s->ev_conv[i], &s->ev_dslide[i], &s->ev_dec[i]};
     for (cudaEvent_t* ev : evs) RYK_CUDA(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
@@ -853,6 +913,133 @@ int ryk_session_stage_times(ryk_engine* h, int id, float* start, float* end) {
     }
   }
   return n;
+}
+
+
+// ---- output re-blocker + silence gate -----------------------------------------------------------------
+static Reblock* get_reblock(Engine* e, int id) { return (id >= 0 && id < (int)e->reblocks.size()) ? e->reblocks[id] : nullptr; }
+
+int ryk_reblock_create(ryk_engine* h, int out_audio_chunk, int max_in, int n_fft, int hop, double threshold_db, int* reblock_id) {
+  Engine* e = &h->impl;
+  RYK_CUDA(cudaSetDevice(e->device));
+  RYK_CHECK(out_audio_chunk > n_fft / 2 && max_in > 0, "out_audio_chunk must exceed n_fft / 2 (reflect-centred STFT)");
+  RYK_CHECK(n_fft >= 64 && n_fft <= 4096 && (n_fft & (n_fft - 1)) == 0 && hop > 0, "unsupported STFT geometry");
+  Reblock* R = new Reblock();
+  for (int i = 0; i < kRing; ++i) R->ev[i] = nullptr;
+  R->chunk = out_audio_chunk; R->max_in = max_in; R->n_fft = n_fft; R->hop = hop; R->threshold_db = threshold_db;
+  R->cap = 2 * out_audio_chunk + 2 * max_in;
+  auto A = [&](void** p, size_t bytes) -> int { RYK_CUDA(cudaMalloc(p, bytes)); RYK_CUDA(cudaMemset(*p, 0, bytes)); R->allocs.push_back(*p); return 0; };
+  auto H = [&](void** p, size_t bytes) -> int { RYK_CUDA(cudaMallocHost(p, bytes)); memset(*p, 0, bytes); R->pinned.push_back(*p); return 0; };
+  int rc = 0;
+  rc |= A((void**)&R->d_state, sizeof(ReblockState));
+  for (int i = 0; i < 2; ++i) rc |= A((void**)&R->d_frag[i], sizeof(double) * R->cap);
+  rc |= A((void**)&R->d_scratch, sizeof(double) * output_gate_scratch_doubles(out_audio_chunk, n_fft, hop));
+  rc |= A((void**)&R->d_stage_in, sizeof(double) * max_in);
+  rc |= A((void**)&R->d_stage_n, sizeof(int));
+  for (int i = 0; i < kRing && !rc; ++i) {
+    rc |= A((void**)&R->d_chunk[i], sizeof(double) * out_audio_chunk);
+    rc |= A((void**)&R->d_nvalid[i], sizeof(int));
+    rc |= A((void**)&R->d_status[i], sizeof(int));
+    rc |= A((void**)&R->d_power[i], sizeof(double));
+    rc |= H((void**)&R->h_chunk[i], sizeof(double) * out_audio_chunk);
+    rc |= H((void**)&R->h_status[i], sizeof(int));
+    rc |= H((void**)&R->h_power[i], sizeof(double));
+    if (!rc && cudaEventCreateWithFlags(&R->ev[i], cudaEventDisableTiming) != cudaSuccess) rc = -1;
+  }
+  if (rc) { reblock_free(R); return -1; }
+  e->reblocks.push_back(R);
+  *reblock_id = (int)e->reblocks.size() - 1;
+  return 0;
+}
+
+int ryk_reblock_destroy(ryk_engine* h, int id) {
+  Engine* e = &h->impl;
+  Reblock* R = get_reblock(e, id);
+  RYK_CHECK(R != nullptr, "no such re-blocker");
+  RYK_CUDA(cudaDeviceSynchronize());
+  reblock_free(R);
+  e->reblocks[id] = nullptr;
+  return 0;
+}
+
+// Append *n_dev samples (device memory) and emit at most one chunk + its gate decision into ring slot ticket % 8.
+// session_id >= 0: the work is queued on that session's decode stream right behind its latest step; with wave_dev == NULL the
+// step's own output (blocks + count) is consumed in place.  session_id < 0: engine stream, wave_dev / n_dev required.
+int ryk_reblock_push_device(ryk_engine* h, int id, int session_id, const double* wave_dev, const int* n_dev, long long* ticket) {
+  Engine* e = &h->impl;
+  RYK_CUDA(cudaSetDevice(e->device));
+  Reblock* R = get_reblock(e, id);
+  RYK_CHECK(R != nullptr, "no such re-blocker");
+  cudaStream_t st = e->stream;
+  if (session_id >= 0) {
+    Session* s = get_session(e, session_id);
+    RYK_CHECK(s != nullptr, "no such session");
+    RYK_CHECK(s->step > 0, "the session has not processed a chunk yet");
+    st = s->sD;
+    if (!wave_dev) {
+      const int b = (int)((s->step - 1) & 1);
+      RYK_CHECK(s->max_blocks * s->cfg.vocoder_buffer_size <= R->max_in, "re-blocker max_in is smaller than the session's block capacity");
+      wave_dev = s->d_out_fixed[b]; n_dev = s->d_n_fixed[b];
+    }
+  }
+  RYK_CHECK(wave_dev != nullptr && n_dev != nullptr, "wave_dev / n_dev are required without an attached session");
+  const long long k = R->pushed;
+  const int r = (int)(k % kRing);
+  k_reblock<<<1, 1024, 0, st>>>(R->d_state, R->d_frag[0], R->d_frag[1], R->cap, wave_dev, n_dev, R->max_in, R->chunk, R->d_chunk[r], R->d_nvalid[r]);
+  e->launches += 1;
+  RYK_CUDA(cudaGetLastError());
+  if (output_gate_async(e, R->d_chunk[r], R->d_nvalid[r], R->chunk, R->n_fft, R->hop, R->threshold_db, R->d_scratch, R->d_power[r], R->d_status[r], st)) return -1;
+  RYK_CUDA(cudaMemcpyAsync(R->h_status[r], R->d_status[r], sizeof(int), cudaMemcpyDeviceToHost, st));
+  RYK_CUDA(cudaMemcpyAsync(R->h_power[r], R->d_power[r], sizeof(double), cudaMemcpyDeviceToHost, st));
+  RYK_CUDA(cudaMemcpyAsync(R->h_chunk[r], R->d_chunk[r], sizeof(double) * R->chunk, cudaMemcpyDeviceToHost, st));
+  RYK_CUDA(cudaEventRecord(R->ev[r], st));
+  R->pushed++;
+  if (ticket) *ticket = k;
+  return 0;
+}
+
+// Wait for push `ticket` (one of the last 8): *status 0 = no chunk this step, 1 = chunk written to chunk_out, 2 = chunk was
+// silent (the reference forwards None); *power_db = mean STFT power of the chunk (0 when status is 0).
+int ryk_reblock_collect(ryk_engine* h, int id, long long ticket, double* chunk_out, int* status, double* power_db) {
+  Engine* e = &h->impl;
+  Reblock* R = get_reblock(e, id);
+  RYK_CHECK(R != nullptr, "no such re-blocker");
+  RYK_CHECK(ticket >= 0 && ticket < R->pushed && ticket + kRing > R->pushed, "ticket is not among the last 8 pushes");
+  const int r = (int)(ticket % kRing);
+  RYK_CUDA(cudaEventSynchronize(R->ev[r]));
+  const int stt = *R->h_status[r];
+  if (status) *status = stt;
+  if (power_db) *power_db = *R->h_power[r];
+  if (chunk_out && stt != 0) memcpy(chunk_out, R->h_chunk[r], sizeof(double) * R->chunk);
+  return 0;
+}
+
+// Device pointers of ring slot ticket % 8 (valid until 8 further pushes; ordered after the push on its stream).
+int ryk_reblock_result_device(ryk_engine* h, int id, long long ticket, const double** chunk_dev, const int** status_dev, const double** power_dev) {
+  Engine* e = &h->impl;
+  Reblock* R = get_reblock(e, id);
+  RYK_CHECK(R != nullptr, "no such re-blocker");
+  RYK_CHECK(ticket >= 0 && ticket < R->pushed && ticket + kRing > R->pushed, "ticket is not among the last 8 pushes");
+  const int r = (int)(ticket % kRing);
+  if (chunk_dev) *chunk_dev = R->d_chunk[r];
+  if (status_dev) *status_dev = R->d_status[r];
+  if (power_dev) *power_dev = R->d_power[r];
+  return 0;
+}
+
+// Host buffers: H2D + push + collect.
+int ryk_reblock_push(ryk_engine* h, int id, const double* wave, int n, double* chunk_out, int* status, double* power_db) {
+  Engine* e = &h->impl;
+  RYK_CUDA(cudaSetDevice(e->device));
+  Reblock* R = get_reblock(e, id);
+  RYK_CHECK(R != nullptr, "no such re-blocker");
+  RYK_CHECK(n >= 0 && n <= R->max_in, "more samples than the re-blocker's max_in");
+  if (n > 0) RYK_CUDA(cudaMemcpyAsync(R->d_stage_in, wave, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
+  RYK_CUDA(cudaMemcpyAsync(R->d_stage_n, &n, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  RYK_CUDA(cudaStreamSynchronize(e->stream));           // n lives on the caller's stack
+  long long ticket = 0;
+  if (ryk_reblock_push_device(h, id, -1, R->d_stage_in, R->d_stage_n, &ticket)) return -1;
+  return ryk_reblock_collect(h, id, ticket, chunk_out, status, power_db);
 }
 
 }  // extern "C"

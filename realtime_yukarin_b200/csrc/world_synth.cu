@@ -510,4 +510,356 @@ int synth_drain_async(Engine* e, Synth* s, double* d_out, int max_blocks, cudaSt
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------ offline Synthesis()
+// Vocoder.decode = pyworld.synthesize (realtime_voice_conversion/yukarin_wrapper/vocoder.py:50-62),
+// WORLD synthesis.cpp Synthesis(): whole-utterance time base (with the extrapolated coarse point and the lowest-f0 clamp),
+// fractional pulse time shift, Hanning dc-remover over the whole fft_size, plain overlap-add.  Shares the per-pulse
+// machinery (shared-memory FP64 FFT chains, position-addressed xorshift128 noise) with the realtime synthesizer above.
+struct OfflineDev {
+  int fs, fft_size, n_frames, y_length;
+  double frame_period;                                   // seconds
+  const double* f0; const float* sp; const float* ap;    // [n_frames], [n_frames][nb]
+  double *if0, *ivuv, *tp, *totals;                      // [y_length] x 3, [ceil(y_length / 256)]
+  long long* p_index; double* p_shift; int* p_vuv; int* n_pulses;
+  const uint32_t* noise; int cap_noise;
+  const double* dc_remover;                              // [fft_size]
+  double* resp;                                          // [batch][fft_size]
+  double* y;
+};
+
+__global__ void __launch_bounds__(1024) k_off_timebase(OfflineDev S) {
+  __shared__ int wsum[32];
+  __shared__ int sh_total;
+  const int nf = S.n_frames, ny = S.y_length;
+  const double fp = S.frame_period, fs = (double)S.fs;
+  const double lowest_f0 = fs / S.fft_size + 1.0;
+  const int nc = nf + 1;
+  auto cfr = [&](int j) { double v = S.f0[j]; return v < lowest_f0 ? 0.0 : v; };
+  auto cf = [&](int j) { return j < nf ? cfr(j) : (nf >= 2 ? __dsub_rn(__dmul_rn(cfr(nf - 1), 2.0), cfr(nf - 2)) : cfr(0)); };
+  auto cvr = [&](int j) { return cfr(j) == 0.0 ? 0.0 : 1.0; };
+  auto cv = [&](int j) { return j < nf ? cvr(j) : (nf >= 2 ? cvr(nf - 1) * 2.0 - cvr(nf - 2) : cvr(0)); };
+  auto ct = [&](int j) { return __dmul_rn((double)j, fp); };
+  for (int i = threadIdx.x; i < ny; i += blockDim.x) {
+    const double t = (double)i / fs;
+    int lo = 0, hi = nc;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (ct(mid) <= t) lo = mid + 1; else hi = mid; }
+    const int k = lo < 1 ? 1 : (lo > nc - 1 ? nc - 1 : lo);
+    const double x0 = ct(k - 1), x1 = ct(k);
+    const double sx = __ddiv_rn(__dsub_rn(t, x0), __dsub_rn(x1, x0));
+    const double fa = cf(k - 1), fb = cf(k), va = cv(k - 1), vb = cv(k);
+    const double fi = __dadd_rn(fa, __dmul_rn(sx, __dsub_rn(fb, fa)));       // no FMA contraction (see k_synth_add)
+    double vi = __dadd_rn(va, __dmul_rn(sx, __dsub_rn(vb, va)));
+    vi = vi > 0.5 ? 1.0 : 0.0;
+    S.if0[i] = vi == 0.0 ? kDefaultF0 : fi;
+    S.ivuv[i] = vi;
+  }
+  __syncthreads();
+  // total phase: inclusive prefix sum of 2 pi f0 / fs in the fixed blocked order (256-sample blocks, then block totals)
+  const int BLK = 256, nblk = (ny + BLK - 1) / BLK;
+  for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
+    const int b0 = b * BLK, b1 = min(b0 + BLK, ny);
+    double local = 0.0;
+    for (int i = b0; i < b1; ++i) { local = __dadd_rn(local, 2.0 * kPi * S.if0[i] / fs); S.tp[i] = local; }
+    S.totals[b] = local;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double base = 0.0;
+    for (int b = 0; b < nblk; ++b) { const double t = S.totals[b]; S.totals[b] = base; base = __dadd_rn(base, t); }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ny; i += blockDim.x) S.tp[i] = __dadd_rn(S.totals[i / BLK], S.tp[i]);
+  __syncthreads();
+  // ordered pulse compaction
+  const int per = (ny - 1 + blockDim.x - 1) / blockDim.x;
+  const int lo = threadIdx.x * per, hi = min(lo + per, ny - 1);
+  int cnt = 0;
+  for (int i = lo; i < hi; ++i) {
+    const double a = fmod(S.tp[i], 2.0 * kPi), b = fmod(S.tp[i + 1], 2.0 * kPi);
+    cnt += fabs(b - a) > kPi ? 1 : 0;
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = cnt;
+  for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int v = wsum[lane], iv = v;
+    for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += u; }
+    wsum[lane] = iv - v;
+    if (lane == 31) sh_total = iv;
+  }
+  __syncthreads();
+  int pos = wsum[w] + inc - cnt;
+  for (int i = lo; i < hi; ++i) {
+    const double a = fmod(S.tp[i], 2.0 * kPi), b = fmod(S.tp[i + 1], 2.0 * kPi);
+    if (fabs(b - a) > kPi) {
+      const double y1 = a - 2.0 * kPi, y2 = b;
+      const double x = -y1 / (y2 - y1);
+      S.p_index[pos] = i; S.p_shift[pos] = x / fs; S.p_vuv[pos] = S.ivuv[i] > 0.5 ? 1 : 0;
+      ++pos;
+    }
+  }
+  if (threadIdx.x == 0) *S.n_pulses = sh_total;
+}
+
+// one CTA per pulse of the batch [first, first + count)
+__global__ void __launch_bounds__(256) k_off_pulse(OfflineDev S, int first, int count, const double2* __restrict__ tw) {
+  extern __shared__ double2 sm2[];
+  if ((int)blockIdx.x >= count) return;
+  const int n = S.fft_size, nb = n / 2 + 1, lg = ilog2(n);
+  double2* A = sm2;
+  double2* Nz = sm2 + n;
+  double* spec = (double*)(sm2 + 2 * n);
+  double* apr = spec + nb + 1;
+  double* periodic = apr + nb + 1;
+  double* scratch = periodic + n;
+  const int np_ = *S.n_pulses;
+  const int p = first + blockIdx.x;
+  const long long idx = S.p_index[p];
+  const long long nxt = S.p_index[p + 1 < np_ ? p + 1 : np_ - 1];
+  int noise_size = (int)(nxt - idx);
+  if (noise_size > n) noise_size = n;
+  const int vuv = S.p_vuv[p];
+  const double t = (double)idx / (double)S.fs;
+  int fl = (int)floor(t / S.frame_period), ce = (int)ceil(t / S.frame_period);
+  if (fl > S.n_frames - 1) fl = S.n_frames - 1;
+  if (ce > S.n_frames - 1) ce = S.n_frames - 1;
+  const double interp = t / S.frame_period - fl;
+  const float* sp0 = S.sp + (size_t)fl * nb; const float* sp1 = S.sp + (size_t)ce * nb;
+  const float* ap0 = S.ap + (size_t)fl * nb; const float* ap1 = S.ap + (size_t)ce * nb;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+    double sv, av;
+    if (fl == ce) { sv = fabs((double)sp0[i]); av = safe_ap((double)ap0[i]); }
+    else {
+      sv = (1.0 - interp) * fabs((double)sp0[i]) + interp * fabs((double)sp1[i]);
+      av = (1.0 - interp) * safe_ap((double)ap0[i]) + interp * safe_ap((double)ap1[i]);
+    }
+    spec[i] = sv; apr[i] = av * av;
+  }
+  __syncthreads();
+  const bool has_periodic = !(vuv == 0 || apr[0] > 0.999);
+  if (!has_periodic) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) periodic[i] = 0.0;
+  } else {
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) A[i] = make_double2(log(spec[i] * (1.0 - apr[i]) + kSafeMin) / 2.0, 0.0);
+    min_phase_smem(A, n, lg, tw);
+    const double coef = 2.0 * kPi * S.p_shift[p] * S.fs / n;          // linear-phase fractional delay
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+      const double2 v = A[i];
+      const double re2 = cos(coef * i), im2 = sqrt(1.0 - re2 * re2);
+      A[i] = make_double2(v.x * re2 + v.y * im2, v.y * re2 - v.x * im2);
+    }
+    irfft_smem(A, n, lg, tw);
+    double part = 0.0;
+    for (int i = n / 2 + threadIdx.x; i < n; i += blockDim.x) part += A[i - n / 2].x;      // fftshift: periodic[i] = tmp[i - n/2]
+    const double dc = block_sum(part, scratch);
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+      periodic[i] = i < n / 2 ? -dc * S.dc_remover[i] : A[i - n / 2].x - dc * S.dc_remover[i];
+  }
+  __syncthreads();
+  double part = 0.0;
+  for (int i = threadIdx.x; i < noise_size; i += blockDim.x)
+    part += (double)S.noise[(idx + i) % S.cap_noise] / 268435456.0 - 6.0;
+  const double avg = noise_size > 0 ? block_sum(part, scratch) / noise_size : block_sum(part, scratch);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double v = 0.0;
+    if (i < noise_size) v = ((double)S.noise[(idx + i) % S.cap_noise] / 268435456.0 - 6.0) - avg;
+    Nz[i] = make_double2(v, 0.0);
+  }
+  fft_smem(Nz, n, lg, -1, tw);
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+    const double v = vuv != 0 ? log(spec[i] * apr[i]) / 2.0 : log(spec[i]) / 2.0;
+    A[i] = make_double2(v, 0.0);
+  }
+  min_phase_smem(A, n, lg, tw);
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+    const double2 m = A[i], z = Nz[i];
+    A[i] = make_double2(m.x * z.x - m.y * z.y, m.x * z.y + m.y * z.x);
+  }
+  irfft_smem(A, n, lg, tw);
+  const double sq = sqrt((double)noise_size);
+  double* resp = S.resp + (size_t)blockIdx.x * n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double aper = i < n / 2 ? A[i + n / 2].x : A[i - n / 2].x;
+    resp[i] = (periodic[i] * sq + aper) / n;
+  }
+}
+
+// gather overlap-add of one pulse batch, in pulse order (deterministic): y[a] += sum of the batch's responses covering a
+__global__ void __launch_bounds__(256) k_off_ola(OfflineDev S, int first, int count) {
+  const int n = S.fft_size;
+  for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < S.y_length; a += gridDim.x * blockDim.x) {
+    // pulses of the batch with idx in [a - n/2, a + n/2 - 1]
+    int lo = 0, hi = count;
+    const long long want = (long long)a - n / 2;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (S.p_index[first + mid] < want) lo = mid + 1; else hi = mid; }
+    double v = S.y[a];
+    for (int q = lo; q < count; ++q) {
+      const long long idx = S.p_index[first + q];
+      if (idx > (long long)a + n / 2 - 1) break;
+      v += S.resp[(size_t)q * n + (a - (idx - n / 2 + 1))];
+    }
+    S.y[a] = v;
+  }
+}
+
+// Host buffers in, host buffer out (the per-op level of the C ABI).  Returns the number of pulses, < 0 on error.
+int world_synthesize_run(Engine* e, const double* f0, int n_frames, const float* sp, const float* ap, int fs, double frame_period_ms,
+                         int fft_size, double* y, int y_length, long long* pulse_index, double* pulse_shift, int* pulse_vuv, int max_pulses) {
+  if (synth_module_init(e)) return -1;
+  RYK_CHECK(fft_size >= 64 && fft_size <= kTwiddleN && (fft_size & (fft_size - 1)) == 0, "unsupported synthesis fft size");
+  RYK_CHECK(n_frames >= 1 && y_length >= 0 && y_length < (1 << 28), "bad synthesis length");
+  if (y_length == 0) return 0;
+  cudaStream_t st = e->stream;
+  const int n = fft_size, nb = n / 2 + 1;
+  if (y_length < 2) { y[0] = 0.0; return 0; }
+  std::vector<void*> allocs;
+  auto A = [&](void** p, size_t bytes) -> int { RYK_CUDA(cudaMalloc(p, bytes)); allocs.push_back(*p); return 0; };
+  auto cleanup = [&]() { for (void* p : allocs) cudaFree(p); };
+  OfflineDev S;
+  memset(&S, 0, sizeof(S));
+  S.fs = fs; S.fft_size = n; S.n_frames = n_frames; S.y_length = y_length; S.frame_period = frame_period_ms / 1000.0;
+  const int tiles = (y_length + n + kNoiseTile - 1) / kNoiseTile;
+  RYK_CHECK(tiles < 65536, "utterance too long for the noise jump table");
+  const int nblk = (y_length + 255) / 256;
+  double* d_f0 = nullptr; float *d_sp = nullptr, *d_ap = nullptr; uint32_t* d_noise = nullptr; double* d_dc = nullptr; SynthState* d_state = nullptr;
+  int rc = 0;
+  const int kBatch = 4096;
+  rc |= A((void**)&d_f0, sizeof(double) * n_frames);
+  rc |= A((void**)&d_sp, sizeof(float) * (size_t)n_frames * nb);
+  rc |= A((void**)&d_ap, sizeof(float) * (size_t)n_frames * nb);
+  rc |= A((void**)&S.if0, sizeof(double) * y_length);
+  rc |= A((void**)&S.ivuv, sizeof(double) * y_length);
+  rc |= A((void**)&S.tp, sizeof(double) * y_length);
+  rc |= A((void**)&S.totals, sizeof(double) * nblk);
+  rc |= A((void**)&S.p_index, sizeof(long long) * y_length);
+  rc |= A((void**)&S.p_shift, sizeof(double) * y_length);
+  rc |= A((void**)&S.p_vuv, sizeof(int) * y_length);
+  rc |= A((void**)&S.n_pulses, sizeof(int));
+  rc |= A((void**)&d_noise, sizeof(uint32_t) * (size_t)tiles * kNoiseTile);
+  rc |= A((void**)&d_dc, sizeof(double) * n);
+  rc |= A((void**)&d_state, sizeof(SynthState));
+  rc |= A((void**)&S.resp, sizeof(double) * (size_t)kBatch * n);
+  rc |= A((void**)&S.y, sizeof(double) * y_length);
+  if (rc) { cleanup(); return -1; }
+  S.f0 = d_f0; S.sp = d_sp; S.ap = d_ap; S.noise = d_noise; S.cap_noise = tiles * kNoiseTile; S.dc_remover = d_dc;
+  std::vector<double> dc(n);
+  { double sum = 0.0;
+    for (int i = 0; i < n / 2; ++i) { dc[i] = 0.5 - 0.5 * cos(2.0 * kPi * (i + 1.0) / (1.0 + n)); dc[n - i - 1] = dc[i]; sum += dc[i] * 2.0; }
+    for (int i = 0; i < n / 2; ++i) { dc[i] /= sum; dc[n - i - 1] = dc[i]; } }
+  SynthState init;
+  memset(&init, 0, sizeof(init));
+  init.rng_state[0][0] = 123456789u; init.rng_state[0][1] = 362436069u; init.rng_state[0][2] = 521288629u; init.rng_state[0][3] = 88675123u;
+  auto fail = [&](const char* what) { set_error(what); cleanup(); return -1; };
+#define OFF_CUDA(x) do { cudaError_t err_ = (x); if (err_ != cudaSuccess) return fail(cudaGetErrorString(err_)); } while (0)
+  OFF_CUDA(cudaMemcpyAsync(d_f0, f0, sizeof(double) * n_frames, cudaMemcpyHostToDevice, st));
+  OFF_CUDA(cudaMemcpyAsync(d_sp, sp, sizeof(float) * (size_t)n_frames * nb, cudaMemcpyHostToDevice, st));
+  OFF_CUDA(cudaMemcpyAsync(d_ap, ap, sizeof(float) * (size_t)n_frames * nb, cudaMemcpyHostToDevice, st));
+  OFF_CUDA(cudaMemcpyAsync(d_dc, dc.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  OFF_CUDA(cudaMemcpyAsync(d_state, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+  OFF_CUDA(cudaMemsetAsync(S.y, 0, sizeof(double) * y_length, st));
+  {
+    SynthDev N;
+    memset(&N, 0, sizeof(N));
+    N.state = d_state; N.noise = d_noise; N.cap_noise = S.cap_noise;
+    k_synth_noise<<<tiles, 256, 0, st>>>(N, e->d_jump, e->d_jump + 8 * 512, 0, 0);
+  }
+  k_off_timebase<<<1, 1024, 0, st>>>(S);
+  e->launches += 2;
+  int np_ = 0;
+  OFF_CUDA(cudaMemcpyAsync(&np_, S.n_pulses, sizeof(int), cudaMemcpyDeviceToHost, st));
+  OFF_CUDA(cudaStreamSynchronize(st));
+  for (int first = 0; first < np_; first += kBatch) {
+    const int count = np_ - first < kBatch ? np_ - first : kBatch;
+    k_off_pulse<<<count, 256, pulse_smem_bytes(n), st>>>(S, first, count, e->d_twiddle);
+    k_off_ola<<<(y_length + 255) / 256, 256, 0, st>>>(S, first, count);
+    e->launches += 2;
+  }
+  OFF_CUDA(cudaGetLastError());
+  OFF_CUDA(cudaMemcpyAsync(y, S.y, sizeof(double) * y_length, cudaMemcpyDeviceToHost, st));
+  const int nq = np_ < max_pulses ? np_ : max_pulses;
+  if (pulse_index && nq > 0) OFF_CUDA(cudaMemcpyAsync(pulse_index, S.p_index, sizeof(long long) * nq, cudaMemcpyDeviceToHost, st));
+  if (pulse_shift && nq > 0) OFF_CUDA(cudaMemcpyAsync(pulse_shift, S.p_shift, sizeof(double) * nq, cudaMemcpyDeviceToHost, st));
+  if (pulse_vuv && nq > 0) OFF_CUDA(cudaMemcpyAsync(pulse_vuv, S.p_vuv, sizeof(int) * nq, cudaMemcpyDeviceToHost, st));
+  OFF_CUDA(cudaStreamSynchronize(st));
+#undef OFF_CUDA
+  cleanup();
+  return np_;
+}
+
+// ------------------------------------------------------------------------------------ output silence gate
+// realtime_voice_conversion/worker/decode_worker.py:53-59 --
+//   power = librosa.core.power_to_db(numpy.abs(librosa.stft(wave)) ** 2).mean();  the chunk is dropped if power < -threshold.
+// k_ogate_stft : one CTA per STFT frame (n_fft 2048, hop 512, periodic Hann, reflect-centred): FP64 smem FFT -> dB per bin
+// k_ogate_mean : top_db clip against the global maximum and the mean; writes {power, pass} -- all on the device, no host sync.
+__global__ void __launch_bounds__(256) k_ogate_stft(const double* __restrict__ wave, const int* __restrict__ n_valid, int n, int n_fft, int hop,
+                                                   double amin, double* __restrict__ db, double* __restrict__ fmx, const double2* __restrict__ tw) {
+  extern __shared__ double2 sm2[];
+  __shared__ double red[32];
+  if (n_valid && *n_valid < n) return;                 // no chunk was emitted this step
+  const int f = blockIdx.x, nb = n_fft / 2 + 1, pad = n_fft / 2, lg = ilog2(n_fft);
+  for (int j = threadIdx.x; j < n_fft; j += blockDim.x) {
+    int idx = f * hop + j - pad;
+    if (idx < 0) idx = -idx;
+    if (idx >= n) idx = 2 * (n - 1) - idx;
+    if (idx < 0) idx = 0;
+    if (idx >= n) idx = n - 1;
+    const double w = 0.5 - 0.5 * cos(2.0 * kPi * j / n_fft);
+    sm2[j] = make_double2(wave[idx] * w, 0.0);
+  }
+  fft_smem(sm2, n_fft, lg, -1, tw);
+  double mx = -1e300;
+  for (int k = threadIdx.x; k < nb; k += blockDim.x) {
+    const double2 v = sm2[k];
+    const double pw = v.x * v.x + v.y * v.y;
+    const double d = 10.0 * log10(pw > amin ? pw : amin);
+    db[(size_t)f * nb + k] = d;
+    mx = fmax(mx, d);
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) { for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmax(mx, red[w]); fmx[f] = mx; }
+}
+
+__global__ void __launch_bounds__(1024) k_ogate_mean(const double* __restrict__ db, const double* __restrict__ fmx, const int* __restrict__ n_valid, int n,
+                                                    int frames, int nb, double top_db, double threshold_db, double* __restrict__ power, int* __restrict__ status) {
+  __shared__ double scratch[32];
+  if (n_valid && *n_valid < n) { if (threadIdx.x == 0) { *power = 0.0; *status = 0; } return; }
+  double mx = -1e300;
+  for (int f = 0; f < frames; ++f) mx = fmax(mx, fmx[f]);
+  const double floor_db = mx - top_db;
+  double part = 0.0;
+  const size_t total = (size_t)frames * nb;
+  for (size_t i = threadIdx.x; i < total; i += blockDim.x) { const double d = db[i]; part += d > floor_db ? d : floor_db; }
+  const double sum = block_sum(part, scratch);
+  if (threadIdx.x == 0) {
+    const double pw = sum / (double)total;
+    *power = pw;
+    *status = pw < -threshold_db ? 2 : 1;              // 1: chunk passes, 2: chunk is silent (the reference sends None)
+  }
+}
+
+int output_gate_frames(int n, int hop) { return 1 + n / hop; }
+size_t output_gate_scratch_doubles(int n, int n_fft, int hop) { return (size_t)output_gate_frames(n, hop) * (n_fft / 2 + 1 + 1); }
+
+// Stream-ordered, device pointers.  d_n_valid (may be null): the gate only runs when *d_n_valid >= n (else status 0).
+int output_gate_async(Engine* e, const double* d_wave, const int* d_n_valid, int n, int n_fft, int hop, double threshold_db,
+                      double* d_scratch, double* d_power, int* d_status, cudaStream_t st) {
+  RYK_CHECK(n_fft >= 64 && n_fft <= kTwiddleN && (n_fft & (n_fft - 1)) == 0, "unsupported STFT size for the output gate");
+  RYK_CHECK(n > n_fft / 2, "output chunk too short for a reflect-centred STFT");
+  static bool attr_set = false;
+  if (!attr_set) { RYK_CUDA(cudaFuncSetAttribute(k_ogate_stft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double2) * kTwiddleN))); attr_set = true; }
+  const int frames = output_gate_frames(n, hop), nb = n_fft / 2 + 1;
+  double* d_db = d_scratch;
+  double* d_fmax = d_scratch + (size_t)frames * nb;
+  k_ogate_stft<<<frames, 256, sizeof(double2) * n_fft, st>>>(d_wave, d_n_valid, n, n_fft, hop, 1e-10, d_db, d_fmax, e->d_twiddle);
+  k_ogate_mean<<<1, 1024, 0, st>>>(d_db, d_fmax, d_n_valid, n, frames, nb, 80.0, threshold_db, d_power, d_status);
+  e->launches += 2;
+  RYK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace ryk

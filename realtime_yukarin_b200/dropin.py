@@ -1,6 +1,6 @@
 """Import aliases that make this package answer to the names the reference's drivers import:
 
-    realtime_voice_conversion.{config, stream[.base_stream|...], segment.*, yukarin_wrapper.*, converter.*}
+    realtime_voice_conversion.{config, stream[.base_stream|...], segment.*, yukarin_wrapper.*, converter.*, worker.utility}
     yukarin[.acoustic_feature|.wave|.param|.config|.f0_converter],  become_yukarin[.param|.config.sr_config]
 
 Nothing is copied: each alias module is a thin namespace whose attributes are this package's objects
@@ -22,7 +22,7 @@ def _module(name: str, **attrs) -> types.ModuleType:
 
 
 def install() -> None:
-    from . import config, converter, feature, models, params, segment, stream, vocoder, voice_changer
+    from . import config, converter, feature, models, params, segment, stream, vocoder, voice_changer, worker
 
     rvc = 'realtime_voice_conversion'
     _module(rvc)
@@ -46,6 +46,8 @@ def install() -> None:
             AcousticFeatureWrapper=feature.AcousticFeatureWrapper)
     _module(f'{rvc}.yukarin_wrapper.acoustic_feature_wrapper', AcousticFeatureWrapper=feature.AcousticFeatureWrapper,
             CrepeAcousticFeatureWrapper=vocoder.CrepeAcousticFeatureWrapper)
+    _module(f'{rvc}.worker')
+    _module(f'{rvc}.worker.utility', Item=worker.Item)
     _module(f'{rvc}.converter')
     _module(f'{rvc}.converter.yukarin_converter', YukarinConverter=converter.YukarinConverter)
 

@@ -48,6 +48,8 @@ EXPORTED_SYMBOLS = [
     'ryk_synth_synthesis2', 'ryk_synth_decode', 'ryk_session_create', 'ryk_session_destroy', 'ryk_session_push',
     'ryk_session_push_device', 'ryk_session_submit', 'ryk_session_collect', 'ryk_group_create', 'ryk_group_destroy',
     'ryk_group_size', 'ryk_session_stage_times', 'ryk_group_submit', 'ryk_group_collect', 'ryk_group_push_device', 'ryk_test_conv_layer', 'ryk_debug_dio', 'ryk_debug_synth_pulses', 'ryk_debug_synth_timebase', 'ryk_engine_profile', 'ryk_engine_profile_read', 'ryk_engine_timer_start', 'ryk_engine_timer_stop',
+    'ryk_world_synthesize_length', 'ryk_world_synthesize', 'ryk_output_gate', 'ryk_reblock_create', 'ryk_reblock_destroy',
+    'ryk_reblock_push', 'ryk_reblock_push_device', 'ryk_reblock_collect', 'ryk_reblock_result_device',
 ]
 
 
@@ -278,6 +280,67 @@ class Engine(object):
         nblk = ctypes.c_int()
         self._check(self.lib.ryk_synth_decode(self._h, sid, _dp(f0), len(f0), _fp(sp), _fp(ap), _dp(out), int(max_blocks), ctypes.byref(nblk)))
         return out[:nblk.value * B].copy()
+
+    # ---- offline synthesis (pyworld.synthesize) and the output silence gate / re-blocker ----
+    def world_synthesize(self, f0, sp, ap, fs, frame_period, fft_size=None, return_pulses=False):
+        """Vocoder.decode's pyworld.synthesize (vocoder.py:50-62): (T,) f0, (T, nb) sp / ap -> float64 wave."""
+        f0 = numpy.ascontiguousarray(numpy.asarray(f0).ravel(), dtype=numpy.float64)
+        sp, ap = _f32(sp), _f32(ap)
+        if fft_size is None:
+            fft_size = (sp.shape[1] - 1) * 2
+        n = self.lib.ryk_world_synthesize_length(len(f0), ctypes.c_double(frame_period), int(fs))
+        y = numpy.zeros(max(n, 1), dtype=numpy.float64)
+        cap = max(n, 1) if return_pulses else 1
+        idx = numpy.zeros(cap, numpy.int64); shift = numpy.zeros(cap); vuv = numpy.zeros(cap, numpy.int32)
+        ny, npulse = ctypes.c_int(), ctypes.c_int()
+        self._check(self.lib.ryk_world_synthesize(
+            self._h, _dp(f0), len(f0), _fp(sp), _fp(ap), int(fs), ctypes.c_double(frame_period), int(fft_size), _dp(y), len(y), ctypes.byref(ny),
+            idx.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)), _dp(shift), vuv.ctypes.data_as(c_int_p), cap if return_pulses else 0,
+            ctypes.byref(npulse)))
+        y = y[:ny.value]
+        if return_pulses:
+            k = min(npulse.value, cap)
+            return y, idx[:k], shift[:k], vuv[:k]
+        return y
+
+    def output_gate(self, wave, threshold_db, n_fft=2048, hop=512):
+        """(mean STFT power in dB, keep?) of one output chunk (decode_worker.py:56-58)."""
+        w = numpy.ascontiguousarray(numpy.asarray(wave).ravel(), dtype=numpy.float64)
+        pw, ok = ctypes.c_double(), ctypes.c_int()
+        self._check(self.lib.ryk_output_gate(self._h, _dp(w), len(w), int(n_fft), int(hop), ctypes.c_double(threshold_db), ctypes.byref(pw),
+                                             ctypes.byref(ok)))
+        return pw.value, bool(ok.value)
+
+    def reblock_create(self, out_audio_chunk, max_in, threshold_db, n_fft=2048, hop=512) -> int:
+        rid = ctypes.c_int()
+        self._check(self.lib.ryk_reblock_create(self._h, int(out_audio_chunk), int(max_in), int(n_fft), int(hop), ctypes.c_double(threshold_db),
+                                                ctypes.byref(rid)))
+        self._reblock_chunk = getattr(self, '_reblock_chunk', {})
+        self._reblock_chunk[rid.value] = int(out_audio_chunk)
+        return rid.value
+
+    def reblock_destroy(self, rid: int):
+        self._check(self.lib.ryk_reblock_destroy(self._h, rid))
+
+    def reblock_push(self, rid: int, wave):
+        """Host samples in; returns (status, chunk or None, power_db): status 0 none, 1 chunk, 2 silent chunk (dropped)."""
+        w = numpy.ascontiguousarray(numpy.asarray(wave).ravel(), dtype=numpy.float64)
+        out = numpy.empty(self._reblock_chunk[rid], dtype=numpy.float64)
+        st, pw = ctypes.c_int(), ctypes.c_double()
+        self._check(self.lib.ryk_reblock_push(self._h, rid, _dp(w), len(w), _dp(out), ctypes.byref(st), ctypes.byref(pw)))
+        return st.value, (out if st.value == 1 else None), pw.value
+
+    def reblock_push_device(self, rid: int, session_id: int = -1, wave_dev_ptr: int = 0, n_dev_ptr: int = 0) -> int:
+        ticket = ctypes.c_longlong()
+        self._check(self.lib.ryk_reblock_push_device(self._h, rid, int(session_id), ctypes.c_void_p(wave_dev_ptr or None),
+                                                     ctypes.c_void_p(n_dev_ptr or None), ctypes.byref(ticket)))
+        return ticket.value
+
+    def reblock_collect(self, rid: int, ticket: int):
+        out = numpy.empty(self._reblock_chunk[rid], dtype=numpy.float64)
+        st, pw = ctypes.c_int(), ctypes.c_double()
+        self._check(self.lib.ryk_reblock_collect(self._h, rid, ctypes.c_longlong(ticket), _dp(out), ctypes.byref(st), ctypes.byref(pw)))
+        return st.value, (out if st.value == 1 else None), pw.value
 
     # ---- diagnostics ----
     def debug_synth_pulses(self, sid, first=0, count=None):

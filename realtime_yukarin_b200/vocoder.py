@@ -32,15 +32,11 @@ class Vocoder(object):
                            fft_length=p.fft_length, order=p.order, alpha=p.alpha, dtype=p.dtype)
 
     def decode(self, acoustic_feature: AcousticFeature) -> Wave:
-        """Whole-utterance synthesis (vocoder.py:50-62): a fresh device synthesizer fed once and flushed."""
-        engine = default_engine()
-        fft_size = cheaptrick_fft_size(self.out_sampling_rate)
-        sid = engine.synth_create(self.out_sampling_rate, self.acoustic_param.frame_period, fft_size, 1024)
-        try:
-            f = acoustic_feature
-            out = engine.synth_decode(sid, numpy.asarray(f.f0, numpy.float64).ravel(), f.sp, f.ap)
-        finally:
-            engine.synth_destroy(sid)
+        """Whole-utterance synthesis = pyworld.synthesize (vocoder.py:50-62): WORLD's offline Synthesis() on the device
+        (ryk_world_synthesize); int(T * frame_period * fs / 1000) samples."""
+        f = acoustic_feature
+        out = default_engine().world_synthesize(numpy.asarray(f.f0, numpy.float64).ravel(), f.sp, f.ap, self.out_sampling_rate,
+                                                self.acoustic_param.frame_period)
         return Wave(out, sampling_rate=self.out_sampling_rate)
 
 

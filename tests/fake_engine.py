@@ -66,3 +66,23 @@ class OracleEngine:
 
     def synth_destroy(self, sid):
         self.synths.pop(sid, None)
+
+    # ---- offline synthesis, output gate and re-blocker ----
+    def world_synthesize(self, f0, sp, ap, fs, frame_period, fft_size=None, return_pulses=False):
+        return W.synthesize(f0, sp, ap, fs, frame_period, fft_size, return_pulses)
+
+    def output_gate(self, wave, threshold_db, n_fft=2048, hop=512):
+        pw = W.stft_power_db_mean(wave, n_fft, hop)
+        return pw, not (pw < -threshold_db)
+
+    def reblock_create(self, out_audio_chunk, max_in, threshold_db, n_fft=2048, hop=512):
+        self.reblocks = getattr(self, 'reblocks', {})
+        self.reblocks[len(self.reblocks)] = opipe.OutputReblockOracle(out_audio_chunk, threshold_db)
+        return len(self.reblocks) - 1
+
+    def reblock_push(self, rid, wave):
+        st, chunk = self.reblocks[rid].push(wave)
+        return st, chunk, self.reblocks[rid].last_power or 0.0
+
+    def reblock_destroy(self, rid):
+        self.reblocks.pop(rid, None)

@@ -1,0 +1,136 @@
+"""SURVEY 8(f) ranks 1-3 on the CPU: the oracle's offline Synthesis() and output-gate restatements against independent
+numpy / scipy computations and analytic properties, and the host-side worker logic (Item / OutputReblocker / the
+run.py audio-loop body) with the GPU engine replaced by the oracle-backed stand-in."""
+import numpy as np
+import pytest
+import scipy.signal as ss
+
+from oracle import pipeline as opipe
+from oracle import world as W
+from realtime_yukarin_b200 import engine as eng_mod
+from realtime_yukarin_b200 import synthetic
+from tests.fake_engine import OracleEngine
+
+CFG = opipe.PathConfig()
+
+
+def _librosa_style_power_db_mean(x, n_fft=2048, hop=512):
+    xp = np.pad(x, n_fft // 2, mode='reflect')
+    win = ss.get_window('hann', n_fft, fftbins=True)
+    frames = 1 + len(x) // hop
+    S = np.stack([np.fft.rfft(xp[f * hop:f * hop + n_fft] * win) for f in range(frames)], 1)
+    db = 10 * np.log10(np.maximum(1e-10, np.abs(S) ** 2))
+    return float(np.maximum(db, db.max() - 80.0).mean())
+
+
+@pytest.mark.parametrize('n,scale', [(7200, 0.1), (2400, 1e-3), (24000, 1e-7), (7200, 0.0)])
+def test_output_gate_oracle_matches_numpy_stft(n, scale):
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n) * scale
+    assert abs(W.stft_power_db_mean(x) - _librosa_style_power_db_mean(x)) < 1e-9
+    if scale == 0.0:       # all-zero chunk: every bin clamps to amin -> -100 dB, below any sensible threshold
+        assert W.stft_power_db_mean(x) == pytest.approx(-100.0)
+
+
+def test_output_gate_scaling_property():
+    """power_to_db is 20 log10 of the amplitude: scaling the chunk by 10 raises the mean by exactly 20 dB (no clipping active)."""
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(7200) * 0.01
+    assert W.stft_power_db_mean(10 * x) - W.stft_power_db_mean(x) == pytest.approx(20.0, abs=1e-9)
+
+
+def test_offline_synthesis_length_and_pulses():
+    x = synthetic.synthetic_speech(1.0, stream=2)
+    f = opipe.extract_features(x, CFG)
+    f0 = f['f0'].ravel().astype(np.float64)
+    y, idx, shift, vuv = W.synthesize(f0, f['sp'], f['ap'], 24000, 5.0, return_pulses=True)
+    assert len(y) == int(len(f0) * 5.0 * 24000 / 1000)                 # pyworld.synthesize's y_length
+    assert np.all(np.diff(idx) > 0) and idx[0] >= 0 and idx[-1] < len(y) - 1
+    assert np.all((shift >= 0) & (shift <= 1.0 / 24000 + 1e-18))         # fractional shift lies inside one sample
+    # voiced pulses follow the f0 contour: interval between consecutive voiced pulses ~ fs / f0 at that frame
+    iv = np.diff(idx)
+    fr = np.minimum(len(f0) - 1, (idx[:-1] / 120.0).astype(int))
+    both_voiced = (vuv[:-1] == 1) & (vuv[1:] == 1) & (f0[fr] > 0) & (f0[np.minimum(len(f0) - 1, fr + 1)] > 0)
+    rel = np.abs(iv[both_voiced] - 24000.0 / f0[fr[both_voiced]]) / (24000.0 / f0[fr[both_voiced]])
+    assert np.median(rel) < 0.05
+    # unvoiced stretches pulse at the 500 Hz default: exactly every 48 samples
+    un = (vuv[:-1] == 0) & (vuv[1:] == 0)
+    assert un.any() and np.all(np.abs(iv[un] - 48) <= 1)
+    # analysis -> synthesis keeps the level and the coarse spectrum
+    n = min(len(x), len(y))
+    assert 0.7 < np.sqrt(np.mean(y[:n] ** 2)) / np.sqrt(np.mean(x[:n] ** 2)) < 1.4
+    X, Y = np.abs(np.fft.rfft(x[:n]))[:3000], np.abs(np.fft.rfft(y[:n]))[:3000]
+    assert np.corrcoef(X, Y)[0, 1] > 0.7
+
+
+def test_offline_synthesis_unvoiced_only_is_noise_shaped_by_sp():
+    """f0 = 0 everywhere: no periodic part; output power follows the spectral envelope level (linearity in sqrt(sp))."""
+    nb = 513
+    f0 = np.zeros(100)
+    ap = np.full((100, nb), 0.5, np.float32)
+    y1 = W.synthesize(f0, np.full((100, nb), 1e-4, np.float32), ap, 24000, 5.0)
+    y2 = W.synthesize(f0, np.full((100, nb), 4e-4, np.float32), ap, 24000, 5.0)
+    assert np.allclose(y2, 2.0 * y1, rtol=1e-9, atol=1e-15)            # same noise draws, amplitude = sqrt(sp)
+    assert np.isfinite(y1).all() and np.abs(y1).max() > 0
+
+
+def test_reblock_oracle_matches_reference_fragment_logic():
+    """decode_worker.py:38-59 traced by hand: blocks of 1024 -> chunks of 2400 samples, at most one per step."""
+    rb = opipe.OutputReblockOracle(2400, 80.0)
+    rng = np.random.default_rng(0)
+    stream = rng.standard_normal(20 * 1024) * 0.05
+    got, fed = [], 0
+    for blocks in (2, 3, 2, 0, 3, 2, 2, 3, 3):
+        st, chunk = rb.push(stream[fed:fed + blocks * 1024])
+        fed += blocks * 1024
+        got.append((st, chunk))
+    emitted = [c for s, c in got if s == 1]
+    assert [s for s, _ in got] == [0, 1, 1, 0, 1, 1, 1, 1, 1]      # 2048 | 5120 -> 2720 | 4768 -> 2368 | 2368 | 5440 -> ... (hand trace)
+    assert np.array_equal(np.concatenate(emitted), stream[:len(emitted) * 2400])
+    assert rb.push(np.zeros(2400))[0] in (1, 2)
+    rb2 = opipe.OutputReblockOracle(2400, 80.0)
+    assert rb2.push(np.zeros(4096))[0] == 2                                  # digital silence is gated away
+
+
+def test_worker_classes_with_oracle_engine(small_models):
+    from realtime_yukarin_b200.worker import Item, OutputReblocker
+    fake = OracleEngine(small_models['stage1_model_path'], small_models['stage2_model_path'])
+    eng_mod.set_default_engine(fake)
+    try:
+        it = Item(item=np.zeros(3), index=7)
+        assert it.index == 7 and len(it.item) == 3
+        rb = OutputReblocker(out_audio_chunk=7200, output_silent_threshold=80.0)
+        ref = opipe.OutputReblockOracle(7200, 80.0)
+        rng = np.random.default_rng(1)
+        for k in range(6):
+            w = rng.standard_normal(7 * 1024) * (0.1 if k != 3 else 1e-9)
+            a = rb.push(w)
+            st, b = ref.push(w)
+            assert (a is None) == (b is None)
+            if a is not None:
+                assert np.array_equal(a, b)
+            assert rb.last_status == st
+        rb.close()
+    finally:
+        eng_mod.set_default_engine(None)
+
+
+def test_vocoder_decode_is_offline_synthesis(small_models):
+    """Vocoder.decode (vocoder.py:50-62) goes through world_synthesize and returns pyworld.synthesize's length."""
+    from realtime_yukarin_b200.config import VocodeMode
+    from realtime_yukarin_b200.feature import AcousticFeature
+    from realtime_yukarin_b200.params import create_from_json
+    from realtime_yukarin_b200.vocoder import Vocoder
+    fake = OracleEngine(small_models['stage1_model_path'], small_models['stage2_model_path'])
+    eng_mod.set_default_engine(fake)
+    try:
+        acp = create_from_json(small_models['stage1_config_path']).dataset.acoustic_param
+        voc = Vocoder(acoustic_param=acp, out_sampling_rate=24000, extract_f0_mode=VocodeMode.WORLD)
+        x = synthetic.synthetic_speech(0.5, stream=9)
+        f = opipe.extract_features(x, CFG)
+        feat = AcousticFeature(f0=f['f0'], sp=f['sp'], ap=f['ap'], mc=f['mc'], voiced=f['voiced'])
+        w = voc.decode(feat)
+        assert w.sampling_rate == 24000 and len(w.wave) == int(len(f['f0']) * 5.0 * 24)
+        assert np.array_equal(w.wave, W.synthesize(f['f0'].ravel().astype(np.float64), f['sp'], f['ap'], 24000, 5.0))
+    finally:
+        eng_mod.set_default_engine(None)
