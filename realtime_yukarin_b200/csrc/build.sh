@@ -5,7 +5,7 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -Wno-unused-variable --expt-relaxed-constexpr $RYK_NVCC_EXTRA"
 mkdir -p _obj
-SRCS="api conv_direct conv_tc unet world_analysis world_synth features convert session"
+SRCS="api conv_direct conv_tc conv_tc2 unet world_analysis world_synth features convert session"
 pids=""
 for s in $SRCS; do
   if [ ! -f _obj/$s.o ] || [ $s.cu -nt _obj/$s.o ] || [ -n "$(find . -maxdepth 1 \( -name '*.h' -o -name '*.cuh' \) -newer _obj/$s.o 2>/dev/null)" ] || [ ../../include/ryk.h -nt _obj/$s.o ]; then

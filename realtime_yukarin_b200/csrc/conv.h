@@ -2,6 +2,7 @@
 // FP16 tcgen05 tensor-core path (conv_tc.cu) and the U-Net scheduler (unet.cu).
 #pragma once
 #include <cuda.h>
+#include <cudaTypedefs.h>
 
 #include "common.cuh"
 
@@ -34,6 +35,9 @@ struct ConvLayer {
   int tile_w = 0, tile_h = 0;             // pixel tile = tile_w x tile_h = 128
   int block_n = 0;
   bool tc_ready = false;
+  // CTA-pair kernel (conv_tc2.cu): accumulator groups per pair (1 / 2 / 4 parity classes), N per group, half-tile weight map
+  bool tc2 = false; int tc2_groups = 0, tc2_ng = 0;
+  CUtensorMap tmB2;
 };
 
 // Weight repacking from the Chainer layouts the model files use:
@@ -48,5 +52,11 @@ int tc_init();                                           // resolves cuTensorMap
 int tc_layer_prepare(ConvLayer& L, int num_sms);         // builds tensor maps, picks tiles / split-K (needs final pointers)
 int conv_tc_run(const ConvLayer& L, cudaStream_t st);
 size_t tc_splitk_ws_bytes(const ConvLayer& L, int num_sms);
+
+// conv_tc2.cu
+int tc2_init();
+bool tc2_layer_config(const ConvLayer& L, int num_sms, int* groups, int* ng);     // needs L.tile_w / tile_h
+int tc2_layer_prepare(ConvLayer& L, PFN_cuTensorMapEncodeTiled_v12000 encode);
+int conv_tc2_run(const ConvLayer& L, cudaStream_t st, bool pdl);
 
 }  // namespace ryk

@@ -27,71 +27,9 @@
 #include <vector>
 #include <stdio.h>
 #include "conv.h"
+#include "tc_ptx.cuh"
 
 namespace ryk {
-
-constexpr int kBlockM = 128;
-constexpr int kBlockK = 64;          // fp16 elements = 128 bytes = one swizzle row
-constexpr int kUmmaK = 16;
-constexpr int kTcThreads = 192;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// Programmatic dependent launch: every kernel of a U-Net forward is a dependent of the one before it in the stream.
-// pdl_trigger() lets the NEXT kernel's CTAs be scheduled as soon as all CTAs of this grid have started (they run their
-// prologue -- barrier init, TMEM allocation, tensor-map prefetch, scale/shift staging -- in the shadow of this grid's
-// tail); pdl_wait() blocks until the PREVIOUS grid has completed and its memory is visible, and must precede every
-// access to activations / workspaces.  Both are no-ops for launches without the programmatic attribute.
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t"
-      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// K-major, 128B-swizzled operand: 8-row atoms of 1024 B (SBO), LBO unused, descriptor version 1 (sm_100)
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((1024u >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
 
 struct TcParams {
   int transposed, B, Hout, Wout, Cout;
@@ -669,6 +607,7 @@ int tc_init() {
     RYK_CHECK(qres == cudaDriverEntryPointSuccess && fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
     g_encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
   }
+  if (tc2_init()) return -1;
   RYK_CUDA(cudaFuncSetAttribute(k_conv_tc<64, 6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<64, 6>()));
   RYK_CUDA(cudaFuncSetAttribute(k_conv_tc<128, 6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<128, 6>()));
   RYK_CUDA(cudaFuncSetAttribute(k_conv_tc<256, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<256, 4>()));
@@ -759,6 +698,7 @@ static void tc_geometry(const ConvLayer& L, int num_sms, int* tile_w, int* tile_
     int cps = (total_chunks + ks - 1) / ks;
     ks = (total_chunks + cps - 1) / cps;                // every split owns at least one chunk
   }
+  { ConvLayer T = L; T.tile_w = tw; T.tile_h = th; int g_, n_; if (tc2_layer_config(T, num_sms, &g_, &n_)) ks = 1; }   // pair kernel: no split-K
   *tile_w = tw; *tile_h = th; *block_n = bn; *ksplit = ks;
 }
 
@@ -783,6 +723,8 @@ int tc_layer_prepare(ConvLayer& L, int num_sms) {
   if (make_weight_map(&L.tmB, L.w_tc, K, rows, L.block_n)) return -1;
   // output map for the TMA-store epilogue: deconv classes write every other pixel (element strides = conv strides)
   if (make_act_map(&L.tmO, L.out, L.Cout, L.Wout, L.Hout, L.B, L.tile_w, L.tile_h, L.transposed ? L.SW : 1, L.transposed ? L.SH : 1)) return -1;
+  L.tc2 = tc2_layer_config(L, num_sms, &L.tc2_groups, &L.tc2_ng);
+  if (L.tc2 && tc2_layer_prepare(L, g_encode)) return -1;
   RYK_CHECK(L.ksplit == 1 || L.splitk_ws != nullptr, "split-K layer without a workspace");
   if (L.ksplit > 1) {
     if (make_ws_map(&L.tmW, L.splitk_ws, L.Cout, L.Wout, L.Hout, L.B, L.ksplit, L.tile_w, L.tile_h, L.transposed ? L.SW : 1, L.transposed ? L.SH : 1)) return -1;
@@ -811,6 +753,7 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 
 int conv_tc_run(const ConvLayer& L, cudaStream_t st) {
   RYK_CHECK(L.tc_ready, "tc layer not prepared");
+  if (L.tc2) return conv_tc2_run(L, st, pdl_enabled());
   TcParams p;
   p.transposed = L.transposed; p.B = L.B; p.Hout = L.Hout; p.Wout = L.Wout; p.Cout = L.Cout;
   p.Hc = L.transposed ? L.Hin : L.Hout; p.Wc = L.transposed ? L.Win : L.Wout;

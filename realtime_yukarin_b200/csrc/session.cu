@@ -22,6 +22,7 @@
 // stream C needs it.
 #include <math.h>
 #include <stdio.h>
+#include <chrono>
 #include <stdlib.h>
 #include <string.h>
 #include <map>
@@ -75,6 +76,7 @@ struct Session {
   double* d_out_fixed[2];              // blocks written by the (captured) decode graph, by parity
   int* d_n_fixed[2];
   bool use_graphs = true;
+  bool host_prof = false; double host_wait_us = 0.0, host_total_us = 0.0; long long host_steps = 0;   // RYK_HOST_PROF=1
   std::map<int, StageGraph> graphs;
   Synth* synth = nullptr;
   DioPlan* dio[2] = {nullptr, nullptr};     // one analysis plan per chunk parity
@@ -220,6 +222,9 @@ static Session* get_session(Engine* e, int id) { return (id >= 0 && id < (int)e-
 
 static void session_free(Session* s) {
   if (!s) return;
+  if (s->host_prof && s->host_steps > 0)
+    fprintf(stderr, "[ryk host prof] %lld steps: %.1f us per step on the host, of which %.1f us waiting for the gate count\n", s->host_steps,
+            s->host_total_us / s->host_steps, s->host_wait_us / s->host_steps);
   for (cudaStream_t st : {s->sE, s->sA[0], s->sA[1], s->sC, s->sC2, s->sD}) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
   for (int i = 0; i < kRing; ++i)
     for (cudaEvent_t ev : {s->ev_gate[i], s->ev_pro[i], s->ev_count[i], s->ev_enc[i], s->ev_cslide[i], s->ev_s1[i], s->ev_conv[i], s->ev_dslide[i], s->ev_dec[i]}) if (ev) cudaEventDestroy(ev);
@@ -412,7 +417,11 @@ static int session_front(Engine* e, Session* s, const float* d_chunk_user) {
     RYK_CUDA(cudaStreamWaitEvent(s->sC, s->ev_dslide[(k - 2) % kRing], 0));   // cv_{f0,ap,voiced}_out[b] consumed by decode k-2
     RYK_CUDA(cudaStreamWaitEvent(s->sC, s->ev_conv[(k - 2) % kRing], 0));     // cv_sp_mid[b] consumed by stage 2 of k-2
   }
-  RYK_CUDA(cudaEventSynchronize(s->ev_count[r]));                              // effective-frame count of THIS step
+  {
+    const auto t0 = std::chrono::steady_clock::now();
+    RYK_CUDA(cudaEventSynchronize(s->ev_count[r]));                            // effective-frame count of THIS step
+    if (s->host_prof) s->host_wait_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+  }
   const int t_eff = s->h_count[r][0], tp1 = s->h_count[r][1];
   RYK_CHECK(tp1 / 128 < 16, "window too long for the stage-1 graph table");
   TSTAMP(2, 0, s->sC);
@@ -510,6 +519,9 @@ static int session_back(Engine* e, Session* s) {
 }
 
 static int session_enqueue(Engine* e, Session* s, const float* d_chunk_user) {
+  const auto host_t0 = std::chrono::steady_clock::now();
+  struct HostProf { Session* s; std::chrono::steady_clock::time_point t0;
+    ~HostProf() { if (s->host_prof) { s->host_total_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); s->host_steps++; } } } host_prof_guard{s, host_t0};
   const bool was_profiling = e->profile;
   e->profile = false;                                      // the session places its own timing events (between graph launches)
   int rc = session_front(e, s, d_chunk_user);
@@ -621,6 +633,7 @@ int ryk_session_create(ryk_engine* h, const ryk_session_config* cfg, int* sessio
     for (cudaEvent_t* ev : evs) RYK_CUDA(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
   }
   { const char* v = getenv("RYK_STAGE_TIMES"); s->stage_times = v && atoi(v) != 0; }
+  { const char* v = getenv("RYK_HOST_PROF"); s->host_prof = v && atoi(v) != 0; }
   if (s->stage_times) for (int a = 0; a < 5; ++a) for (int w = 0; w < 2; ++w) for (int i = 0; i < kRing; ++i) RYK_CUDA(cudaEventCreate(&s->tev[a][w][i]));
   auto A = [&](void** p, size_t bytes) -> int { RYK_CUDA(cudaMalloc(p, bytes ? bytes : 16)); RYK_CUDA(cudaMemset(*p, 0, bytes ? bytes : 16)); s->allocs.push_back(*p); return 0; };
   auto P = [&](void** p, size_t bytes) -> int { RYK_CUDA(cudaMallocHost(p, bytes ? bytes : 16)); memset(*p, 0, bytes ? bytes : 16); s->pinned.push_back(*p); return 0; };

@@ -709,6 +709,8 @@ __global__ void __launch_bounds__(256) k_off_ola(OfflineDev S, int first, int co
 int world_synthesize_run(Engine* e, const double* f0, int n_frames, const float* sp, const float* ap, int fs, double frame_period_ms,
                          int fft_size, double* y, int y_length, long long* pulse_index, double* pulse_shift, int* pulse_vuv, int max_pulses) {
   if (synth_module_init(e)) return -1;
+  { static bool attr_set = false;
+    if (!attr_set) { RYK_CUDA(cudaFuncSetAttribute(k_off_pulse, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_set = true; } }
   RYK_CHECK(fft_size >= 64 && fft_size <= kTwiddleN && (fft_size & (fft_size - 1)) == 0, "unsupported synthesis fft size");
   RYK_CHECK(n_frames >= 1 && y_length >= 0 && y_length < (1 << 28), "bad synthesis length");
   if (y_length == 0) return 0;

@@ -115,3 +115,47 @@ def test_stage1_last_layer_kernel(engine, case):
     err = np.abs(got - ref).max()
     print('stage-1 last layer', case, 'max err', err)
     assert err < 1e-4, err
+
+
+PAIR_CASES = [
+    # CTA-pair kernel (conv_tc2.cu, cta_group::2), forced with RYK_TC2=2: transposed, B, H, W, C0, C1, Cout, act
+    (0, 1, 32, 64, 64, 0, 128, 1),       # conv, N = 128, 4 pixel tiles (2 pairs)
+    (0, 2, 16, 16, 128, 0, 256, 1),      # conv, two N tiles, batch 2, 64-pixel images (tile covers two batch rows? no: 1 tile per image)
+    (0, 1, 48, 80, 64, 64, 128, 1),      # conv, two sources, ragged tile edges (24 x 40 outputs)
+    (1, 1, 12, 16, 128, 128, 64, 2),     # deconv, 4 fused parity classes of N = 64 (d6 shape family)
+    (1, 2, 24, 32, 64, 64, 128, 2),      # deconv, 2 fused classes of N = 128 (d5 shape family), batch 2
+    (1, 1, 3, 4, 256, 0, 256, 2),        # deconv, per-class N = 128 x 2 N tiles, ONE pixel tile -> padded pair
+    (1, 1, 20, 24, 64, 0, 64, 2),        # deconv, 4 classes, ragged edges, odd tile count
+    (1, 1, 48, 64, 256, 256, 256, 2),    # deconv, d4 shape family: 16 channel chunks per tap
+]
+
+
+@pytest.mark.parametrize('case', PAIR_CASES)
+def test_pair_kernel(engine, case):
+    """k_conv_tc2: UMMA M = 256 over a CTA pair, class-fused transposed convs; same tolerance as the one-CTA tcgen05 kernel."""
+    import os
+    tr, B, H, W, C0, C1, Cout, act = case
+    rng = np.random.default_rng(abs(hash(case)) % (2 ** 31))
+    in0 = rng.standard_normal((B, H, W, C0)).astype(np.float32)
+    in1 = rng.standard_normal((B, H, W, C1)).astype(np.float32) if C1 else None
+    Cin = C0 + C1
+    shape = (Cin, Cout, 4, 4) if tr else (Cout, Cin, 4, 4)
+    Wt = (rng.standard_normal(shape) / np.sqrt(Cin * 16 / (4 if tr else 1))).astype(np.float32)
+    scale = rng.uniform(0.8, 1.2, Cout).astype(np.float32)
+    shift = (0.1 * rng.standard_normal(Cout)).astype(np.float32)
+    ref = _ref(in0, in1, Wt, scale, shift, tr, 4, 2, 1, act)
+    old = os.environ.get('RYK_TC2')
+    try:
+        os.environ['RYK_TC2'] = '0'
+        base, _ = engine.test_conv_layer(in0, in1, Wt, scale, shift, tr, 4, 2, 1, act, use_tc=1)
+        os.environ['RYK_TC2'] = '2'
+        got, ms = engine.test_conv_layer(in0, in1, Wt, scale, shift, tr, 4, 2, 1, act, use_tc=1, repeat=3)
+    finally:
+        if old is None:
+            os.environ.pop('RYK_TC2', None)
+        else:
+            os.environ['RYK_TC2'] = old
+    err, err_base = np.abs(got - ref).max(), np.abs(base - ref).max()
+    print('pair kernel', case, 'max err', err, '(one-CTA kernel', err_base, ') ms', ms)
+    assert err < 3e-2, err
+    assert np.abs(got - base).max() < 2e-2          # same fp16 operands, fp32 accumulation in a different order

@@ -117,17 +117,28 @@ def test_realtime_pipeline_matches_oracle_workers(engine, small_models, T):
     ac, sr, f0c = _load(engine, small_models)
     engine.set_precision('fp32')
     p1, p2 = onets.load_npz(small_models['stage1_model_path']), onets.load_npz(small_models['stage2_model_path'])
-    cfg = _config(small_models, T, 50.0)
-    pipe = RealtimePipeline(cfg, acoustic_param=ac.config.dataset.acoustic_param, engine=engine, depth=3)
-    orc = opipe.StreamOracle(CFG, p1, p2, f0c.stats(), buffer_time=T, extra=(0.0, 0.5, 0.0), backend='torch')
-    rb = opipe.OutputReblockOracle(cfg.out_audio_chunk, cfg.output_silent_threshold)
     x = synthetic.synthetic_speech(3.0, stream=41)
-    x[int(1.2 * 24000):int(2.1 * 24000)] *= 1e-6                   # a stretch that the output gate must drop
-    n = cfg.in_audio_chunk
+    x[int(1.2 * 24000):int(2.1 * 24000)] *= 1e-6                   # a muted stretch (the input gate turns it into silent frames)
+    n = round(T * 24000)
     K = len(x) // n
-    expected = []
-    for k in range(K):
-        expected.append(rb.push(orc.push(x[k * n:(k + 1) * n])))
+    # the oracle's raw decode-worker input, then a threshold that gates roughly half of the chunks (stage 2 with random weights
+    # does not keep muted frames quiet, so a fixed dB value would gate nothing or everything)
+    orc = opipe.StreamOracle(CFG, p1, p2, f0c.stats(), buffer_time=T, extra=(0.0, 0.5, 0.0), backend='torch')
+    raw = [orc.push(x[k * n:(k + 1) * n]) for k in range(K)]
+    probe = opipe.OutputReblockOracle(n, 1e9)
+    powers = []
+    for r in raw:
+        if probe.push(r)[0] != 0:
+            powers.append(probe.last_power)
+    ps = np.sort(np.asarray(powers))
+    gi = int(np.argmax(np.diff(ps)))                               # widest gap between consecutive chunk powers: robust split point
+    thr = -float(0.5 * (ps[gi] + ps[gi + 1]))
+    cfg = _config(small_models, T, thr)
+    pipe = RealtimePipeline(cfg, acoustic_param=ac.config.dataset.acoustic_param, engine=engine, depth=3)
+    rb = opipe.OutputReblockOracle(cfg.out_audio_chunk, cfg.output_silent_threshold)
+    expected = [rb.push(r) for r in raw]
+    margin = min(abs(pw + thr) for pw in powers)                   # distance of the closest chunk to the threshold (dB)
+    assert margin > 1e-3, 'degenerate threshold'
     got = []
     for k in range(K):
         pipe.put(Item(item=x[k * n:(k + 1) * n], index=k))
