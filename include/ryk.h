@@ -139,6 +139,14 @@ int ryk_reblock_collect(ryk_engine* e, int reblock_id, long long ticket, double*
 int ryk_reblock_result_device(ryk_engine* e, int reblock_id, long long ticket, const double** chunk_dev, const int** status_dev,
                               const double** power_dev);
 
+/* ---- sample-rate conversion for wav input (check.py:80 librosa.load(path, sr=input_rate)) --------
+ * Polyphase FIR resampling, the upfirdn step of scipy.signal.resample_poly: up / down must be coprime, `taps` is the
+ * odd-length low-pass filter already scaled by `up` (realtime_yukarin_b200/wave_io.py: resample_filter), edges are
+ * zero-padded; y receives ryk_resample_length(n, up, down) = ceil(n * up / down) samples. */
+int ryk_resample_length(int n, int up, int down);
+int ryk_resample_poly(ryk_engine* e, const float* x, int n, int up, int down, const double* taps, int n_taps, float* y,
+                      int y_capacity, int* n_out);
+
 /* ---- device-resident streaming session (one audio stream) -------------------------------------- */
 typedef struct {
   int fs;                       /* 24000 */

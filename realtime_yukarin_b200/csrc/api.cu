@@ -607,6 +607,31 @@ int ryk_output_gate(ryk_engine* h, const double* wave, int n, int n_fft, int hop
 }
 
 
+int ryk_resample_length(int n, int up, int down) {
+  if (n <= 0 || up <= 0 || down <= 0) return 0;
+  const long long m = (long long)n * up;
+  return (int)(m / down + (m % down != 0));
+}
+
+int ryk_resample_poly(ryk_engine* h, const float* x, int n, int up, int down, const double* taps, int n_taps, float* y, int y_capacity, int* n_out) {
+  Engine* e = E(h);
+  RYK_CUDA(cudaSetDevice(e->device));
+  RYK_CHECK(x && taps && y && n > 0 && up > 0 && down > 0 && n_taps > 0 && (n_taps & 1), "bad resampler arguments (the filter must have an odd number of taps)");
+  const int no = ryk_resample_length(n, up, down);
+  RYK_CHECK(no <= y_capacity, "output buffer too small: ryk_resample_length samples are written");
+  void* buf = nullptr;
+  const size_t bx = ((sizeof(float) * (size_t)n + 255) / 256) * 256, bh = ((sizeof(double) * (size_t)n_taps + 255) / 256) * 256;
+  if (engine_scratch(e, bx + bh + sizeof(float) * (size_t)no + 256, &buf)) return -1;
+  float* d_x = (float*)buf; double* d_h = (double*)((char*)buf + bx); float* d_y = (float*)((char*)buf + bx + bh);
+  RYK_CUDA(cudaMemcpyAsync(d_x, x, sizeof(float) * n, cudaMemcpyHostToDevice, e->stream));
+  RYK_CUDA(cudaMemcpyAsync(d_h, taps, sizeof(double) * n_taps, cudaMemcpyHostToDevice, e->stream));
+  if (resample_poly_run(e, d_x, n, up, down, d_h, n_taps, d_y, no, e->stream)) return -1;
+  RYK_CUDA(cudaMemcpyAsync(y, d_y, sizeof(float) * no, cudaMemcpyDeviceToHost, e->stream));
+  RYK_CUDA(cudaStreamSynchronize(e->stream));
+  if (n_out) *n_out = no;
+  return 0;
+}
+
 // ---- diagnostics: the synthesizer's pulse ring (index, time, vuv) and scalar state
 int ryk_debug_synth_pulses(ryk_engine* h, int id, long long first, int count, long long* index, double* time, int* vuv, long long* state7) {
   Engine* e = E(h);

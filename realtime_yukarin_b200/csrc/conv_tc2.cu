@@ -19,7 +19,10 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <stdlib.h>
+#include <stdio.h>
 #include <string.h>
+
+#include <vector>
 
 #include "conv.h"
 #include "tc_ptx.cuh"
@@ -63,6 +66,16 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 
+#ifdef RYK_TC_TIMELINE
+// diagnostics build only (RYK_NVCC_EXTRA=-DRYK_TC_TIMELINE): per-CTA phase timestamps, dumped by conv_tc2_run to RYK_TC_TIMELINE_FILE
+constexpr int kTl2MaxCtas = 8192, kTl2Slots = 10;
+__device__ unsigned long long g_tl2[kTl2MaxCtas * kTl2Slots];
+__device__ __forceinline__ unsigned long long tl2_now() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define TL2(slot) do { int c_ = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z); if (c_ < kTl2MaxCtas) g_tl2[c_ * kTl2Slots + (slot)] = tl2_now(); } while (0)
+#else
+#define TL2(slot) do {} while (0)
+#endif
+
 // One staged A view and the (accumulator group, class-local tap) pairs it feeds.
 struct Tc2View { int8_t dy, dx, npairs, group[4], tap[4]; int8_t pad_; };
 struct Tc2Params {
@@ -101,6 +114,12 @@ k_conv_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUt
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();            // 0: leader (issues the MMAs), 1: peer
   pdl_trigger();
+  if (threadIdx.x == 0) {
+    TL2(0);
+#ifdef RYK_TC_TIMELINE
+    { unsigned sm; asm volatile("mov.u32 %0, %smid;" : "=r"(sm)); int c_ = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z); if (c_ < kTl2MaxCtas) { g_tl2[c_ * kTl2Slots + 9] = sm; g_tl2[c_ * kTl2Slots + 8] = rank; } }
+#endif
+  }
 
   // tile coordinates: the pair owns pixel tiles blockIdx.x (even: leader, odd: peer) of the class-local output grid
   int mt = blockIdx.x;
@@ -136,7 +155,9 @@ k_conv_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUt
   cluster_sync_all();                 // barriers of BOTH CTAs are initialised before any remote complete_tx / multicast arrive
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (threadIdx.x == 0) TL2(7);       // after the cluster barrier, before the grid dependency wait
   pdl_wait();
+  if (threadIdx.x == 0) TL2(1);
 
   auto view_of = [&](int v, int& dy, int& dx, int& npairs) {
     if (p.conv16) { dy = v >> 2; dx = v & 3; npairs = 1; }
@@ -183,6 +204,7 @@ k_conv_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUt
         view_of(v, dy, dx, npairs);
         const int sa = ia % kSA;
         mbar_wait(&fullA[sa], (ia / kSA) & 1);
+        if (ia == 0) TL2(2);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint64_t adesc = make_sw128_desc(smem_u32(smem_a + sa * kABytes));
         for (int q = 0; q < npairs; ++q) {
@@ -204,9 +226,11 @@ k_conv_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUt
       }
     }
     umma_commit_2sm(tmem_full);
+    TL2(3);
   } else if (warp < 4) {
     // ===== epilogue (both CTAs, own 128 pixels): one pass per accumulator group =====
     mbar_wait(tmem_full, 0);
+    if (threadIdx.x == 0) TL2(4);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int row = warp * 32 + lane;
     for (int g = 0; g < p.n_groups; ++g) {
@@ -266,12 +290,14 @@ k_conv_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUt
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
   }
+  if (threadIdx.x == 0) TL2(5);
   // both CTAs are done with TMEM and with each other's shared memory / barriers before either one deallocates or exits
   __syncwarp();
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   cluster_sync_all();
   if (warp == 4) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols) : "memory");
+    if (lane == 0) TL2(6);
   }
 }
 
@@ -280,20 +306,22 @@ template <int NG, int kSA, int kSB> static constexpr size_t tc2_smem_bytes() {
   return (size_t)kSA * (kBlockM * kBlockK * 2) + (size_t)kSB * ((NG / 2) * kBlockK * 2) + (2 * kSA + 2 * kSB + 1) * 8 + 16 + 1024 + 2 * NG * 4 + 32;
 }
 
-// instantiations: (N per group, A stages, B stages, TMEM columns)
-#define TC2_G1_128 k_conv_tc2<128, 4, 4, 128>      // plain convs and per-class transposed convs, N = 128
-#define TC2_G2_128 k_conv_tc2<128, 4, 4, 256>      // two parity classes of N = 128 (Cout = 128)
-#define TC2_G4_64 k_conv_tc2<64, 4, 6, 256>        // four parity classes of N = 64 (Cout = 64)
+// instantiations: (N per group, A stages, B stages, TMEM columns); RYK_TC2_DEEP=1 selects the deeper B rings (tuning)
+#define TC2_LIST(X)                                                                                       \
+  X(128, 4, 4, 128) X(128, 4, 6, 128) X(128, 4, 4, 256) X(128, 4, 6, 256) X(64, 4, 6, 256) X(64, 4, 12, 256) X(64, 4, 8, 128)
 
 int tc2_init() {
-  RYK_CUDA(cudaFuncSetAttribute(TC2_G1_128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc2_smem_bytes<128, 4, 4>()));
-  RYK_CUDA(cudaFuncSetAttribute(TC2_G2_128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc2_smem_bytes<128, 4, 4>()));
-  RYK_CUDA(cudaFuncSetAttribute(TC2_G4_64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc2_smem_bytes<64, 4, 6>()));
+#define TC2_ATTR(NG, SA, SB, TC) RYK_CUDA(cudaFuncSetAttribute(k_conv_tc2<NG, SA, SB, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc2_smem_bytes<NG, SA, SB>()));
+  TC2_LIST(TC2_ATTR)
+#undef TC2_ATTR
   return 0;
 }
 
-// RYK_TC2: 0 = never, 1 (default) = where the pair kernel fills the GPU, 2 = wherever the shape allows (unit tests)
-static int tc2_mode() { const char* v = getenv("RYK_TC2"); return v ? atoi(v) : 1; }
+static int tc2_env(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
+
+// RYK_TC2: 0 (default) = never, 1 = where the pair kernel fills the GPU, 2 = wherever the shape allows (unit tests).
+// Off by default: at batch 1 the pair pipeline is latency-bound, the one-CTA kernel is faster.
+static int tc2_mode() { return tc2_env("RYK_TC2", 0); }
 
 // Picks (groups, N per group) for the pair kernel; false: the layer stays on the one-CTA-per-tile kernel of conv_tc.cu.
 bool tc2_layer_config(const ConvLayer& L, int num_sms, int* groups, int* ng) {
@@ -310,7 +338,7 @@ bool tc2_layer_config(const ConvLayer& L, int num_sms, int* groups, int* ng) {
   if (!L.transposed) {
     if (L.Cout % 128 != 0) return false;
     G = 1; NG = 128; ctas = tiles_x * (L.Cout / 128);
-  } else if (L.Cout == 64) { G = 4; NG = 64; ctas = tiles_x; }
+  } else if (L.Cout == 64) { G = tc2_env("RYK_TC2_G64", 4) == 2 ? 2 : 4; NG = 64; ctas = tiles_x * (4 / G); }
   else if (L.Cout == 128) { G = 2; NG = 128; ctas = tiles_x * 2; }
   else if (L.Cout % 128 == 0) { G = 1; NG = 128; ctas = tiles_x * (L.Cout / 128) * 4; }
   else return false;
@@ -380,10 +408,31 @@ int conv_tc2_run(const ConvLayer& L, cudaStream_t st, bool pdl) {
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl ? 2 : 1;
-  if (G == 1) { cfg.dynamicSmemBytes = tc2_smem_bytes<128, 4, 4>(); RYK_CUDA(cudaLaunchKernelEx(&cfg, TC2_G1_128, L.tmA0, L.tmA1, L.tmB2, L.tmO, p)); }
-  else if (G == 2) { cfg.dynamicSmemBytes = tc2_smem_bytes<128, 4, 4>(); RYK_CUDA(cudaLaunchKernelEx(&cfg, TC2_G2_128, L.tmA0, L.tmA1, L.tmB2, L.tmO, p)); }
-  else { cfg.dynamicSmemBytes = tc2_smem_bytes<64, 4, 6>(); RYK_CUDA(cudaLaunchKernelEx(&cfg, TC2_G4_64, L.tmA0, L.tmA1, L.tmB2, L.tmO, p)); }
+  const bool deep = tc2_env("RYK_TC2_DEEP", 0) != 0;
+#define TC2_LAUNCH(NGv, SA, SB, TC) do { cfg.dynamicSmemBytes = tc2_smem_bytes<NGv, SA, SB>(); \
+    RYK_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc2<NGv, SA, SB, TC>, L.tmA0, L.tmA1, L.tmB2, L.tmO, p)); } while (0)
+  if (NG == 128 && G == 1) { if (deep) TC2_LAUNCH(128, 4, 6, 128); else TC2_LAUNCH(128, 4, 4, 128); }
+  else if (NG == 128 && G == 2) { if (deep) TC2_LAUNCH(128, 4, 6, 256); else TC2_LAUNCH(128, 4, 4, 256); }
+  else if (NG == 64 && G == 4) { if (deep) TC2_LAUNCH(64, 4, 12, 256); else TC2_LAUNCH(64, 4, 6, 256); }
+  else if (NG == 64 && G == 2) TC2_LAUNCH(64, 4, 8, 128);
+  else { set_error("pair kernel: unsupported (groups, N) combination"); return -1; }
+#undef TC2_LAUNCH
   RYK_CUDA(cudaGetLastError());
+#ifdef RYK_TC_TIMELINE
+  cudaStreamCaptureStatus cap_ = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cap_);
+  if (const char* path = cap_ == cudaStreamCaptureStatusNone ? getenv("RYK_TC_TIMELINE_FILE") : nullptr) {
+    cudaStreamSynchronize(st);
+    static std::vector<unsigned long long> h(kTl2MaxCtas * kTl2Slots);
+    cudaMemcpyFromSymbol(h.data(), g_tl2, sizeof(unsigned long long) * h.size());
+    int n = grid.x * grid.y * grid.z; if (n > kTl2MaxCtas) n = kTl2MaxCtas;
+    if (FILE* f = fopen(path, "w")) {
+      fprintf(f, "# pair kernel grid %d %d %d groups %d ng %d\n", grid.x, grid.y, grid.z, G, NG);
+      for (int c = 0; c < n; ++c) { for (int k = 0; k < kTl2Slots; ++k) fprintf(f, "%llu ", h[c * kTl2Slots + k]); fprintf(f, "\n"); }
+      fclose(f);
+    }
+  }
+#endif
   return 0;
 }
 

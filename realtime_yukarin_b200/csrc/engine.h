@@ -83,6 +83,9 @@ size_t output_gate_scratch_doubles(int n, int n_fft, int hop);
 int sptk_prepare(Engine* e, int order, double alpha, int fft_size);                 // builds G and H on the device
 int mc2sp_run(Engine* e, const float* d_mc, int T, int order, int fft_size, double add, float* d_sp_f32, double* d_sp_f64, cudaStream_t st);
 
+// features.cu: polyphase resampler (wav I/O row)
+int resample_poly_run(Engine* e, const float* d_x, int n, int up, int down, const double* d_h, int n_taps, float* d_y, int n_out, cudaStream_t st);
+
 // gate.cu
 int gate_mask_run(Engine* e, const float* d_wave, int n, int frame_length, int hop, double threshold_db, int n_frames,
                   double* d_mse_scratch, uint8_t* d_mask, int* d_index /*compacted frame ids*/, int* d_count, cudaStream_t st);

@@ -294,4 +294,34 @@ int sr_epilogue_run(Engine* e, const float* d_y, int T, int nb, float* d_sp_out,
   return 0;
 }
 
+// ------------------------------------------------------------------------------------ polyphase resampler
+// SURVEY 8(f) rank 3 (check.py:80 librosa.load(..., sr=input_rate)): scipy.signal.resample_poly's upfirdn step on the device.
+//   y[i] = sum over j of x[j] * h[(i + n_pre_remove) * down - j * up - n_pre_pad],  0 <= tap index < n_taps, x zero outside [0, n)
+// One thread per output sample, FP64 accumulation over the ~n_taps / up taps that hit an input sample (ascending j).
+__global__ void __launch_bounds__(256) k_resample_poly(const float* __restrict__ x, int n, int up, int down, const double* __restrict__ h, int n_taps,
+                                                      int n_pre_pad, int n_pre_remove, float* __restrict__ y, int n_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  const long long t = (long long)(i + n_pre_remove) * down - n_pre_pad;       // tap index of x[0]
+  // tap = t - j * up in [0, n_taps)  <=>  (t - n_taps + 1) / up <= j <= t / up
+  long long jlo = t - (n_taps - 1);
+  jlo = jlo <= 0 ? 0 : (jlo + up - 1) / up;
+  long long jhi = t < 0 ? -1 : t / up;
+  if (jhi > n - 1) jhi = n - 1;
+  double acc = 0.0;
+  for (long long j = jlo; j <= jhi; ++j) acc += (double)x[j] * h[t - j * up];
+  y[i] = (float)acc;
+}
+
+int resample_poly_run(Engine* e, const float* d_x, int n, int up, int down, const double* d_h, int n_taps, float* d_y, int n_out, cudaStream_t st) {
+  const int half_len = (n_taps - 1) / 2;
+  const int n_pre_pad = down - half_len % down;
+  const int n_pre_remove = (half_len + n_pre_pad) / down;
+  if (n_out <= 0) return 0;
+  k_resample_poly<<<(n_out + 255) / 256, 256, 0, st>>>(d_x, n, up, down, d_h, n_taps, n_pre_pad, n_pre_remove, d_y, n_out);
+  RYK_CUDA(cudaGetLastError());
+  e->launches++;
+  return 0;
+}
+
 }  // namespace ryk

@@ -76,6 +76,7 @@ struct Session {
   double* d_out_fixed[2];              // blocks written by the (captured) decode graph, by parity
   int* d_n_fixed[2];
   bool use_graphs = true;
+  bool merge_s2 = false;           // this step: stage-2 prologue + 16 layers + epilogue replayed as ONE graph (no profiling events in between)
   bool host_prof = false; double host_wait_us = 0.0, host_total_us = 0.0; long long host_steps = 0;   // RYK_HOST_PROF=1
   std::map<int, StageGraph> graphs;
   Synth* synth = nullptr;
@@ -330,7 +331,7 @@ static int run_stage(Engine* e, Session* s, int key, cudaStream_t st, F&& body, 
 }
 
 enum { G_E1 = 0, G_E2 = 2, G_S1 = 4 /* + 2 * bucket + parity; bucket 0 = no effective frame, else padded length / 128 (1..15) */,
-       G_S2A = 40, G_S2B = 42, G_S2C = 44, G_D = 46, G_D1 = 48 };
+       G_S2A = 40, G_S2B = 42, G_S2C = 44, G_D = 46, G_D1 = 48, G_S2M = 50 };
 
 // Stage 1 of a chunk of parity b: slide the feature window, (gather ->) 1-D U-Net at padded length tp1 (0: no effective frame,
 // voice_changer.py:32-35 skips the net) -> scatter into the silent template + f0 map, mc2sp.  One graph per (tp1 bucket, parity);
@@ -446,7 +447,7 @@ static int session_front(Engine* e, Session* s, const float* d_chunk_user) {
   } else {
     UNetPlan* p2 = nullptr;
     if (unet_get_plan(e, e->stage2, 1, Tp, 512, e->precision, &p2, s->owner)) return -1;
-    if (run_stage(e, s, G_S2A + b, s->sC2, [&]() -> int {
+    if (!s->merge_s2 && run_stage(e, s, G_S2A + b, s->sC2, [&]() -> int {
           if (sr_prologue_run(e, s->cv_sp_mid[b], s->Tw, Tp, s->nb, (float*)p2->d_in, s->sC2, s->d_colmin)) return -1;
           return unet_forward(e, p2, s->sC2, 0, 0);
         })) return -1;
@@ -462,6 +463,14 @@ static int session_mid_single(Engine* e, Session* s, bool was_profiling) {
   if (unet_get_plan(e, e->stage2, 1, Tp, 512, e->precision, &p2, s->owner)) return -1;
   cudaEvent_t pe0 = nullptr, pe1 = nullptr;
   if (was_profiling) { RYK_CUDA(cudaEventCreate(&pe0)); RYK_CUDA(cudaEventCreate(&pe1)); RYK_CUDA(cudaEventRecord(pe0, s->sC2)); }
+  if (s->merge_s2) {
+    // whole stage 2 as one graph: no launch gaps between prologue, the 16 layers and the epilogue (PDL chains through)
+    return run_stage(e, s, G_S2M + b, s->sC2, [&]() -> int {
+      if (sr_prologue_run(e, s->cv_sp_mid[b], s->Tw, Tp, s->nb, (float*)p2->d_in, s->sC2, s->d_colmin)) return -1;
+      if (unet_forward(e, p2, s->sC2, 0, 15)) return -1;
+      return sr_epilogue_run(e, (const float*)p2->d_out, s->Tw, s->nb, s->cv_sp_out[b], s->sC2);
+    });
+  }
   if (run_stage(e, s, G_S2B + b, s->sC2, [&]() -> int { return unet_forward(e, p2, s->sC2, 1, 14); })) return -1;
   if (was_profiling) { RYK_CUDA(cudaEventRecord(pe1, s->sC2)); e->prof_events.emplace_back(pe0, pe1); }
   return 0;
@@ -478,7 +487,7 @@ static int session_back(Engine* e, Session* s) {
   } else {
     UNetPlan* p2 = nullptr;
     if (unet_get_plan(e, e->stage2, 1, Tp, 512, e->precision, &p2, s->owner)) return -1;
-    if (run_stage(e, s, G_S2C + b, s->sC2, [&]() -> int {
+    if (!s->merge_s2 && run_stage(e, s, G_S2C + b, s->sC2, [&]() -> int {
           if (unet_forward(e, p2, s->sC2, 15, 15)) return -1;
           return sr_epilogue_run(e, (const float*)p2->d_out, s->Tw, s->nb, s->cv_sp_out[b], s->sC2);
         })) return -1;
@@ -524,6 +533,8 @@ static int session_enqueue(Engine* e, Session* s, const float* d_chunk_user) {
     ~HostProf() { if (s->host_prof) { s->host_total_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); s->host_steps++; } } } host_prof_guard{s, host_t0};
   const bool was_profiling = e->profile;
   e->profile = false;                                      // the session places its own timing events (between graph launches)
+  { static int no_merge = -1; if (no_merge < 0) { const char* v = getenv("RYK_NO_S2_MERGE"); no_merge = v && atoi(v) ? 1 : 0; }
+    s->merge_s2 = !was_profiling && !s->group && s->use_graphs && !no_merge && session_skip_mask() == 0; }
   int rc = session_front(e, s, d_chunk_user);
   if (!rc) rc = session_mid_single(e, s, was_profiling);
   if (!rc) rc = session_back(e, s);

@@ -13,7 +13,7 @@ import numpy
 from .world_consts import cheaptrick_fft_size, dio_num_frames  # noqa: F401  (re-exported)
 
 _CSRC = Path(__file__).resolve().parent / 'csrc'
-_LIB_PATH = _CSRC / 'libryk.so'
+_LIB_PATH = Path(os.environ['RYK_LIB']) if os.environ.get('RYK_LIB') else _CSRC / 'libryk.so'     # RYK_LIB: diagnostics builds
 
 c_int_p = ctypes.POINTER(ctypes.c_int)
 c_float_p = ctypes.POINTER(ctypes.c_float)
@@ -49,7 +49,8 @@ EXPORTED_SYMBOLS = [
     'ryk_session_push_device', 'ryk_session_submit', 'ryk_session_collect', 'ryk_group_create', 'ryk_group_destroy',
     'ryk_group_size', 'ryk_session_stage_times', 'ryk_group_submit', 'ryk_group_collect', 'ryk_group_push_device', 'ryk_test_conv_layer', 'ryk_debug_dio', 'ryk_debug_synth_pulses', 'ryk_debug_synth_timebase', 'ryk_engine_profile', 'ryk_engine_profile_read', 'ryk_engine_timer_start', 'ryk_engine_timer_stop',
     'ryk_world_synthesize_length', 'ryk_world_synthesize', 'ryk_output_gate', 'ryk_reblock_create', 'ryk_reblock_destroy',
-    'ryk_reblock_push', 'ryk_reblock_push_device', 'ryk_reblock_collect', 'ryk_reblock_result_device',
+    'ryk_reblock_push', 'ryk_reblock_push_device', 'ryk_reblock_collect', 'ryk_reblock_result_device', 'ryk_resample_length',
+    'ryk_resample_poly',
 ]
 
 
@@ -341,6 +342,16 @@ class Engine(object):
         st, pw = ctypes.c_int(), ctypes.c_double()
         self._check(self.lib.ryk_reblock_collect(self._h, rid, ctypes.c_longlong(ticket), _dp(out), ctypes.byref(st), ctypes.byref(pw)))
         return st.value, (out if st.value == 1 else None), pw.value
+
+    def resample_poly(self, x, up: int, down: int, taps) -> numpy.ndarray:
+        """scipy.signal.resample_poly's filtering step on the device (wave_io.resample designs `taps`)."""
+        x = _f32(x)
+        taps = numpy.ascontiguousarray(taps, dtype=numpy.float64)
+        n = self.lib.ryk_resample_length(len(x), int(up), int(down))
+        y = numpy.empty(max(n, 1), dtype=numpy.float32)
+        no = ctypes.c_int()
+        self._check(self.lib.ryk_resample_poly(self._h, _fp(x), len(x), int(up), int(down), _dp(taps), len(taps), _fp(y), len(y), ctypes.byref(no)))
+        return y[:no.value]
 
     # ---- diagnostics ----
     def debug_synth_pulses(self, sid, first=0, count=None):

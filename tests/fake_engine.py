@@ -86,3 +86,7 @@ class OracleEngine:
 
     def reblock_destroy(self, rid):
         self.reblocks.pop(rid, None)
+
+    def resample_poly(self, x, up, down, taps):
+        import scipy.signal as ss
+        return ss.resample_poly(np.asarray(x, np.float64), up, down, window=np.asarray(taps, np.float64) / up).astype(np.float32)
