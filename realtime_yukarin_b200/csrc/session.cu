@@ -533,8 +533,9 @@ static int session_enqueue(Engine* e, Session* s, const float* d_chunk_user) {
     ~HostProf() { if (s->host_prof) { s->host_total_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); s->host_steps++; } } } host_prof_guard{s, host_t0};
   const bool was_profiling = e->profile;
   e->profile = false;                                      // the session places its own timing events (between graph launches)
-  { static int no_merge = -1; if (no_merge < 0) { const char* v = getenv("RYK_NO_S2_MERGE"); no_merge = v && atoi(v) ? 1 : 0; }
-    s->merge_s2 = !was_profiling && !s->group && s->use_graphs && !no_merge && session_skip_mask() == 0; }
+  // RYK_S2_MERGE=1 (experiment, off by default: +1 % end to end): replay stage 2 as one graph on steps without profiling events
+  { static int merge = -1; if (merge < 0) { const char* v = getenv("RYK_S2_MERGE"); merge = v && atoi(v) ? 1 : 0; }
+    s->merge_s2 = merge && !was_profiling && !s->group && s->use_graphs && session_skip_mask() == 0; }
   int rc = session_front(e, s, d_chunk_user);
   if (!rc) rc = session_mid_single(e, s, was_profiling);
   if (!rc) rc = session_back(e, s);

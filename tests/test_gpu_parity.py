@@ -238,6 +238,9 @@ def test_device_session_matches_oracle_stream(engine, small_models):
         y, r = np.concatenate(outs), np.concatenate(refs)
         rmse = float(np.sqrt(np.mean((y - r) ** 2)))
         print(f'session T={T} extra={extra}: {len(y)} samples, rmse {rmse:.3e}, signal rms {float(np.sqrt(np.mean(r ** 2))):.3e}')
+        if rmse >= 1e-3:      # diagnostics: which chunks differ, and by how much
+            per = [(k, len(a), float(np.sqrt(np.mean((a - b) ** 2))) if len(a) else 0.0) for k, (a, b) in enumerate(zip(outs, refs))]
+            print('per-chunk (index, samples, rmse):', [(k, n_, f'{e_:.1e}') for k, n_, e_ in per if e_ > 1e-5])
         assert rmse < 1e-3
         engine.session_destroy(sid)
     engine.set_precision('fp16')

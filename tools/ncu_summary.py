@@ -7,6 +7,12 @@ KEEP = [
     ('Kernel Name', 'kernel'), ('launch__grid_size', 'grid'), ('launch__block_size', 'block'), ('launch__registers_per_thread', 'regs'),
     ('gpu__time_duration.sum', 'duration_us'), ('dram__bytes_read.sum', 'dram_read'), ('dram__bytes_write.sum', 'dram_write'),
     ('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'dram_pct'), ('lts__t_bytes.sum', 'l2_bytes'),
+    ('l1tex__m_xbar2l1tex_read_bytes.sum', 'l2_to_sm_read'), ('l1tex__m_xbar2l1tex_read_bytes.sum.per_second', 'l2_to_sm_rate'),
+    ('lts__throughput.avg.pct_of_peak_sustained_elapsed', 'l2_pct'),
+    ('sm__inst_executed_pipe_tensor_op_hmma.avg.pct_of_peak_sustained_active', 'tensor_hmma_pct_active'),
+    ('sm__pipe_tensor_op_hmma_cycles_active.avg.pct_of_peak_sustained_active', 'tensor_hmma_cycles_pct'),
+    ('sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active', 'tensor_subpipe_hmma_pct'),
+    ('launch__occupancy_limit_registers', 'occ_limit_regs'), ('launch__cluster_dim_x', 'cluster_x'),
     ('sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm_pct'),
     ('TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed', 'tensor_pipe_pct'),
     ('sm__warps_active.avg.pct_of_peak_sustained_active', 'warps_active_pct'),
