@@ -647,7 +647,9 @@ int ryk_session_create(ryk_engine* h, const ryk_session_config* cfg, int* sessio
   { const char* v = getenv("RYK_STAGE_TIMES"); s->stage_times = v && atoi(v) != 0; }
   { const char* v = getenv("RYK_HOST_PROF"); s->host_prof = v && atoi(v) != 0; }
   if (s->stage_times) for (int a = 0; a < 5; ++a) for (int w = 0; w < 2; ++w) for (int i = 0; i < kRing; ++i) RYK_CUDA(cudaEventCreate(&s->tev[a][w][i]));
-  auto A = [&](void** p, size_t bytes) -> int { RYK_CUDA(cudaMalloc(p, bytes ? bytes : 16)); RYK_CUDA(cudaMemset(*p, 0, bytes ? bytes : 16)); s->allocs.push_back(*p); return 0; };
+  // zero-fill on the ENGINE stream: the template fill below (k_fill_rows on e->stream, a non-blocking stream) must be ordered after
+  // it -- a legacy-default-stream cudaMemset is not, and could land after the fill (seen once as a 4e-3 RMSE mismatch)
+  auto A = [&](void** p, size_t bytes) -> int { RYK_CUDA(cudaMalloc(p, bytes ? bytes : 16)); RYK_CUDA(cudaMemsetAsync(*p, 0, bytes ? bytes : 16, e->stream)); s->allocs.push_back(*p); return 0; };
   auto P = [&](void** p, size_t bytes) -> int { RYK_CUDA(cudaMallocHost(p, bytes ? bytes : 16)); memset(*p, 0, bytes ? bytes : 16); s->pinned.push_back(*p); return 0; };
   const int n_enc = s->Lw / s->hop;
   for (int i = 0; i < 2; ++i) {
@@ -972,6 +974,7 @@ int ryk_reblock_create(ryk_engine* h, int out_audio_chunk, int max_in, int n_fft
     if (!rc && cudaEventCreateWithFlags(&R->ev[i], cudaEventDisableTiming) != cudaSuccess) rc = -1;
   }
   if (rc) { reblock_free(R); return -1; }
+  RYK_CUDA(cudaDeviceSynchronize());             // the zero-fills ran on the legacy default stream; pushes use other (non-blocking) streams
   e->reblocks.push_back(R);
   *reblock_id = (int)e->reblocks.size() - 1;
   return 0;
