@@ -90,3 +90,44 @@ class OracleEngine:
     def resample_poly(self, x, up, down, taps):
         import scipy.signal as ss
         return ss.resample_poly(np.asarray(x, np.float64), up, down, window=np.asarray(taps, np.float64) / up).astype(np.float32)
+
+    # ---- device-session stand-in (worker.RealtimePipeline on CPU): StreamOracle + OutputReblockOracle, results kept per ticket ----
+    def session_create(self, cfg):
+        self.sessions = getattr(self, 'sessions', {})
+        sid = len(self.sessions)
+        stats = self.stats if self.stats is not None else (float(np.log(150.0)), 0.2, float(np.log(250.0)), 0.2)
+        pc = opipe.PathConfig(threshold_db=cfg.threshold_db)
+        orc = opipe.StreamOracle(pc, self.p1, self.p2, stats, buffer_time=cfg.buffer_time,
+                                 extra=(cfg.encode_extra_time, cfg.convert_extra_time, cfg.decode_extra_time), backend=self.backend)
+        self.sessions[sid] = dict(orc=orc, out={}, step=0, last=None)
+        return sid
+
+    def session_submit(self, sid, wave):
+        S = self.sessions[sid]
+        S['last'] = S['orc'].push(np.asarray(wave, np.float32))
+        S['out'][S['step']] = S['last']
+        S['step'] += 1
+        return S['step'] - 1
+
+    def session_collect(self, sid, ticket, out):
+        y = self.sessions[sid]['out'].pop(ticket)
+        out[:len(y)] = y
+        return out[:len(y)]
+
+    def session_destroy(self, sid):
+        self.sessions.pop(sid, None)
+
+    def reblock_push_device(self, rid, session_id=-1, wave_dev_ptr=0, n_dev_ptr=0):
+        assert session_id >= 0, 'the stand-in only supports the attached mode'
+        R = self.reblocks[rid]
+        res = getattr(R, 'results', None)
+        if res is None:
+            res = R.results = {}
+            R.pushed = 0
+        st, chunk = R.push(self.sessions[session_id]['last'])
+        res[R.pushed] = (st, chunk, R.last_power or 0.0)
+        R.pushed += 1
+        return R.pushed - 1
+
+    def reblock_collect(self, rid, ticket):
+        return self.reblocks[rid].results.pop(ticket)

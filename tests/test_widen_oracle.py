@@ -134,3 +134,44 @@ def test_vocoder_decode_is_offline_synthesis(small_models):
         assert np.array_equal(w.wave, W.synthesize(f['f0'].ravel().astype(np.float64), f['sp'], f['ap'], 24000, 5.0))
     finally:
         eng_mod.set_default_engine(None)
+
+
+def test_realtime_pipeline_audio_loop_on_cpu(small_models):
+    """worker.RealtimePipeline over the oracle-backed session stand-in: put / get_nowait keep index order and item
+    semantics (None = no chunk yet or silent), and process() is the run.py:160-199 loop body (scaling, re-ordering, zeros)."""
+    from realtime_yukarin_b200.config import Config, VocodeMode
+    from realtime_yukarin_b200.worker import Item, RealtimePipeline
+    fake = OracleEngine(small_models['stage1_model_path'], small_models['stage2_model_path'])
+    cfg = Config(input_device_name=None, output_device_name=None, input_rate=24000, output_rate=24000, frame_period=5.0, buffer_time=0.3,
+                 extract_f0_mode=VocodeMode.WORLD, vocoder_buffer_size=1024, input_scale=0.5, output_scale=2.0, input_silent_threshold=60.0,
+                 output_silent_threshold=80.0, encode_extra_time=0.0, convert_extra_time=0.5, decode_extra_time=0.0,
+                 **{k: small_models[k] for k in ('input_statistics_path', 'target_statistics_path', 'stage1_model_path', 'stage1_config_path',
+                                                 'stage2_model_path', 'stage2_config_path')})
+    x = synthetic.synthetic_speech(2.4, stream=17)
+    n = cfg.in_audio_chunk
+    K = len(x) // n
+    # expected: the same oracle objects driven by hand
+    from oracle import nets as onets
+    p1, p2 = onets.load_npz(small_models['stage1_model_path']), onets.load_npz(small_models['stage2_model_path'])
+    stats = (float(np.log(150.0)), 0.2, float(np.log(250.0)), 0.2)
+    orc = opipe.StreamOracle(opipe.PathConfig(threshold_db=60.0), p1, p2, stats, buffer_time=0.3, extra=(0.0, 0.5, 0.0), backend='torch')
+    rb = opipe.OutputReblockOracle(cfg.out_audio_chunk, 80.0)
+    expected = [rb.push(orc.push((x[k * n:(k + 1) * n] * cfg.input_scale).astype(np.float32)))[1] for k in range(K)]
+
+    pipe = RealtimePipeline(cfg, engine=fake, depth=2)
+    pipe.put(Item(item=x[:n] * cfg.input_scale, index=0))
+    assert pipe.get_nowait() is None                      # still in flight
+    it = pipe.get()
+    assert it.index == 0 and (it.item is None) == (expected[0] is None)
+    pipe.close()
+
+    pipe = RealtimePipeline(cfg, engine=fake, depth=2)
+    outs = [pipe.process(x[k * n:(k + 1) * n]) for k in range(K)]
+    assert all(o.dtype == np.float32 and len(o) == cfg.out_audio_chunk for o in outs)
+    assert not outs[0].any() and not outs[1].any()        # depth 2: nothing has been collected yet -> the loop plays zeros
+    # from step `depth` on, iteration k plays item k - depth (or zeros when that item is None)
+    for k in range(2, K):
+        e = expected[k - 2]
+        want = np.zeros(cfg.out_audio_chunk, np.float32) if e is None else (e * cfg.output_scale)[:cfg.out_audio_chunk].astype(np.float32)
+        assert np.array_equal(outs[k], want), k
+    pipe.close()
