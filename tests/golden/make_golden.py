@@ -23,5 +23,12 @@ out = Path(__file__).resolve().parent
 np.savez_compressed(out / 'golden_small.npz', wave=x, f0=f['f0'].ravel(), voiced=f['voiced'].ravel(),
                     log_sp_sub=np.log(f['sp'][:, ::16]).astype(np.float32), ap_sub=f['ap'][:, ::16], mc=f['mc'],
                     resynth=y.astype(np.float32))
+# offline Synthesis() (pulse plan + waveform), output-gate power of 0.3 s chunks of that waveform, re-blocker statuses
+yo, pidx, pshift, pvuv = W.synthesize(f['f0'].ravel().astype(np.float64), f['sp'], f['ap'], 24000, 5.0, return_pulses=True)
+powers = np.array([W.stft_power_db_mean(yo[a:a + 7200]) for a in range(0, len(yo) - 7199, 7200)])
+rb = opipe.OutputReblockOracle(7200, 30.0)
+statuses = np.array([rb.push(y[a:a + 1024] if a // 1024 % 5 else 1e-6 * y[a:a + 1024])[0] for a in range(0, len(y), 1024)], dtype=np.int32)
+np.savez_compressed(out / 'golden_widen.npz', offline=yo.astype(np.float32), pulse_index=pidx, pulse_shift=pshift, pulse_vuv=pvuv, gate_power=powers,
+                    reblock_status=statuses)
 (out / 'golden_meta.json').write_text(json.dumps(meta))
 print('wrote', out / 'golden_small.npz', 'frames', len(f['f0']), 'samples out', len(y))

@@ -217,3 +217,22 @@ def test_golden_fixtures():
     s = W.RealtimeSynthesizer(FS, 5.0, 1024, 1024)
     y = s.decode(f['f0'].ravel().astype(np.float64), f['sp'], f['ap'])
     assert len(y) == len(z['resynth']) and np.abs(y - z['resynth']).max() < 1e-4 * np.abs(z['resynth']).max()
+
+
+def test_golden_fixtures_widen():
+    """Regression pin of the SURVEY 8(f) oracle rows (offline Synthesis, output gate, re-blocker): tests/golden/golden_widen.npz."""
+    meta = json.loads((GOLDEN / 'golden_meta.json').read_text())
+    z = np.load(GOLDEN / 'golden_widen.npz')
+    x = synthetic.synthetic_speech(meta['seconds'], stream=meta['stream'])
+    f = opipe.extract_features(x, opipe.PathConfig())
+    yo, pidx, pshift, pvuv = W.synthesize(f['f0'].ravel().astype(np.float64), f['sp'], f['ap'], 24000, 5.0, return_pulses=True)
+    assert np.array_equal(pidx, z['pulse_index']) and np.array_equal(pvuv, z['pulse_vuv'])
+    assert np.allclose(pshift, z['pulse_shift'], rtol=0, atol=1e-15)
+    assert len(yo) == len(z['offline']) and np.abs(yo - z['offline']).max() < 1e-6 * max(1.0, np.abs(z['offline']).max())
+    powers = np.array([W.stft_power_db_mean(yo[a:a + 7200]) for a in range(0, len(yo) - 7199, 7200)])
+    assert np.allclose(powers, z['gate_power'], rtol=0, atol=1e-6)
+    s = W.RealtimeSynthesizer(FS, 5.0, 1024, 1024)
+    y = s.decode(f['f0'].ravel().astype(np.float64), f['sp'], f['ap'])
+    rb = opipe.OutputReblockOracle(7200, 30.0)
+    statuses = [rb.push(y[a:a + 1024] if a // 1024 % 5 else 1e-6 * y[a:a + 1024])[0] for a in range(0, len(y), 1024)]
+    assert statuses == z['reblock_status'].tolist()
