@@ -45,11 +45,9 @@ __global__ void __launch_bounds__(1024) k_synth_add(SynthDev S, const double* __
   const long long cum_before = st->cumulative_frame;
   // a. frames into the ring
   for (int i = threadIdx.x; i < n; i += blockDim.x) S.f0[(cum_before + 1 + i) % S.cap_frames] = f0[i];
-  for (size_t i = threadIdx.x; i < (size_t)n * nb; i += blockDim.x) {
-    int fr = i / nb, k = i % nb;
-    size_t slot = (size_t)((cum_before + 1 + fr) % S.cap_frames) * nb + k;
-    S.sp[slot] = sp[i];
-    S.ap[slot] = ap[i];
+  for (int fr = threadIdx.x / 256; fr < n; fr += blockDim.x / 256) {          // one 256-thread quarter of the CTA per frame row
+    const size_t dst = (size_t)((cum_before + 1 + fr) % S.cap_frames) * nb, src = (size_t)fr * nb;
+    for (int k = threadIdx.x & 255; k < nb; k += 256) { S.sp[dst + k] = sp[src + k]; S.ap[dst + k] = ap[src + k]; }
   }
   __syncthreads();
   const long long cum = cum_before + n;
@@ -100,14 +98,22 @@ __global__ void __launch_bounds__(1024) k_synth_add(SynthDev S, const double* __
     const int BLK = 256;
     const int nblk = (np_ + BLK - 1) / BLK;
     double* totals = scan_scratch;                       // nblk <= 1024 (max_samples_per_add / 256)
+    // increments first, by all threads (the FP64 division is the long-latency part); the per-block running sums below are then a
+    // plain load-add-store chain.  Same values, same order of additions as before (and as the oracle).
+    for (int i = threadIdx.x; i < np_; i += blockDim.x) S.tp[i] = i == 0 ? 0.0 : 2.0 * kPi * S.if0[i - hf] / fs;
+    __syncthreads();
     for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
       int b0 = b * BLK, b1 = min(b0 + BLK, np_);
       double local = 0.0;
-      for (int i = b0; i < b1; ++i) {
-        double inc = i == 0 ? 0.0 : 2.0 * kPi * S.if0[i - hf] / fs;
-        local = __dadd_rn(local, inc);
-        S.tp[i] = local;
+      int i = b0;
+      for (; i + 8 <= b1; i += 8) {
+        double v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = S.tp[i + j];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { local = __dadd_rn(local, v[j]); S.tp[i + j] = local; }
       }
+      for (; i < b1; ++i) { local = __dadd_rn(local, S.tp[i]); S.tp[i] = local; }
       totals[b] = local;
     }
     __syncthreads();
@@ -234,10 +240,11 @@ __global__ void k_synth_plan(SynthDev S, int max_blocks) {
 }
 
 // ------------------------------------------------------------------------------------ per-pulse response
+constexpr int kPulseGrid = 296;      // 2 CTAs x 148 SMs; more pulses than that in one drain are handled by the grid-stride loop
 __global__ void __launch_bounds__(256) k_synth_pulse(SynthDev S, const double2* __restrict__ tw) {
   extern __shared__ double2 sm2[];
   SynthState* st = S.state;
-  if ((int)blockIdx.x >= st->plan_count) return;
+  const int plan_count = st->plan_count;
   const int n = S.fft_size, nb = n / 2 + 1, lg = ilog2(n);
   double2* A = sm2;
   double2* Nz = sm2 + n;
@@ -245,7 +252,11 @@ __global__ void __launch_bounds__(256) k_synth_pulse(SynthDev S, const double2* 
   double* apr = spec + nb + 1;
   double* periodic = apr + nb + 1;
   double* scratch = periodic + n;
-  const long long p = st->plan_first + blockIdx.x;
+  // grid-stride over the planned pulses: the grid is sized for a typical chunk (one wave of CTAs), not for the worst case --
+  // 2048 mostly-empty CTAs of 50 KB shared memory each used to queue behind the stage-2 conv CTAs just to exit
+  for (int pq = blockIdx.x; pq < plan_count; pq += gridDim.x) {
+  __syncthreads();
+  const long long p = st->plan_first + pq;
   const int slot = (int)(p % S.cap_pulses);
   const double t = S.p_time[slot];
   const int vuv = S.p_vuv[slot];
@@ -310,10 +321,11 @@ __global__ void __launch_bounds__(256) k_synth_pulse(SynthDev S, const double2* 
   }
   irfft_smem(A, n, lg, tw);
   const double sq = sqrt((double)noise_size);
-  double* resp = S.resp + (size_t)blockIdx.x * n;
+  double* resp = S.resp + (size_t)pq * n;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     double aper = i < n / 2 ? A[i + n / 2].x : A[i - n / 2].x;
     resp[i] = (periodic[i] * sq + aper) / n;
+  }
   }
 }
 
@@ -501,7 +513,7 @@ int synth_add_async(Engine* e, Synth* s, const double* d_f0, int n, const float*
 int synth_drain_async(Engine* e, Synth* s, double* d_out, int max_blocks, cudaStream_t st) {
   SynthDev& D = s->dev;
   k_synth_plan<<<1, 32, 0, st>>>(D, max_blocks);
-  k_synth_pulse<<<D.max_pulses, 256, pulse_smem_bytes(D.fft_size), st>>>(D, e->d_twiddle);
+  k_synth_pulse<<<D.max_pulses < kPulseGrid ? D.max_pulses : kPulseGrid, 256, pulse_smem_bytes(D.fft_size), st>>>(D, e->d_twiddle);
   int total = max_blocks * D.buffer_size + D.carry_len;
   k_synth_ola<<<(total + 255) / 256, 256, 0, st>>>(D, d_out, max_blocks * D.buffer_size, 0);
   k_synth_ola<<<1, 32, 0, st>>>(D, d_out, 0, 1);
