@@ -2,6 +2,7 @@
 
     realtime_voice_conversion.{config, stream[.base_stream|...], segment.*, yukarin_wrapper.*, converter.*, worker.utility}
     yukarin[.acoustic_feature|.wave|.param|.config|.f0_converter],  become_yukarin[.param|.config.sr_config]
+    librosa.{load, output.write_wav} (wav I/O of check.py; only if librosa itself is not installed)
 
 Nothing is copied: each alias module is a thin namespace whose attributes are this package's objects
 (import sites: check.py:7-17, tests/test_*.py of the reference).
@@ -22,7 +23,7 @@ def _module(name: str, **attrs) -> types.ModuleType:
 
 
 def install() -> None:
-    from . import config, converter, feature, models, params, segment, stream, vocoder, voice_changer, worker
+    from . import config, converter, feature, models, params, segment, stream, vocoder, voice_changer, wave_io, worker
 
     rvc = 'realtime_voice_conversion'
     _module(rvc)
@@ -50,6 +51,16 @@ def install() -> None:
     _module(f'{rvc}.worker.utility', Item=worker.Item)
     _module(f'{rvc}.converter')
     _module(f'{rvc}.converter.yukarin_converter', YukarinConverter=converter.YukarinConverter)
+
+    # `librosa` as check.py uses it (check.py:80 load, check.py:112 output.write_wav) -- only when the real package is absent
+    try:
+        import librosa  # noqa: F401
+    except ImportError:
+        def _load(path, sr=None, **_):
+            w = wave_io.load_wave(path, sr)
+            return w.wave, w.sampling_rate
+        _module('librosa', load=_load)
+        _module('librosa.output', write_wav=lambda path, y, sr, **_: wave_io.write_wav(path, y, sr))
 
     _module('yukarin', AcousticConverter=models.AcousticConverter, AcousticFeature=feature.AcousticFeature, Wave=feature.Wave)
     _module('yukarin.acoustic_feature', AcousticFeature=feature.AcousticFeature)

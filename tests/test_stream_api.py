@@ -189,3 +189,63 @@ def test_reference_unit_tests_run_unmodified(name):
     suite = unittest.defaultTestLoader.loadTestsFromModule(mod)
     result = unittest.TextTestRunner(verbosity=0).run(suite)
     assert result.testsRun > 0 and result.wasSuccessful(), result.failures + result.errors
+
+
+REF_CHECK = Path('/root/reference/check.py')
+
+
+@pytest.mark.skipif(not REF_CHECK.exists(), reason='reference checkout not present (GPU box)')
+def test_reference_check_py_runs_unmodified(tmp_path, small_models):
+    """BASELINE config 1: the reference's own check.py (read-only, unmodified) driven through the drop-in aliases -- wav in,
+    EncodeStream / ConvertStream / DecodeStream over 1 s pieces with extras (0, 1, 0), wav out -- with the GPU engine replaced by
+    the oracle-backed stand-in; the written wav must equal the same flow composed by hand from the oracle's functions."""
+    from oracle import nets as onets
+    from oracle import pipeline as opipe
+    from oracle import world as W
+    from realtime_yukarin_b200 import engine as eng_mod
+    from realtime_yukarin_b200 import synthetic, wave_io
+    from realtime_yukarin_b200.models import F0Converter
+    from tests.fake_engine import OracleEngine
+    dropin.install()
+    fake = OracleEngine(small_models['stage1_model_path'], small_models['stage2_model_path'])
+    eng_mod.set_default_engine(fake)
+    try:
+        spec = importlib.util.spec_from_file_location('_reference_check', REF_CHECK)
+        check = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(check)
+        N = 3
+        x = synthetic.synthetic_speech(N + 0.4, stream=23)
+        wave_io.write_wav(tmp_path / 'in.wav', x, 24000)
+        check.check(input_path=tmp_path / 'in.wav', input_time_length=N, output_path=tmp_path / 'out.wav',
+                    **{k: small_models[k] for k in ('input_statistics_path', 'target_statistics_path', 'stage1_model_path',
+                                                    'stage1_config_path', 'stage2_model_path', 'stage2_config_path')})
+        got, sr = wave_io.read_wav(tmp_path / 'out.wav')
+        assert sr == 24000
+
+        # the same flow by hand: per-piece analysis, convert windows of 1 + 1 + 1 s with silent padding outside the file, decode
+        cfg = opipe.PathConfig()
+        p1, p2 = onets.load_npz(small_models['stage1_model_path']), onets.load_npz(small_models['stage2_model_path'])
+        stats = F0Converter(small_models['input_statistics_path'], small_models['target_statistics_path']).stats()
+        pieces = [x[i * 24000:(i + 1) * 24000] for i in range(N)]
+        feats = [opipe.extract_features(w, cfg) for w in pieces]
+        cat = {k: np.concatenate([f[k] for f in feats]) for k in ('f0', 'ap', 'mc', 'voiced')}
+        wave_all = np.concatenate(pieces)
+        T = 200
+        silent_mc = np.zeros((1, cfg.order + 1), np.float32)
+        silent_mc[0, 0] = opipe.SILENT_MC0
+        win = opipe.StreamOracle._window
+        synth = W.RealtimeSynthesizer(24000, 5.0, 1024, 1024)
+        outs = []
+        for i in range(N):
+            first = (i - 1) * T
+            wfeat = dict(f0=win(cat['f0'], first, 3 * T, 0.0), ap=win(cat['ap'], first, 3 * T, 0.0), mc=win(cat['mc'], first, 3 * T, silent_mc),
+                         voiced=win(cat['voiced'], first, 3 * T, False))
+            wwave = win(wave_all, first * cfg.hop, 3 * T * cfg.hop, 0.0)
+            conv = opipe.convert_window(wwave, wfeat, cfg, p1, p2, stats, backend='torch')
+            y = synth.decode(conv['f0'][T:-T].ravel().astype(np.float64), conv['sp'][T:-T], conv['ap'][T:-T])
+            outs.append(np.nan_to_num(y, nan=0.0))
+        ref = np.concatenate(outs).astype(np.float32)
+        assert len(got) == len(ref) and len(ref) > 0
+        assert np.abs(got - ref).max() < 1e-6 * max(1.0, float(np.abs(ref).max()))
+    finally:
+        eng_mod.set_default_engine(None)
