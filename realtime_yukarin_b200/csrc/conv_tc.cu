@@ -178,12 +178,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
     if (threadIdx.x == 0) TL(4);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int row = warp * 32 + lane;                 // accumulator row == TMEM lane == pixel of the tile
-    const int hl = row / p.tile_w, wl = row - hl * p.tile_w;
-    const int my = oy0 + hl, mx = ox0 + wl;            // class-local output coordinate
-    const bool valid = (my < p.Hc) && (mx < p.Wc) && my_chunks > 0;
-    int oy = my, ox = mx;
-    if (p.transposed) { oy = my * p.sh + py; ox = mx * p.sw + px; }
-    const size_t pix = ((size_t)(b * p.Hout + oy) * p.Wout + ox);
+    // (out-of-range pixels of ragged tiles need no masking: both TMA stores below clip at the tensor-map bounds)
 #pragma unroll 1
     for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
       uint32_t r[32];
@@ -199,7 +194,6 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       {
-        const int n = n0 + c0;
         if (p.ws) {
           // split-K partial tile (raw FP32 sums) -> swizzled staging, one [128 pixels][32 channels] block per iteration;
           // stored below by TMA into this split's slice of the workspace; k_splitk_reduce sums the slices

@@ -27,9 +27,9 @@ __global__ void __launch_bounds__(1024) k_synth_add(SynthDev S, const double* __
                                                    const float* __restrict__ sp, const float* __restrict__ ap) {
   SynthState* st = S.state;
   __shared__ double scan_scratch[1024];
-  __shared__ long long sh_first_frame, sh_start, sh_np;
+  __shared__ long long sh_first_frame, sh_start;
   __shared__ int sh_ns, sh_hf, sh_ok;
-  __shared__ double sh_handoff_f0, sh_tp0;
+  __shared__ double sh_handoff_f0;
   __shared__ int wsum[32];
   __shared__ int sh_total;
   const int nb = S.fft_size / 2 + 1;
