@@ -18,7 +18,10 @@
  *   ryk_synth_synthesis2       <- world4py apidefinitions._Synthesis2 (+ the per-sample buffer read-out)        vocoder.py:102-104
  *   ryk_synth_decode           <- RealtimeVocoder.decode as one call (add + drain)                              vocoder.py:89-120
  *   ryk_session_*              <- the encode/convert/decode StreamWrapper chain of one audio stream kept on
- *                                 device                                                                       rvc/worker/*.py, rvc/stream/*.py
+ *                                 device                                                                       rvc/worker/, rvc/stream/ (all modules)
+ *   ryk_world_synthesize       <- pyworld.synthesize (Vocoder.decode, offline)                                  rvc/yukarin_wrapper/vocoder.py:50-62
+ *   ryk_output_gate, ryk_reblock_* <- decode worker: wave_fragment re-blocking + librosa stft/power_to_db gate   rvc/worker/decode_worker.py:38-59
+ *   ryk_resample_poly          <- librosa.load(path, sr=input_rate) resampling                                  check.py:80
  *
  * Conventions: all functions return 0 on success and a negative value on error unless stated otherwise
  * (ryk_last_error() describes the failure); "host" pointers are ordinary process memory, "dev"

@@ -48,3 +48,26 @@ def test_product_package_does_not_import_the_oracle():
     for path in list(pkg.rglob('*.py')) + list(pkg.rglob('*.cu')) + list(pkg.rglob('*.h')) + list(pkg.rglob('*.cuh')):
         text = path.read_text()
         assert 'import oracle' not in text and 'from oracle' not in text and 'world_oracle' not in text, path
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/ryk.h must compile as C99 on its own (no C++ / CUDA / torch types), and every entry point
+    must be callable from C with the declared prototype (compile + link a C translation unit against libryk.so)."""
+    import subprocess
+    src = tmp_path / 'use_ryk.c'
+    src.write_text(
+        '#include "ryk.h"\n'
+        'int main(void) {\n'
+        '  ryk_engine* e = 0; int n = 0; double pw = 0; int keep = 0; float y[4];\n'
+        '  if (ryk_abi_version() != 1) return 1;\n'
+        '  if (ryk_world_synthesize_length(200, 5.0, 24000) != 24000) return 2;\n'
+        '  if (ryk_resample_length(147, 80, 147) != 80) return 3;\n'
+        '  if (ryk_world_num_frames(7200, 24000, 5.0) != 61) return 4;\n'
+        '  (void)e; (void)n; (void)pw; (void)keep; (void)y;\n'
+        '  return 0;\n'
+        '}\n')
+    lib_dir = ROOT / 'realtime_yukarin_b200' / 'csrc'
+    exe = tmp_path / 'use_ryk'
+    subprocess.check_call(['gcc', '-std=c99', '-Wall', '-Werror', '-pedantic', '-I', str(ROOT / 'include'), str(src), '-o', str(exe),
+                           '-L', str(lib_dir), '-lryk', f'-Wl,-rpath,{lib_dir}', '-Wl,-rpath,/usr/local/cuda/lib64'])
+    assert subprocess.call([str(exe)]) == 0          # pure host-side entry points: no GPU needed
