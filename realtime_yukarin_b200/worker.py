@@ -77,7 +77,11 @@ class RealtimePipeline(object):
         assert config.input_rate == config.output_rate, 'the accelerated path runs analysis and synthesis at one rate'
         self.depth = max(1, min(int(depth), 5))
         self._sid = self.engine.session_create(cfg)
-        n_out_cap = (config.in_audio_chunk // config.vocoder_buffer_size + 5) * config.vocoder_buffer_size + 8192
+        # capacity of one step's synthesizer output, as the session sizes it: (decode-window samples // block + 4) blocks
+        rate = round(1000 / float(config.frame_period))
+        hop = round(config.output_rate * float(config.frame_period) / 1000)
+        td = round(config.buffer_time * rate) + 2 * round(config.decode_extra_time * rate)
+        n_out_cap = (td * hop // config.vocoder_buffer_size + 4) * config.vocoder_buffer_size
         self._scratch = numpy.empty(n_out_cap, dtype=numpy.float64)
         self._rid = self.engine.reblock_create(config.out_audio_chunk, n_out_cap, float(config.output_silent_threshold))
         self._inflight: Deque[Tuple[Item, int, int]] = deque()      # (item, session ticket, re-blocker ticket)
