@@ -12,5 +12,7 @@ from .params import AcousticParam, Param  # noqa: F401
 from .segment import (BaseSegmentMethod, FeatureSegmentMethod, FeatureWrapperSegmentMethod, Segment,  # noqa: F401
                       WaveSegmentMethod)
 from .stream import BaseStream, ConvertStream, DecodeStream, EncodeStream, StreamWrapper  # noqa: F401
+from .wave_io import load_wave, save_wave  # noqa: F401
+from .worker import Item, OutputReblocker, RealtimePipeline  # noqa: F401
 
 __version__ = '0.1.0'

@@ -97,6 +97,7 @@ class Engine(object):
         self._check(self.lib.ryk_engine_create(ctypes.c_int(device), ctypes.byref(h)))
         self._h = h
         self._synth_block = {}
+        self._reblock_chunk = {}           # re-blocker id -> out_audio_chunk
 
     # ---- plumbing ----
     def _check(self, rc: int):
@@ -316,7 +317,6 @@ class Engine(object):
         rid = ctypes.c_int()
         self._check(self.lib.ryk_reblock_create(self._h, int(out_audio_chunk), int(max_in), int(n_fft), int(hop), ctypes.c_double(threshold_db),
                                                 ctypes.byref(rid)))
-        self._reblock_chunk = getattr(self, '_reblock_chunk', {})
         self._reblock_chunk[rid.value] = int(out_audio_chunk)
         return rid.value
 
