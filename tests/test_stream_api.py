@@ -249,3 +249,40 @@ def test_reference_check_py_runs_unmodified(tmp_path, small_models):
         assert np.abs(got - ref).max() < 1e-6 * max(1.0, float(np.abs(ref).max()))
     finally:
         eng_mod.set_default_engine(None)
+
+
+REF_CONFIG = Path('/root/reference/config.yaml')
+
+
+@pytest.mark.skipif(not REF_CONFIG.exists(), reason='reference checkout not present (GPU box)')
+def test_config_reads_the_reference_yaml():
+    """Config.from_yaml (config.py:44-71) on the reference's own config.yaml: same fields, enum and derived chunk sizes."""
+    from realtime_yukarin_b200.config import Config, VocodeMode
+    c = Config.from_yaml(REF_CONFIG)
+    assert c.input_rate == 24000 and c.output_rate == 24000 and c.frame_period == 5 and c.buffer_time == 1
+    assert c.extract_f0_mode is VocodeMode.WORLD and c.vocoder_buffer_size == 1024
+    assert (c.encode_extra_time, c.convert_extra_time, c.decode_extra_time) == (0.0, 0.5, 0.0)
+    assert c.input_silent_threshold == 80 and c.output_silent_threshold == 80
+    assert c.in_audio_chunk == 24000 and c.out_audio_chunk == 24000          # config.py:37-43
+    assert isinstance(c.stage1_model_path, Path) and c.stage2_config_path.name == 'config.json'
+
+
+def test_make_yukarin_converter_loads_both_stages(small_models):
+    """YukarinConverter.make_yukarin_converter (converter/yukarin_converter.py:22-60): statistics, stage-1 and stage-2 models land
+    in the engine (here the oracle-backed stand-in) and the converter exposes the objects VoiceChanger needs."""
+    from realtime_yukarin_b200 import engine as eng_mod
+    from realtime_yukarin_b200.converter import YukarinConverter
+    from realtime_yukarin_b200.voice_changer import VoiceChanger
+    from tests.fake_engine import OracleEngine
+    fake = OracleEngine(small_models['stage1_model_path'], small_models['stage2_model_path'])
+    eng_mod.set_default_engine(fake)
+    try:
+        conv = YukarinConverter.make_yukarin_converter(**{k: small_models[k] for k in (
+            'input_statistics_path', 'target_statistics_path', 'stage1_model_path', 'stage1_config_path', 'stage2_model_path',
+            'stage2_config_path')})
+        assert conv.acoustic_converter.config.dataset.acoustic_param.sampling_rate == 24000
+        assert fake.stats is not None and len(fake.stats) == 4           # log-f0 statistics reached the engine
+        vc = VoiceChanger(super_resolution=conv.super_resolution, acoustic_converter=conv.acoustic_converter, threshold=80)
+        assert vc.threshold == 80
+    finally:
+        eng_mod.set_default_engine(None)
