@@ -17,7 +17,7 @@ from realtime_yukarin_b200.voice_changer import VoiceChanger
 from tests.fake_engine import OracleEngine
 
 
-@pytest.mark.parametrize('T,extra', [(0.3, (0.0, 0.5, 0.0)), (0.1, (0.1, 0.2, 0.0))])
+@pytest.mark.parametrize('T,extra', [(0.3, (0.0, 0.5, 0.0)), (0.1, (0.1, 0.2, 0.0)), (0.3, (0.1, 0.5, 0.1)), (0.2, (0.0, 0.0, 0.0)), (0.1, (0.0, 0.5, 0.0))])
 def test_stream_classes_reproduce_oracle_stream(small_models, T, extra):
     paths = small_models
     fake = OracleEngine(paths['stage1_model_path'], paths['stage2_model_path'])

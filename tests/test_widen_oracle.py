@@ -175,3 +175,89 @@ def test_realtime_pipeline_audio_loop_on_cpu(small_models):
         want = np.zeros(cfg.out_audio_chunk, np.float32) if e is None else (e * cfg.output_scale)[:cfg.out_audio_chunk].astype(np.float32)
         assert np.array_equal(outs[k], want), k
     pipe.close()
+
+
+def _numpy_offline_synthesis(f0, sp, ap, fs, frame_period_ms, fft):
+    """Second, independent writing of WORLD's offline Synthesis() in vectorised numpy (numpy.fft, numpy.interp, cumulative sums in the
+    oracle's blocked order), used only to cross-check oracle/world_oracle.c: wo_synthesize."""
+    fp = frame_period_ms / 1000.0
+    n = len(f0)
+    ny = int(n * frame_period_ms * fs / 1000.0)
+    lowest = fs / fft + 1.0
+    cf = np.where(f0 < lowest, 0.0, f0)
+    cv = (cf != 0).astype(float)
+    ct = np.arange(n + 1) * fp
+    cf = np.append(cf, cf[-1] * 2 - cf[-2])
+    cv = np.append(cv, cv[-1] * 2 - cv[-2])
+    t = np.arange(ny) / fs
+    vuv = (np.interp(t, ct, cv) > 0.5).astype(float)
+    f0i = np.where(vuv == 0, 500.0, np.interp(t, ct, cf))
+    inc = 2 * np.pi * f0i / fs
+    tp = np.empty(ny)
+    base = 0.0
+    for b0 in range(0, ny, 256):                        # the oracle's fixed blocked summation order
+        loc = np.cumsum(inc[b0:b0 + 256])
+        tp[b0:b0 + 256] = base + loc
+        base = base + loc[-1]
+    wp = np.fmod(tp, 2 * np.pi)
+    idx = np.nonzero(np.abs(np.diff(wp)) > np.pi)[0]
+    y1, y2 = wp[idx] - 2 * np.pi, wp[idx + 1]
+    shift = (-y1 / (y2 - y1)) / fs
+    half = fft // 2
+    i = np.arange(half)
+    dcr = 0.5 - 0.5 * np.cos(2 * np.pi * (i + 1.0) / (1.0 + fft))
+    dcr = np.concatenate([dcr, dcr[::-1]])
+    dcr /= dcr.sum()
+    k = np.arange(half + 1)
+
+    def min_phase(log_half):                            # folded-cepstrum minimum phase, as WORLD's GetMinimumPhaseSpectrum
+        full = np.concatenate([log_half, log_half[-2:0:-1]])
+        cep = np.fft.fft(full).real                     # WORLD uses a forward FFT and divides by n at the end
+        cep[1:half] *= 2.0
+        cep[half + 1:] = 0.0
+        spec = np.fft.fft(cep)[:half + 1] / fft
+        return np.exp(spec.real) * np.exp(1j * spec.imag)
+
+    y = np.zeros(ny)
+    for p, q in enumerate(idx):
+        nxt = idx[min(p + 1, len(idx) - 1)]
+        noise_size = min(int(nxt - q), fft)
+        tt = t[q]
+        fl, ce = min(n - 1, int(np.floor(tt / fp))), min(n - 1, int(np.ceil(tt / fp)))
+        w = tt / fp - fl
+        s = np.abs(sp[fl].astype(float)) if fl == ce else (1 - w) * np.abs(sp[fl].astype(float)) + w * np.abs(sp[ce].astype(float))
+        clip = lambda a: np.clip(a.astype(float), 0.001, 0.999999999999)
+        a = clip(ap[fl]) ** 2 if fl == ce else ((1 - w) * clip(ap[fl]) + w * clip(ap[ce])) ** 2
+        if vuv[q] == 0 or a[0] > 0.999:
+            per = np.zeros(fft)
+        else:
+            m = min_phase(np.log(s * (1 - a) + 1e-12) / 2)
+            coef = 2 * np.pi * shift[p] * fs / fft
+            re2 = np.cos(coef * k)
+            m = m * (re2 - 1j * np.sqrt(1 - re2 * re2))
+            per = np.fft.fftshift(np.fft.irfft(m, fft) * fft)
+            dc = per[half:].sum()
+            per = np.concatenate([-dc * dcr[:half], per[half:] - dc * dcr[half:]])
+        nz = np.zeros(fft)
+        if noise_size > 0:
+            r = W.randn_stream(int(q), noise_size)
+            nz[:noise_size] = r - r.mean()
+        m = min_phase(np.log(s * a) / 2 if vuv[q] != 0 else np.log(s) / 2)
+        aper = np.fft.fftshift(np.fft.irfft(m * np.fft.rfft(nz), fft) * fft)
+        resp = (per * np.sqrt(noise_size) + aper) / fft
+        off = int(q) - half + 1
+        lo, hi = max(0, -off), min(fft, ny - off)
+        y[off + lo:off + hi] += resp[lo:hi]
+    return y, idx, shift
+
+
+def test_offline_synthesis_oracle_agrees_with_an_independent_numpy_writing():
+    x = synthetic.synthetic_speech(0.5, stream=3)
+    f = opipe.extract_features(x, CFG)
+    f0 = f['f0'].ravel().astype(np.float64)
+    y, idx, shift, _ = W.synthesize(f0, f['sp'], f['ap'], 24000, 5.0, return_pulses=True)
+    y2, idx2, shift2 = _numpy_offline_synthesis(f0, f['sp'], f['ap'], 24000, 5.0, 1024)
+    assert np.array_equal(idx, idx2)
+    assert np.allclose(shift, shift2, rtol=0, atol=1e-15)
+    assert len(y) == len(y2)
+    assert np.abs(y - y2).max() < 1e-9 * max(1.0, np.abs(y).max())
