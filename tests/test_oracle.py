@@ -236,3 +236,18 @@ def test_golden_fixtures_widen():
     rb = opipe.OutputReblockOracle(7200, 30.0)
     statuses = [rb.push(y[a:a + 1024] if a // 1024 % 5 else 1e-6 * y[a:a + 1024])[0] for a in range(0, len(y), 1024)]
     assert statuses == z['reblock_status'].tolist()
+
+
+def test_cheaptrick_and_d4c_agree_with_independent_numpy_writings():
+    """oracle/world_oracle.c (C, scalar loops) vs tests/independent_world.py (numpy, written separately from the published
+    algorithm): spectral envelope within 1e-8 in the log domain (running sums over 1e-7-level bins), aperiodicity within 1e-10, on voiced and unvoiced frames."""
+    from tests import independent_world as iw
+    x = synthetic.synthetic_speech(0.6, stream=5).astype(np.float64)
+    f0, t = W.dio(x, FS)[:2]
+    f0 = W.stonemask(x, FS, t, f0)
+    assert (f0 > 0).sum() > 20 and (f0 == 0).sum() > 0
+    sp = W.cheaptrick(x, FS, t, f0)
+    assert np.abs(np.log(iw.cheaptrick_np(x, FS, t, f0)) - np.log(sp)).max() < 1e-8
+    ap = W.d4c(x, FS, t, f0)
+    ap = ap[0] if isinstance(ap, tuple) else ap
+    assert np.abs(iw.d4c_np(x, FS, t, f0) - ap).max() < 1e-10
