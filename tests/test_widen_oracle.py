@@ -261,3 +261,40 @@ def test_offline_synthesis_oracle_agrees_with_an_independent_numpy_writing():
     assert np.allclose(shift, shift2, rtol=0, atol=1e-15)
     assert len(y) == len(y2)
     assert np.abs(y - y2).max() < 1e-9 * max(1.0, np.abs(y).max())
+
+
+def test_run_module_wav_mode_matches_the_audio_loop(tmp_path, small_models):
+    """realtime_yukarin_b200.run (the reference's run.py:22-199 with wav files instead of PyAudio devices): config.yaml -> models ->
+    RealtimePipeline -> audio loop; the written wav is the concatenation of what process() returns chunk by chunk."""
+    import yaml
+    from realtime_yukarin_b200 import run as run_mod
+    from realtime_yukarin_b200 import wave_io
+    from realtime_yukarin_b200.config import Config
+    from realtime_yukarin_b200.converter import YukarinConverter
+    from realtime_yukarin_b200.worker import RealtimePipeline
+    fake = OracleEngine(small_models['stage1_model_path'], small_models['stage2_model_path'])
+    eng_mod.set_default_engine(fake)
+    try:
+        cfg = dict(input_device_name=None, output_device_name=None, input_rate=24000, output_rate=24000, frame_period=5, buffer_time=0.3,
+                   extract_f0_mode='world', vocoder_buffer_size=1024, input_scale=0.5, output_scale=2.0, input_silent_threshold=60,
+                   output_silent_threshold=80, encode_extra_time=0.0, convert_extra_time=0.5, decode_extra_time=0.0,
+                   **{k: str(small_models[k]) for k in ('input_statistics_path', 'target_statistics_path', 'stage1_model_path',
+                                                        'stage1_config_path', 'stage2_model_path', 'stage2_config_path')})
+        (tmp_path / 'config.yaml').write_text(yaml.safe_dump(cfg))
+        x = synthetic.synthetic_speech(1.6, stream=29)
+        wave_io.write_wav(tmp_path / 'in.wav', x, 24000)
+        n = run_mod.run(tmp_path / 'config.yaml', wav_in=tmp_path / 'in.wav', wav_out=tmp_path / 'out.wav', engine=fake, depth=2)
+        assert n == len(x) // 7200
+        got, sr = wave_io.read_wav(tmp_path / 'out.wav')
+        assert sr == 24000 and len(got) == n * 7200
+        # the same loop by hand
+        config = Config.from_yaml(tmp_path / 'config.yaml')
+        conv = YukarinConverter.make_yukarin_converter(**{k: small_models[k] for k in (
+            'input_statistics_path', 'target_statistics_path', 'stage1_model_path', 'stage1_config_path', 'stage2_model_path',
+            'stage2_config_path')})
+        pipe = RealtimePipeline(config, acoustic_param=conv.acoustic_converter.config.dataset.acoustic_param, engine=fake, depth=2)
+        ref = np.concatenate([pipe.process(x[k * 7200:(k + 1) * 7200]) for k in range(n)])
+        pipe.close()
+        assert np.array_equal(got, ref) and np.abs(got).max() > 0
+    finally:
+        eng_mod.set_default_engine(None)
