@@ -286,3 +286,73 @@ def test_make_yukarin_converter_loads_both_stages(small_models):
         assert vc.threshold == 80
     finally:
         eng_mod.set_default_engine(None)
+
+
+REF_PKG = Path('/root/reference/realtime_voice_conversion')
+
+
+def _load_reference_stream_classes():
+    """The reference's own (pure-Python) segment / base_stream modules, loaded by path under private names."""
+    saved = {k: sys.modules.get(k) for k in ('realtime_voice_conversion', 'realtime_voice_conversion.segment',
+                                             'realtime_voice_conversion.segment.segment')}
+    try:
+        import types
+        pkg = types.ModuleType('realtime_voice_conversion'); pkg.__path__ = []
+        sub = types.ModuleType('realtime_voice_conversion.segment'); sub.__path__ = []
+        sys.modules['realtime_voice_conversion'], sys.modules['realtime_voice_conversion.segment'] = pkg, sub
+        spec = importlib.util.spec_from_file_location('realtime_voice_conversion.segment.segment', REF_PKG / 'segment' / 'segment.py')
+        seg = importlib.util.module_from_spec(spec)
+        sys.modules['realtime_voice_conversion.segment.segment'] = seg
+        spec.loader.exec_module(seg)
+        spec = importlib.util.spec_from_file_location('_ref_base_stream', REF_PKG / 'stream' / 'base_stream.py')
+        bs = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(bs)
+        return seg, bs
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+@pytest.mark.skipif(not REF_PKG.exists(), reason='reference checkout not present (GPU box)')
+def test_fetch_and_remove_differential_against_the_reference_classes():
+    """Rows a1-a3 against the REAL reference code: random segment layouts (gaps, overlaps, touching segments) and random fetch
+    windows / remove times through the reference's BaseStream + a wave segment method, and through this package's -- the fetched
+    arrays must be identical element for element."""
+    from hypothesis import given, settings, strategies as st
+    seg_mod, bs_mod = _load_reference_stream_classes()
+
+    class RefWave(seg_mod.BaseSegmentMethod):          # wave_segment.py:8-19 restated on the reference's own base class
+        def length(self, data): return len(data)
+        def pad(self, width): return np.zeros(width, dtype=np.float32)
+        def pick(self, data, first, last): return data[first:last]
+        def concat(self, datas): return np.concatenate(list(datas))
+
+    grid = st.integers(min_value=0, max_value=400).map(lambda k: k * 0.005)
+    segs = st.lists(st.tuples(grid, st.integers(min_value=1, max_value=300)), min_size=0, max_size=6)
+    window = st.tuples(st.integers(-50, 400).map(lambda k: k * 0.005), st.integers(1, 200).map(lambda k: k * 0.005),
+                       st.integers(0, 100).map(lambda k: k * 0.005))
+
+    @settings(max_examples=300, deadline=None)
+    @given(rate=st.sampled_from([200, 1000, 24000]), layout=segs, win=window, rm=st.one_of(st.none(), grid))
+    def check(rate, layout, win, rm):
+        ref = bs_mod.BaseStream(in_segment_method=RefWave(rate), out_segment_method=RefWave(rate))
+        ours = BaseStream(in_segment_method=WaveSegmentMethod(sampling_rate=rate), out_segment_method=WaveSegmentMethod(sampling_rate=rate))
+        base = 1.0
+        for start, n_frames in sorted(layout):
+            n = round(n_frames * 0.005 * rate)
+            data = (base + np.arange(n)).astype(np.float32)
+            base += 100000.0
+            ref.add(start_time=start, data=data)
+            ours.add(start_time=start, data=data)
+        if rm is not None:
+            ref.remove(end_time=rm)
+            ours.remove(end_time=rm)
+            assert [s.start_time for s in ref.stream] == [s.start_time for s in ours.stream]
+        a = ref.fetch(start_time=win[0], time_length=win[1], extra_time=win[2])
+        b = ours.fetch(start_time=win[0], time_length=win[1], extra_time=win[2])
+        assert len(a) == len(b) and np.array_equal(a, b)
+
+    check()
