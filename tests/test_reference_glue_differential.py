@@ -96,3 +96,135 @@ def test_reference_streams_and_voice_changer_over_our_replacements(small_models,
                 assert u.shape == v.shape and np.array_equal(u, v, equal_nan=True), k
     finally:
         eng_mod.set_default_engine(None)
+
+
+def _test_librosa_module():
+    """`librosa.stft` / `librosa.core.power_to_db` for the reference's decode worker (decode_worker.py:56), written here in numpy
+    (librosa 0.6/0.7 defaults: n_fft 2048, hop 512, periodic Hann, reflect-centred; ref 1, amin 1e-10, top_db 80).  Test harness only."""
+    import types
+    import scipy.signal as ss
+
+    def stft(y, n_fft=2048, hop_length=None):
+        hop = hop_length or n_fft // 4
+        yp = np.pad(np.asarray(y, np.float64), n_fft // 2, mode='reflect')
+        win = ss.get_window('hann', n_fft, fftbins=True)
+        frames = 1 + len(y) // hop
+        return np.stack([np.fft.rfft(yp[f * hop:f * hop + n_fft] * win) for f in range(frames)], 1)
+
+    def power_to_db(S, ref=1.0, amin=1e-10, top_db=80.0):
+        db = 10.0 * np.log10(np.maximum(amin, S)) - 10.0 * np.log10(np.maximum(amin, ref))
+        return np.maximum(db, db.max() - top_db)
+
+    lib = types.ModuleType('librosa'); lib.__path__ = []
+    core = types.ModuleType('librosa.core')
+    lib.stft, core.power_to_db, lib.core = stft, power_to_db, core
+    return lib, core
+
+
+def test_reference_workers_over_our_replacements_match_realtime_pipeline(small_models, tmp_path, monkeypatch):
+    """SURVEY 8(f) ranks 1 / 2 against the REAL worker code: the reference's encode_worker / convert_worker / decode_worker
+    (worker/*.py, imported from the checkout, each in a thread with queue.Queue standing in for multiprocessing.Queue) over this
+    package's replacements, versus worker.RealtimePipeline on the same engine: the same Items in the same order -- chunk played,
+    or None (not enough samples yet / gated as silent)."""
+    import queue
+    import threading
+    import types
+    from realtime_yukarin_b200 import engine as eng_mod
+    from realtime_yukarin_b200 import synthetic
+    from realtime_yukarin_b200.config import Config, VocodeMode
+    from realtime_yukarin_b200.models import AcousticConverter, F0Converter, SuperResolution
+    from realtime_yukarin_b200.params import create_from_json, create_sr_from_json
+    from realtime_yukarin_b200.vocoder import RealtimeVocoder
+    from realtime_yukarin_b200.worker import Item, RealtimePipeline
+    from tests.fake_engine import OracleEngine
+    monkeypatch.chdir(tmp_path)                      # the reference's init_logger writes ./log.txt
+    fake = OracleEngine(small_models['stage1_model_path'], small_models['stage2_model_path'])
+    eng_mod.set_default_engine(fake)
+    T, extra = 0.3, (0.0, 0.5, 0.0)
+    x = synthetic.synthetic_speech(3.0, stream=37)
+    x[int(1.2 * 24000):int(2.1 * 24000)] *= 1e-4
+    n = round(T * 24000)
+    K = len(x) // n
+    saved_mods = {k: sys.modules.get(k) for k in ('librosa', 'librosa.core', 'chainer')}
+    try:
+        f0c = F0Converter(small_models['input_statistics_path'], small_models['target_statistics_path'])
+        ac = AcousticConverter(create_from_json(small_models['stage1_config_path']), small_models['stage1_model_path'], f0_converter=f0c, engine=fake)
+        sr = SuperResolution(create_sr_from_json(small_models['stage2_config_path']), small_models['stage2_model_path'], engine=fake)
+        acp = create_from_json(small_models['stage1_config_path']).dataset.acoustic_param
+        def make_cfg(out_thr):
+            return Config(input_device_name=None, output_device_name=None, input_rate=24000, output_rate=24000, frame_period=5.0, buffer_time=T,
+                          extract_f0_mode=VocodeMode.WORLD, vocoder_buffer_size=1024, input_scale=1.0, output_scale=1.0,
+                          input_silent_threshold=60.0, output_silent_threshold=out_thr, encode_extra_time=extra[0],
+                          convert_extra_time=extra[1], decode_extra_time=extra[2],
+                          **{k: small_models[k] for k in ('input_statistics_path', 'target_statistics_path', 'stage1_model_path',
+                                                          'stage1_config_path', 'stage2_model_path', 'stage2_config_path')})
+
+        # a threshold that gates some chunks and keeps others: powers of the ungated chunks, split at their widest gap
+        lib_probe, core_probe = _test_librosa_module()
+        probe = RealtimePipeline(make_cfg(1e9), acoustic_param=acp, engine=fake, depth=1)
+        powers = []
+        for k in range(K):
+            probe.put(Item(item=x[k * n:(k + 1) * n].copy(), index=k))
+            it = probe.get()
+            if it.item is not None:
+                powers.append(float(core_probe.power_to_db(np.abs(lib_probe.stft(it.item)) ** 2).mean()))
+        probe.close()
+        ps = np.sort(np.asarray(powers))
+        gi = int(np.argmax(np.diff(ps)))
+        assert ps[gi + 1] - ps[gi] > 1e-3
+        cfg = make_cfg(-float(0.5 * (ps[gi] + ps[gi + 1])))
+        with _RealReferencePackage() as ref:
+            lib, core = _test_librosa_module()
+            sys.modules['librosa'], sys.modules['librosa.core'] = lib, core
+            chainer = types.ModuleType('chainer')
+            chainer.global_config = types.SimpleNamespace(enable_backprop=True, train=True)
+            sys.modules['chainer'] = chainer
+            workers = ref.load('worker')
+            assert Path(workers.__file__).is_relative_to(REF_ROOT)
+            q_in, q_feat, q_conv, q_out = queue.Queue(), queue.Queue(), queue.Queue(), queue.Queue()
+            locks = [threading.Lock() for _ in range(3)]
+            for lk in locks:
+                lk.acquire()
+            voc = RealtimeVocoder(acoustic_param=acp, out_sampling_rate=24000, extract_f0_mode=VocodeMode.WORLD)
+            threads = [
+                threading.Thread(target=workers.encode_worker, daemon=True, kwargs=dict(
+                    realtime_vocoder=voc, time_length=T, extra_time=extra[0], queue_input=q_in, queue_output=q_feat, acquired_lock=locks[0])),
+                threading.Thread(target=workers.convert_worker, daemon=True, kwargs=dict(
+                    acoustic_converter=ac, super_resolution=sr, time_length=T, extra_time=extra[1], input_silent_threshold=cfg.input_silent_threshold,
+                    queue_input=q_feat, queue_output=q_conv, acquired_lock=locks[1])),
+                threading.Thread(target=workers.decode_worker, daemon=True, kwargs=dict(
+                    realtime_vocoder=voc, time_length=T, extra_time=extra[2], vocoder_buffer_size=1024, out_audio_chunk=cfg.out_audio_chunk,
+                    output_silent_threshold=cfg.output_silent_threshold, queue_input=q_conv, queue_output=q_out, acquired_lock=locks[2])),
+            ]
+            for th in threads:
+                th.start()
+            for lk in locks:                             # run.py:95-96: wait until every worker is ready
+                assert lk.acquire(timeout=30)
+            ref_items = []
+            for k in range(K):
+                q_in.put(workers.utility.Item(item=x[k * n:(k + 1) * n].copy(), index=k) if hasattr(workers, 'utility')
+                         else ref.load('worker.utility').Item(item=x[k * n:(k + 1) * n].copy(), index=k))
+                ref_items.append(q_out.get(timeout=120))
+            assert chainer.global_config.train is False and chainer.global_config.enable_backprop is False      # convert_worker.py:33-34 ran
+        pipe = RealtimePipeline(cfg, acoustic_param=acp, engine=fake, depth=1)
+        ours = []
+        for k in range(K):
+            pipe.put(Item(item=x[k * n:(k + 1) * n].copy(), index=k))
+            ours.append(pipe.get())
+        pipe.close()
+        assert [it.index for it in ref_items] == [it.index for it in ours] == list(range(K))
+        played = silent = 0
+        for a, b in zip(ref_items, ours):
+            assert (a.item is None) == (b.item is None), a.index
+            if a.item is not None:
+                played += 1
+                assert len(a.item) == len(b.item) == cfg.out_audio_chunk
+                assert np.abs(np.asarray(a.item) - b.item).max() < 1e-9
+        assert 0 < played < len(powers)                   # the gate kept some chunks and dropped others, identically on both sides
+    finally:
+        for k, v in saved_mods.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+        eng_mod.set_default_engine(None)
