@@ -228,3 +228,44 @@ def test_reference_workers_over_our_replacements_match_realtime_pipeline(small_m
             else:
                 sys.modules[k] = v
         eng_mod.set_default_engine(None)
+
+
+def test_reference_converter_and_config_modules_over_our_replacements(small_models):
+    """The reference's real converter/yukarin_converter.py and config.py: model loading through the reference's own call site
+    (kwargs gpu=0, out_sampling_rate=24000, F0Converter(input_statistics=...)) lands in this package's classes, and its Config reads
+    the same values from config.yaml as ours."""
+    from realtime_yukarin_b200 import engine as eng_mod
+    from realtime_yukarin_b200 import config as our_config
+    from realtime_yukarin_b200.models import AcousticConverter, SuperResolution
+    from tests.fake_engine import OracleEngine
+    fake = OracleEngine(small_models['stage1_model_path'], small_models['stage2_model_path'])
+    eng_mod.set_default_engine(fake)
+    try:
+        saved_mods = {k: sys.modules.get(k) for k in ('librosa', 'librosa.core', 'chainer')}
+        with _RealReferencePackage() as ref:
+            import types
+            lib, core = _test_librosa_module()             # worker/__init__ (pulled in by yukarin_converter.py:10) imports librosa and chainer
+            sys.modules['librosa'], sys.modules['librosa.core'] = lib, core
+            chainer = types.ModuleType('chainer'); chainer.global_config = types.SimpleNamespace()
+            sys.modules['chainer'] = chainer
+            yc = ref.load('converter.yukarin_converter')
+            assert Path(yc.__file__).is_relative_to(REF_ROOT)
+            conv = yc.YukarinConverter.make_yukarin_converter(**{k: small_models[k] for k in (
+                'input_statistics_path', 'target_statistics_path', 'stage1_model_path', 'stage1_config_path', 'stage2_model_path',
+                'stage2_config_path')})
+            assert isinstance(conv.acoustic_converter, AcousticConverter) and isinstance(conv.super_resolution, SuperResolution)
+            assert fake.stats is not None
+            rc = ref.load('config')
+            a = rc.Config.from_yaml(REF_ROOT / 'config.yaml')
+        b = our_config.Config.from_yaml(REF_ROOT / 'config.yaml')
+        for name in a._fields:
+            va, vb = getattr(a, name), getattr(b, name)
+            assert (va.value if hasattr(va, 'value') else va) == (vb.value if hasattr(vb, 'value') else vb), name
+        assert a.in_audio_chunk == b.in_audio_chunk and a.out_audio_chunk == b.out_audio_chunk
+    finally:
+        for k, v in locals().get('saved_mods', {}).items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+        eng_mod.set_default_engine(None)
