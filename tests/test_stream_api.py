@@ -356,3 +356,38 @@ def test_fetch_and_remove_differential_against_the_reference_classes():
         assert len(a) == len(b) and np.array_equal(a, b)
 
     check()
+
+
+REF_ALL_STREAM = Path('/root/reference/tests/test_all_stream.py')
+
+
+@pytest.mark.skipif(not REF_ALL_STREAM.exists(), reason='reference checkout not present (GPU box)')
+def test_reference_integration_test_runs_unmodified(tmp_path, small_models, monkeypatch):
+    """The reference's own integration test module tests/test_all_stream.py (model paths from the environment, its audioA.wav fixture
+    loaded through `librosa.load(..., sr=24000)`, encode / convert / decode streams with extras (0, 1, 0), wav written at the end),
+    read-only and unmodified, against this package with the oracle-backed engine: every test in it must pass."""
+    from realtime_yukarin_b200 import engine as eng_mod
+    from tests.fake_engine import OracleEngine
+    work = tmp_path / 'work'
+    (work / 'tests' / 'data').mkdir(parents=True)
+    (work / 'tests' / 'data' / 'audioA.wav').symlink_to('/root/reference/tests/data/audioA.wav')      # read in place, never copied
+    monkeypatch.chdir(work)                                   # the module reads tests/data/... and writes ../test_convert_extra05.wav
+    for env, key in (('INPUT_STATISTICS', 'input_statistics_path'), ('TARGET_STATISTICS', 'target_statistics_path'),
+                     ('ACOUSTIC_CONVERT_MODEL', 'stage1_model_path'), ('ACOUSTIC_CONVERT_CONFIG', 'stage1_config_path'),
+                     ('SUPER_RESOLUTION_MODEL', 'stage2_model_path'), ('SUPER_RESOLUTION_CONFIG', 'stage2_config_path')):
+        monkeypatch.setenv(env, str(small_models[key]))
+    dropin.install()
+    fake = OracleEngine(small_models['stage1_model_path'], small_models['stage2_model_path'])
+    eng_mod.set_default_engine(fake)
+    try:
+        spec = importlib.util.spec_from_file_location('_reference_test_all_stream', REF_ALL_STREAM)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        suite = unittest.defaultTestLoader.loadTestsFromModule(mod)
+        result = unittest.TextTestRunner(verbosity=0).run(suite)
+        assert result.testsRun >= 6 and result.wasSuccessful(), result.failures + result.errors
+        from realtime_yukarin_b200 import wave_io
+        y, sr = wave_io.read_wav(tmp_path / 'test_convert_extra05.wav')
+        assert sr == 24000 and len(y) > 24000 and np.isfinite(y).all() and np.abs(y).max() > 0
+    finally:
+        eng_mod.set_default_engine(None)
