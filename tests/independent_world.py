@@ -1,7 +1,9 @@
-"""Independent second writings (vectorised numpy, numpy.fft) of WORLD's CheapTrick and D4C from the published algorithm
-(M. Morise, cheaptrick.cpp / d4c.cpp / common.cpp, v0.2.x) -- TEST INFRASTRUCTURE.  They exist only to cross-check
+"""Independent second writings (vectorised numpy, numpy.fft) of WORLD's DIO, StoneMask, CheapTrick and D4C from the published
+algorithm (M. Morise, dio.cpp / stonemask.cpp / cheaptrick.cpp / d4c.cpp / common.cpp, v0.2.x) -- TEST INFRASTRUCTURE.  They exist only to cross-check
 oracle/world_oracle.c: two writings made independently of each other must agree to rounding (tests/test_oracle.py).
-The DECIDE points are the oracle's (no randn dither, `+ eps` instead of `+ |randn| * eps`)."""
+The DECIDE points are the oracle's (no randn dither, `+ eps` instead of `+ |randn| * eps`).
+History: DIO, CheapTrick and D4C agreed on the first comparison; StoneMask's second writing first used the wrong harmonic weighting
+(sum a_k f_k / k / sum a_k instead of sum a_k f_k / sum a_k k) -- the C oracle had WORLD's form."""
 import numpy as np
 
 from oracle import world as W
@@ -140,5 +142,131 @@ def d4c_np(x, fs, t, f0, fft_out=1024, threshold=0.85):
         axis = np.append(np.arange(nap + 1) * 3000.0, fs / 2.0)
         fx = np.arange(nb_out) * fs / fft_out
         out[i] = 10 ** (W.interp1(axis, coarse, fx) / 20.0)
+    return out
+
+
+
+# ------------------------------------------------------------------------------------ DIO + StoneMask
+def interp1(x, y, xi):
+    x = np.asarray(x); y = np.asarray(y)
+    k = np.clip(np.searchsorted(x, xi, side='right'), 1, len(x) - 1)
+    s = (xi - x[k - 1]) / (x[k] - x[k - 1])
+    return y[k - 1] + s * (y[k] - y[k - 1])
+
+def nuttall(n):
+    t = np.arange(n) / (n - 1.0)
+    return 0.355768 - 0.487396 * np.cos(2 * np.pi * t) + 0.144232 * np.cos(4 * np.pi * t) - 0.012604 * np.cos(6 * np.pi * t)
+
+def zc_engine(x, fs):
+    n = len(x)
+    neg = np.nonzero((x[:-1] > 0.0) & (x[1:] <= 0.0))[0] + 1
+    if len(neg) < 2:
+        return np.zeros(0), np.zeros(0)
+    fine = neg - x[neg - 1] / (x[neg] - x[neg - 1])
+    return (fine[:-1] + fine[1:]) / 2.0 / fs, fs / (fine[1:] - fine[:-1])
+
+def dio_np(x, fs, frame_period=5.0, f0_floor=71.0, f0_ceil=800.0, channels=2.0, allowed_range=0.1):
+    n = len(x)
+    nbands = 1 + int(np.log(f0_ceil / f0_floor) / np.log(2.0) * channels)
+    bounds = f0_floor * 2.0 ** ((np.arange(nbands) + 1) / channels)
+    y_length = 1 + n
+    fft = 2 ** (int(np.log2(y_length + mround(fs / 50.0) * 2 + 1 + 4 * int(1.0 + fs / bounds[0] / 2.0))) + 1)
+    y = np.zeros(fft); y[:n] = x
+    y[:y_length] -= y[:y_length].sum() / y_length
+    Y = np.fft.fft(y)
+    N = mround(fs / 50.0) * 2 + 1
+    lc = np.zeros(fft)
+    lc[:N] = 0.5 - 0.5 * np.cos(np.arange(1, N + 1) * 2 * np.pi / (N + 1))
+    lc[:N] = -lc[:N] / lc[:N].sum()
+    h = (N - 1) // 2
+    f2 = np.zeros(fft)
+    f2[fft - h:] = lc[:h]
+    f2[:N - h] = lc[h:N]
+    f2[0] += 1.0
+    Y = Y * np.fft.fft(f2)
+    f0_length = int(1000.0 * n / fs / frame_period) + 1
+    t = np.arange(f0_length) * frame_period / 1000.0
+    cands = np.zeros((nbands, f0_length)); scores = np.zeros((nbands, f0_length))
+    for b in range(nbands):
+        hl = mround(fs / bounds[b] / 2.0)
+        lp = np.zeros(fft); lp[:hl * 4] = nuttall(hl * 4)
+        filt = np.fft.ifft(Y * np.fft.fft(lp)).real * fft          # WORLD's c2r inverse is unnormalised (scale cancels in zero crossings)
+        sig = filt[hl * 2:hl * 2 + y_length].copy()
+        ev = []
+        ev.append(zc_engine(sig, fs)); ev.append(zc_engine(-sig, fs))
+        d = sig[:-1] - sig[1:]
+        ev.append(zc_engine(d, fs)); ev.append(zc_engine(-d, fs))
+        if any(len(e[0]) - 2 <= 0 for e in ev):
+            scores[b] = 100000.0; continue
+        sets = np.stack([interp1(loc, itv, t) for loc, itv in ev])
+        c = sets.mean(0)
+        s = np.sqrt(((sets - c) ** 2).sum(0) / 3.0)
+        bad = (c > bounds[b]) | (c < bounds[b] / 2.0) | (c > f0_ceil) | (c < f0_floor)
+        c[bad] = 0.0; s[bad] = 100000.0
+        cands[b] = c; scores[b] = s / (c + 1e-12)
+    best = cands[np.argmin(scores, axis=0), np.arange(f0_length)]
+    # FixF0Contour
+    vr = int(0.5 + 1000.0 / frame_period / f0_floor) * 2 + 1
+    if f0_length <= vr:
+        return np.zeros(f0_length), t
+    base = np.zeros(f0_length); base[vr:f0_length - vr] = best[vr:f0_length - vr]
+    s1 = np.zeros(f0_length)
+    for i in range(vr, f0_length):
+        s1[i] = base[i] if abs((base[i] - base[i - 1]) / (1e-12 + base[i])) < allowed_range else 0.0
+    s2 = s1.copy()
+    c = (vr - 1) // 2
+    for i in range(c, f0_length - c):
+        if np.any(s1[i - c:i + c + 1] == 0):
+            s2[i] = 0.0
+    pos = [i for i in range(1, f0_length) if s2[i - 1] == 0 and s2[i] != 0]
+    neg = [i - 1 for i in range(1, f0_length) if s2[i] == 0 and s2[i - 1] != 0]
+    def select(cur, past, idx):
+        ref = (cur * 3.0 - past) / 2.0
+        col = cands[:, idx]
+        bf = col[np.argmin(np.abs(ref - col))]
+        return 0.0 if abs(1.0 - bf / ref) > allowed_range else bf
+    s3 = s2.copy()
+    for i, st in enumerate(neg):
+        limit = f0_length - 1 if i == len(neg) - 1 else neg[i + 1]
+        for j in range(st, limit):
+            s3[j + 1] = select(s3[j], s3[j - 1], j + 1)
+            if s3[j + 1] == 0: break
+    s4 = s3.copy()
+    for i in range(len(pos) - 1, -1, -1):
+        limit = 1 if i == 0 else pos[i - 1]
+        for j in range(pos[i], limit, -1):
+            s4[j - 1] = select(s4[j], s4[j + 1], j - 1)
+            if s4[j - 1] == 0: break
+    return s4, t
+
+def stonemask_np(x, fs, t, f0):
+    n = len(x); out = np.zeros(len(f0))
+    for i, (tt, f) in enumerate(zip(t, f0)):
+        if f <= 40.0 or f > fs / 12.0: continue
+        half = int(1.5 * fs / f + 1.0)
+        wl = (2 * half + 1) / fs
+        bt = -half / fs + np.arange(2 * half + 1) / fs
+        fft = 2 ** (2 + int(np.log(half * 2 + 1.0) / np.log(2.0)))
+        idx = mround((tt + bt[0]) * fs + 0.001) + np.arange(len(bt))
+        tm = (idx - 1.0) / fs - tt
+        mw = 0.42 + 0.5 * np.cos(2 * np.pi * tm / wl) + 0.08 * np.cos(4 * np.pi * tm / wl)
+        dw = np.empty_like(mw)
+        dw[0] = -mw[1] / 2.0; dw[1:-1] = -(mw[2:] - mw[:-2]) / 2.0; dw[-1] = mw[-2] / 2.0
+        safe = np.clip(idx - 1, 0, n - 1)
+        def spec(w):
+            b = np.zeros(fft); b[:len(w)] = x[safe] * w
+            return np.fft.rfft(b)
+        M, D = spec(mw), spec(dw)
+        P = np.abs(M) ** 2
+        NI = M.real * D.imag - M.imag * D.real
+        def fix(f_init, nh):
+            k = np.array([mround(f_init * fft / fs * (j + 1)) for j in range(nh)])
+            inst = np.where(P[k] == 0, 0.0, k * fs / fft + NI[k] / np.where(P[k] == 0, 1, P[k]) * fs / 2.0 / np.pi)
+            amp = np.sqrt(P[k])
+            return (amp * inst).sum() / ((amp * (np.arange(nh) + 1.0)).sum() + 1e-12)      # stonemask.cpp FixF0: harmonic k votes f_k / k, weighted by amplitude * k
+        nh = min(int(fs / 2.0 / f), 6)
+        tent = fix(f, 2)
+        mean = 0.0 if (tent <= 0 or tent > f * 2) else fix(tent, nh)
+        out[i] = f if abs(mean - f) > f * 0.2 else mean
     return out
 

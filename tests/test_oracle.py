@@ -251,3 +251,16 @@ def test_cheaptrick_and_d4c_agree_with_independent_numpy_writings():
     ap = W.d4c(x, FS, t, f0)
     ap = ap[0] if isinstance(ap, tuple) else ap
     assert np.abs(iw.d4c_np(x, FS, t, f0) - ap).max() < 1e-10
+
+
+@pytest.mark.parametrize('stream', [5, 9, 13])
+def test_dio_and_stonemask_agree_with_independent_numpy_writings(stream):
+    """DIO (filter bank, four zero-crossing trains, candidate scoring, four-step contour repair) and StoneMask, C oracle vs
+    tests/independent_world.py: same voiced decisions, f0 within 1e-9 Hz."""
+    from tests import independent_world as iw
+    x = synthetic.synthetic_speech(0.8, stream=stream).astype(np.float64)
+    f0_ref, t_ref = W.dio(x, FS)[:2]
+    f0, t = iw.dio_np(x, FS)
+    assert np.array_equal(t, t_ref) and np.array_equal(f0 > 0, f0_ref > 0) and (f0_ref > 0).sum() > 50
+    assert np.abs(f0 - f0_ref).max() < 1e-9
+    assert np.abs(iw.stonemask_np(x, FS, t_ref, f0_ref) - W.stonemask(x, FS, t_ref, f0_ref)).max() < 1e-9
