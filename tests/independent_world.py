@@ -4,6 +4,8 @@ oracle/world_oracle.c: two writings made independently of each other must agree 
 The DECIDE points are the oracle's (no randn dither, `+ eps` instead of `+ |randn| * eps`).
 History: DIO, CheapTrick and D4C agreed on the first comparison; StoneMask's second writing first used the wrong harmonic weighting
 (sum a_k f_k / k / sum a_k instead of sum a_k f_k / sum a_k k) -- the C oracle had WORLD's form."""
+import math
+
 import numpy as np
 
 from oracle import world as W
@@ -269,4 +271,122 @@ def stonemask_np(x, fs, t, f0):
         mean = 0.0 if (tent <= 0 or tent > f * 2) else fix(tent, nh)
         out[i] = f if abs(mean - f) > f * 0.2 else mean
     return out
+
+
+
+# ------------------------------------------------------------------------------------ realtime synthesizer
+class NumpyRealtimeSynth:
+    """Second writing (numpy) of the realtime synthesizer contract documented in DESIGN.md DECIDE 9-11 / SURVEY A.8."""
+
+    def __init__(self, fs, frame_period_ms, fft, block):
+        self.fs, self.fp, self.n, self.B = fs, frame_period_ms / 1000.0, fft, block
+        self.f0 = np.zeros(0); self.sp = np.zeros((0, fft // 2 + 1), np.float32); self.ap = np.zeros((0, fft // 2 + 1), np.float32)
+        self.handoff = False; self.h_phase = 0.0; self.h_f0 = 0.0
+        self.pulses = []            # (index, time, vuv)
+        self.next_pulse = 0; self.done = 0
+        self.buf = np.zeros(2 * block + fft)
+        i = np.arange(fft // 2)
+        d = 0.5 - 0.5 * np.cos(2 * np.pi * (i + 1.0) / (1.0 + fft // 2))
+        self.dcr = d / d.sum()
+
+    def add(self, f0, sp, ap):
+        n = len(f0)
+        before = len(self.f0) - 1                       # cumulative_frame before
+        self.f0 = np.concatenate([self.f0, f0]); self.sp = np.concatenate([self.sp, sp]); self.ap = np.concatenate([self.ap, ap])
+        cum = before + n
+        if cum < 1:
+            self.h_f0, self.handoff = f0[-1], True
+            return
+        first = cum - n
+        start = max(0, math.ceil(first * self.fp * self.fs)); end = math.ceil(cum * self.fp * self.fs)
+        ns = end - start
+        hf = 1 if self.handoff else 0
+        cum0 = max(first, 0)
+        ct = np.array([cum0 * self.fp] * hf + [(i + cum0 + hf) * self.fp for i in range(n)])
+        cf = np.array([self.h_f0] * hf + list(f0))
+        cv = (cf != 0).astype(float)
+        ta = (np.arange(ns) + start) / self.fs
+        k = np.clip(np.searchsorted(ct, ta, side='right'), 1, len(ct) - 1)
+        s = (ta - ct[k - 1]) / (ct[k] - ct[k - 1])
+        vuv = ((cv[k - 1] + s * (cv[k] - cv[k - 1])) > 0.5).astype(float)
+        if0 = np.where(vuv == 0, 500.0, cf[k - 1] + s * (cf[k] - cf[k - 1]))
+        np_ = ns + hf
+        inc = np.zeros(np_)
+        inc[1:] = 2 * np.pi * if0[np.arange(1, np_) - hf] / self.fs
+        tp = np.empty(np_)
+        base = self.h_phase if hf else 2 * np.pi * if0[0] / self.fs
+        for b0 in range(0, np_, 256):
+            loc = np.cumsum(inc[b0:b0 + 256])
+            tp[b0:b0 + 256] = base + loc
+            base = base + loc[-1]
+        self.h_phase = tp[-1]
+        wp = np.fmod(tp, 2 * np.pi)
+        for i in np.nonzero(np.abs(np.diff(wp)) > np.pi)[0]:
+            t = ta[i] - hf / self.fs
+            idx = int(t * self.fs + 0.5) if t * self.fs > 0 else int(t * self.fs - 0.5)
+            li = min(max(idx - start, 0), ns - 1)
+            self.pulses.append((idx, t, int(vuv[li] > 0.5)))
+        self.h_f0, self.handoff = f0[-1], True
+
+    def _min_phase(self, log_half):
+        n, half = self.n, self.n // 2
+        full = np.concatenate([log_half, log_half[-2:0:-1]])
+        cep = np.fft.fft(full).real
+        cep[1:half] *= 2.0; cep[half + 1:] = 0.0
+        spec = np.fft.fft(cep)[:half + 1] / n
+        return np.exp(spec.real) * np.exp(1j * spec.imag)
+
+    def _response(self, p, noise_size):
+        idx, t, vuv = self.pulses[p]
+        n, half = self.n, self.n // 2
+        cumf = len(self.f0) - 1
+        fl = min(int(t / self.fp), cumf); ce = min(math.ceil(t / self.fp), cumf)
+        w = t / self.fp - int(t / self.fp)
+        clip = lambda a: np.clip(a.astype(float), 0.001, 0.999999999999)
+        if fl == ce:
+            s, a = np.abs(self.sp[fl].astype(float)), clip(self.ap[fl]) ** 2
+        else:
+            s = (1 - w) * np.abs(self.sp[fl].astype(float)) + w * np.abs(self.sp[ce].astype(float))
+            a = ((1 - w) * clip(self.ap[fl]) + w * clip(self.ap[ce])) ** 2
+        if vuv == 0 or a[0] > 0.999:
+            per = np.zeros(n)
+        else:
+            per = np.fft.fftshift(np.fft.irfft(self._min_phase(np.log(s * (1 - a) + 1e-12) / 2), n) * n)
+            dc = per[half:].sum()
+            per = np.concatenate([np.zeros(half), per[half:] - dc * self.dcr])
+        r = W.randn_stream(max(idx, 0), noise_size)
+        nz = np.zeros(n); nz[:noise_size] = r - r.mean()
+        with np.errstate(divide='ignore', invalid='ignore'):
+            m = self._min_phase(np.log(s * a) / 2 if vuv else np.log(s) / 2)
+            aper = np.fft.fftshift(np.fft.irfft(m * np.fft.rfft(nz), n) * n)
+        return (per * np.sqrt(noise_size) + aper) / n
+
+    def synthesis2(self):
+        if not self.pulses or self.done + self.B >= self.pulses[-1][0]:
+            return None
+        B, n = self.B, self.n
+        self.buf = np.concatenate([self.buf[B:], np.zeros(B)])
+        while self.next_pulse < len(self.pulses):
+            cur = self.pulses[self.next_pulse][0]
+            if cur >= self.done + B:
+                break
+            noise_size = min(max(self.pulses[self.next_pulse + 1][0] - cur, 1), n)
+            resp = self._response(self.next_pulse, noise_size)
+            off = cur - self.done - n // 2 + 1
+            lo = max(0, -off)
+            self.buf[off + lo:off + n] += resp[lo:]
+            self.next_pulse += 1
+        self.done += B
+        return self.buf[:B].copy()
+
+    def decode(self, f0, sp, ap):
+        self.add(f0, sp, ap)
+        out = []
+        while True:
+            y = self.synthesis2()
+            if y is None:
+                break
+            out.append(y)
+        return np.concatenate(out) if out else np.zeros(0)
+
 

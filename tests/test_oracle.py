@@ -264,3 +264,24 @@ def test_dio_and_stonemask_agree_with_independent_numpy_writings(stream):
     assert np.array_equal(t, t_ref) and np.array_equal(f0 > 0, f0_ref > 0) and (f0_ref > 0).sum() > 50
     assert np.abs(f0 - f0_ref).max() < 1e-9
     assert np.abs(iw.stonemask_np(x, FS, t_ref, f0_ref) - W.stonemask(x, FS, t_ref, f0_ref)).max() < 1e-9
+
+
+def test_realtime_synthesizer_agrees_with_an_independent_numpy_writing():
+    """The stateful realtime synthesizer (hand-off phase / f0 between AddParameters calls, blocked phase sum, pulse detection, block
+    emission rule, position-addressed noise, half-length dc-remover): C oracle vs tests/independent_world.NumpyRealtimeSynth fed the
+    same 60-frame chunks -- identical pulses, identical block counts, samples within 1e-12."""
+    from tests.independent_world import NumpyRealtimeSynth
+    x = synthetic.synthetic_speech(1.2, stream=7)
+    f = opipe.extract_features(x, opipe.PathConfig())
+    ref, mine = W.RealtimeSynthesizer(FS, 5.0, 1024, 1024), NumpyRealtimeSynth(FS, 5.0, 1024, 1024)
+    total = 0
+    for a in range(0, len(f['f0']), 60):
+        f0 = f['f0'][a:a + 60].ravel().astype(np.float64)
+        yr, ym = ref.decode(f0, f['sp'][a:a + 60], f['ap'][a:a + 60]), mine.decode(f0, f['sp'][a:a + 60], f['ap'][a:a + 60])
+        assert len(yr) == len(ym)
+        if len(yr):
+            assert np.abs(yr - ym).max() < 1e-12
+        total += len(yr)
+    idx, _, vuv = ref.pulses()
+    assert total >= 4 * 1024 and len(idx) > 100
+    assert np.array_equal(idx, [p[0] for p in mine.pulses]) and np.array_equal(vuv, [p[2] for p in mine.pulses])
