@@ -139,6 +139,10 @@ int ryk_reblock_destroy(ryk_engine* e, int reblock_id);
 int ryk_reblock_push(ryk_engine* e, int reblock_id, const double* wave, int n, double* chunk_out, int* status, double* power_db);
 int ryk_reblock_push_device(ryk_engine* e, int reblock_id, int session_id, const double* wave_dev, const int* n_dev, long long* ticket);
 int ryk_reblock_collect(ryk_engine* e, int reblock_id, long long ticket, double* chunk_out, int* status, double* power_db);
+/* Non-blocking: *done = 1 when ryk_reblock_collect(ticket) would not wait (queue_output_wave.get_nowait, run.py:176-182).
+ * collect fails (instead of dropping samples) when a step produced more than the fragment can hold: the reference's
+ * wave_fragment is unbounded (decode_worker.py:47-52), the device fragment holds 2 * (out_audio_chunk + max_in) samples. */
+int ryk_reblock_poll(ryk_engine* e, int reblock_id, long long ticket, int* done);
 int ryk_reblock_result_device(ryk_engine* e, int reblock_id, long long ticket, const double** chunk_dev, const int** status_dev,
                               const double** power_dev);
 
@@ -174,6 +178,8 @@ int ryk_session_push(ryk_engine* e, int session_id, const float* wave, int n, do
  * three CUDA streams, exactly like the reference's three worker processes (run.py:58-93).  push == submit + collect. */
 int ryk_session_submit(ryk_engine* e, int session_id, const float* wave, int n, long long* ticket);
 int ryk_session_collect(ryk_engine* e, int session_id, long long ticket, double* out, int out_capacity, int* n_out);
+/* Non-blocking: *done = 1 when ryk_session_collect(ticket) would not wait (ticket among the last 8 steps). */
+int ryk_session_poll(ryk_engine* e, int session_id, long long ticket, int* done);
 /* Same chunk step with the input already resident in HBM and the output left there (throughput measurement);
  * asynchronous: returns when the work is queued, results are valid after ryk_engine_synchronize. */
 int ryk_session_push_device(ryk_engine* e, int session_id, const float* wave_dev, int n, double* out_dev, int out_capacity,

@@ -765,7 +765,11 @@ int conv_tc_run(const ConvLayer& L, cudaStream_t st) {
   p.act = L.act; p.scale = L.scale; p.shift = L.shift; p.out = (__half*)L.out;
   p.ws = L.ksplit > 1 ? L.splitk_ws : nullptr;
   p.out_pixels = (size_t)L.B * L.Hout * L.Wout;
-  { static int dbg = -1; if (dbg < 0) { const char* v = getenv("RYK_TC_DEBUG"); dbg = v ? atoi(v) : 0; } p.debug = dbg; }
+#ifdef RYK_DIAG
+  { static int dbg = -1; if (dbg < 0) { const char* v = getenv("RYK_TC_DEBUG"); dbg = v ? atoi(v) : 0; } p.debug = dbg; }   // diagnostics builds only
+#else
+  p.debug = 0;
+#endif
   size_t out_elems = (size_t)L.B * L.Hout * L.Wout * L.Cout;
   dim3 grid(L.B * p.tiles_w * p.tiles_h, L.Cout / L.block_n, classes * L.ksplit);
   const int variant = tc_variant();

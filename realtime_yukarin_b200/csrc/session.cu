@@ -146,7 +146,7 @@ struct Reblock {
   double* d_frag[2] = {nullptr, nullptr};
   double* d_scratch = nullptr;
   double* d_chunk[kRing]; int* d_nvalid[kRing]; int* d_status[kRing]; double* d_power[kRing];
-  double* h_chunk[kRing]; int* h_status[kRing]; double* h_power[kRing];
+  double* h_chunk[kRing]; int* h_status[kRing]; double* h_power[kRing]; int* h_overflow[kRing];
   cudaEvent_t ev[kRing];
   double* d_stage_in = nullptr; int* d_stage_n = nullptr;     // staging for the host-buffer entry point
   long long pushed = 0;
@@ -170,7 +170,8 @@ __global__ void __launch_bounds__(1024) k_reblock(ReblockState* __restrict__ st,
   const int len = sh_len, sel = sh_sel;
   int n_in = *n_in_p;
   if (n_in < 0) n_in = 0;
-  if (n_in > max_in) n_in = max_in;
+  int clamped = 0;
+  if (n_in > max_in) { n_in = max_in; clamped = 1; }
   double* cur = sel ? frag1 : frag0;
   double* nxt = sel ? frag0 : frag1;
   const int new_len = len + n_in;
@@ -179,10 +180,10 @@ __global__ void __launch_bounds__(1024) k_reblock(ReblockState* __restrict__ st,
     if (rest > cap) { rest = cap; over = 1; }
     for (int i = threadIdx.x; i < chunk; i += blockDim.x) out[i] = i < len ? cur[i] : in[i - len];
     for (int j = threadIdx.x; j < rest; j += blockDim.x) { const int i = chunk + j; nxt[j] = i < len ? cur[i] : in[i - len]; }
-    if (threadIdx.x == 0) { st->len = rest; st->sel = sel ^ 1; st->overflow |= over; *n_valid = chunk; }
+    if (threadIdx.x == 0) { st->len = rest; st->sel = sel ^ 1; st->overflow |= over | clamped; *n_valid = chunk; }
   } else {
     for (int i = threadIdx.x; i < n_in; i += blockDim.x) cur[len + i] = in[i];
-    if (threadIdx.x == 0) { st->len = new_len; *n_valid = 0; }
+    if (threadIdx.x == 0) { st->len = new_len; st->overflow |= clamped; *n_valid = 0; }
   }
 }
 
@@ -298,10 +299,16 @@ int session_streams_join(Engine* e) {
 // padded effective length), so each variant is stream-captured once and replayed: a step costs ~6 graph launches on
 // the host instead of ~90 kernel launches (the host was the bottleneck at 0.75 ms of launch overhead per 0.78 ms step).
 // RYK_SESSION_SKIP (timing experiments only; results are garbage): bit 0 analysis (E2), 1 stage 1, 2 stage-2 layers 1..14, 3 synthesis
+// Compiled in only with -DRYK_DIAG (tools/gpu_skip_sweep.sh builds a separate diagnostics library): a release libryk.so has no
+// knob that can turn the timed path into a partial one.
 static int session_skip_mask() {
+#ifdef RYK_DIAG
   static int m = -1;
   if (m < 0) { const char* v = getenv("RYK_SESSION_SKIP"); m = v ? atoi(v) : 0; }
   return m;
+#else
+  return 0;
+#endif
 }
 template <typename F>
 static int run_stage(Engine* e, Session* s, int key, cudaStream_t st, F&& body, bool capture_only = false) {
@@ -776,6 +783,19 @@ int ryk_session_collect(ryk_engine* h, int id, long long ticket, double* out, in
   return 0;
 }
 
+// Non-blocking completion query (cudaEventQuery of the step's last decode-stream event): *done = 1 when ryk_session_collect would
+// not wait.  This is what queue_output_wave.get_nowait() needs (run.py:176-182).
+int ryk_session_poll(ryk_engine* h, int id, long long ticket, int* done) {
+  Engine* e = &h->impl;
+  Session* s = get_session(e, id);
+  RYK_CHECK(s != nullptr && done != nullptr, "no such session");
+  RYK_CHECK(ticket >= 0 && ticket < s->step && ticket + kRing > s->step, "ticket is not among the last 8 steps");
+  cudaError_t q = cudaEventQuery(s->ev_dec[ticket % kRing]);
+  if (q != cudaSuccess && q != cudaErrorNotReady) RYK_CUDA(q);
+  *done = q == cudaSuccess ? 1 : 0;
+  return 0;
+}
+
 int ryk_session_push(ryk_engine* h, int id, const float* wave, int n, double* out, int out_capacity, int* n_out) {
   long long ticket = 0;
   if (ryk_session_submit(h, id, wave, n, &ticket)) return -1;
@@ -971,6 +991,7 @@ int ryk_reblock_create(ryk_engine* h, int out_audio_chunk, int max_in, int n_fft
     rc |= H((void**)&R->h_chunk[i], sizeof(double) * out_audio_chunk);
     rc |= H((void**)&R->h_status[i], sizeof(int));
     rc |= H((void**)&R->h_power[i], sizeof(double));
+    rc |= H((void**)&R->h_overflow[i], sizeof(int));
     if (!rc && cudaEventCreateWithFlags(&R->ev[i], cudaEventDisableTiming) != cudaSuccess) rc = -1;
   }
   if (rc) { reblock_free(R); return -1; }
@@ -1020,6 +1041,7 @@ int ryk_reblock_push_device(ryk_engine* h, int id, int session_id, const double*
   RYK_CUDA(cudaMemcpyAsync(R->h_status[r], R->d_status[r], sizeof(int), cudaMemcpyDeviceToHost, st));
   RYK_CUDA(cudaMemcpyAsync(R->h_power[r], R->d_power[r], sizeof(double), cudaMemcpyDeviceToHost, st));
   RYK_CUDA(cudaMemcpyAsync(R->h_chunk[r], R->d_chunk[r], sizeof(double) * R->chunk, cudaMemcpyDeviceToHost, st));
+  RYK_CUDA(cudaMemcpyAsync(R->h_overflow[r], &R->d_state->overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
   RYK_CUDA(cudaEventRecord(R->ev[r], st));
   R->pushed++;
   if (ticket) *ticket = k;
@@ -1035,10 +1057,25 @@ int ryk_reblock_collect(ryk_engine* h, int id, long long ticket, double* chunk_o
   RYK_CHECK(ticket >= 0 && ticket < R->pushed && ticket + kRing > R->pushed, "ticket is not among the last 8 pushes");
   const int r = (int)(ticket % kRing);
   RYK_CUDA(cudaEventSynchronize(R->ev[r]));
+  // the reference's wave_fragment grows without bound when a step yields more than one out_audio_chunk (decode_worker.py:47-52);
+  // the device fragment is bounded, so that configuration is an error here instead of silently dropped samples
+  RYK_CHECK(*R->h_overflow[r] == 0, "re-blocker fragment overflow: a step produced more samples than out_audio_chunk can drain");
   const int stt = *R->h_status[r];
   if (status) *status = stt;
   if (power_db) *power_db = *R->h_power[r];
   if (chunk_out && stt != 0) memcpy(chunk_out, R->h_chunk[r], sizeof(double) * R->chunk);
+  return 0;
+}
+
+// Non-blocking: *done = 1 when ryk_reblock_collect(ticket) would not wait.
+int ryk_reblock_poll(ryk_engine* h, int id, long long ticket, int* done) {
+  Engine* e = &h->impl;
+  Reblock* R = get_reblock(e, id);
+  RYK_CHECK(R != nullptr && done != nullptr, "no such re-blocker");
+  RYK_CHECK(ticket >= 0 && ticket < R->pushed && ticket + kRing > R->pushed, "ticket is not among the last 8 pushes");
+  cudaError_t q = cudaEventQuery(R->ev[ticket % kRing]);
+  if (q != cudaSuccess && q != cudaErrorNotReady) RYK_CUDA(q);
+  *done = q == cudaSuccess ? 1 : 0;
   return 0;
 }
 

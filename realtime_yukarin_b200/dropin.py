@@ -11,8 +11,14 @@ import sys
 import types
 
 
-def _module(name: str, **attrs) -> types.ModuleType:
+_skip = set()
+
+
+def _module(name: str, **attrs):
+    if name.partition('.')[0] in _skip:
+        return None
     m = types.ModuleType(name)
+    m.__ryk_alias__ = True
     m.__dict__.update(attrs)
     m.__path__ = []          # behave like a package so that submodule imports resolve through sys.modules
     sys.modules[name] = m
@@ -22,8 +28,26 @@ def _module(name: str, **attrs) -> types.ModuleType:
     return m
 
 
-def install() -> None:
+def _importable(top: str) -> bool:
+    """True when a REAL package of that name can be imported (an alias this module registered earlier does not count)."""
+    import importlib.util
+    m = sys.modules.get(top)
+    if m is not None:
+        return not getattr(m, '__ryk_alias__', False)
+    try:
+        return importlib.util.find_spec(top) is not None
+    except (ImportError, ValueError):
+        return False
+
+
+def install(force: bool = True) -> None:
+    """Register the aliases.  force=True (default, what a drop-in switch wants): this package answers to the reference's names even
+    if the original packages are installed.  force=False: a family (`realtime_voice_conversion`, `yukarin`, `become_yukarin`) is
+    aliased only when no real package of that name is importable, so an existing installation is never shadowed."""
     from . import config, converter, feature, models, params, segment, stream, vocoder, voice_changer, wave_io, worker
+
+    global _skip
+    _skip = set() if force else {top for top in ('realtime_voice_conversion', 'yukarin', 'become_yukarin') if _importable(top)}
 
     rvc = 'realtime_voice_conversion'
     _module(rvc)
@@ -56,7 +80,7 @@ def install() -> None:
     try:
         import librosa  # noqa: F401
     except ImportError:
-        def _load(path, sr=None, **_):
+        def _load(path, sr=22050, **_):       # librosa.load's default rate; check.py:80 always passes sr=
             w = wave_io.load_wave(path, sr)
             return w.wave, w.sampling_rate
         _module('librosa', load=_load)

@@ -50,7 +50,7 @@ EXPORTED_SYMBOLS = [
     'ryk_group_size', 'ryk_session_stage_times', 'ryk_group_submit', 'ryk_group_collect', 'ryk_group_push_device', 'ryk_test_conv_layer', 'ryk_debug_dio', 'ryk_debug_synth_pulses', 'ryk_debug_synth_timebase', 'ryk_engine_profile', 'ryk_engine_profile_read', 'ryk_engine_timer_start', 'ryk_engine_timer_stop',
     'ryk_world_synthesize_length', 'ryk_world_synthesize', 'ryk_output_gate', 'ryk_reblock_create', 'ryk_reblock_destroy',
     'ryk_reblock_push', 'ryk_reblock_push_device', 'ryk_reblock_collect', 'ryk_reblock_result_device', 'ryk_resample_length',
-    'ryk_resample_poly',
+    'ryk_resample_poly', 'ryk_session_poll', 'ryk_reblock_poll',
 ]
 
 
@@ -255,7 +255,7 @@ class Engine(object):
         sid = ctypes.c_int()
         self._check(self.lib.ryk_synth_create(self._h, int(fs), ctypes.c_double(frame_period), int(fft_size), int(buffer_size),
                                               int(number_of_pointers), ctypes.byref(sid)))
-        self._synth_block[sid.value] = (int(buffer_size), int(fft_size))
+        self._synth_block[sid.value] = (int(buffer_size), int(fft_size), float(fs) * float(frame_period) / 1000.0)
         return sid.value
 
     def synth_destroy(self, sid: int):
@@ -277,7 +277,9 @@ class Engine(object):
         sp, ap = _f32(sp), _f32(ap)
         B = self._synth_block[sid][0]
         if max_blocks is None:
-            max_blocks = max(4, len(f0) * 240 // B + 4)
+            # samples one call can add = frames * (fs * frame_period / 1000) of THIS synthesizer (not a fixed 240 per frame): the
+            # reference loops `while _Synthesis2() != 0` until the synthesizer is empty (vocoder.py:103-116)
+            max_blocks = max(4, int(len(f0) * self._synth_block[sid][2]) // B + 4)
         out = numpy.empty(max_blocks * B, dtype=numpy.float64)
         nblk = ctypes.c_int()
         self._check(self.lib.ryk_synth_decode(self._h, sid, _dp(f0), len(f0), _fp(sp), _fp(ap), _dp(out), int(max_blocks), ctypes.byref(nblk)))
@@ -342,6 +344,11 @@ class Engine(object):
         st, pw = ctypes.c_int(), ctypes.c_double()
         self._check(self.lib.ryk_reblock_collect(self._h, rid, ctypes.c_longlong(ticket), _dp(out), ctypes.byref(st), ctypes.byref(pw)))
         return st.value, (out if st.value == 1 else None), pw.value
+
+    def reblock_poll(self, rid: int, ticket: int) -> bool:
+        done = ctypes.c_int()
+        self._check(self.lib.ryk_reblock_poll(self._h, rid, ctypes.c_longlong(ticket), ctypes.byref(done)))
+        return bool(done.value)
 
     def resample_poly(self, x, up: int, down: int, taps) -> numpy.ndarray:
         """scipy.signal.resample_poly's filtering step on the device (wave_io.resample designs `taps`)."""
@@ -426,6 +433,12 @@ class Engine(object):
         n_out = ctypes.c_int()
         self._check(self.lib.ryk_session_collect(self._h, sid, ctypes.c_longlong(ticket), _dp(out), len(out), ctypes.byref(n_out)))
         return out[:n_out.value]
+
+    def session_poll(self, sid: int, ticket: int) -> bool:
+        """True when session_collect(ticket) would return without waiting (cudaEventQuery, never blocks)."""
+        done = ctypes.c_int()
+        self._check(self.lib.ryk_session_poll(self._h, sid, ctypes.c_longlong(ticket), ctypes.byref(done)))
+        return bool(done.value)
 
     def session_push_device(self, sid: int, wave_dev_ptr: int, n: int, out_dev_ptr: int, out_capacity: int, n_out_dev_ptr: int):
         self._check(self.lib.ryk_session_push_device(self._h, sid, ctypes.c_void_p(wave_dev_ptr), int(n), ctypes.c_void_p(out_dev_ptr),

@@ -96,12 +96,48 @@ class F0Converter(object):
         return engine.f0_convert(f0.ravel(), f0.ravel() != 0).reshape(f0.shape)
 
 
+STATS_KEYS = ('stats/in_mean', 'stats/in_std', 'stats/out_mean', 'stats/out_std')
+
+
+def load_stage1_stats(params: Dict[str, numpy.ndarray], model_path, in_ch: int, out_ch: int, feature_stats=None):
+    """Mel-cepstrum normalisation of stage 1 (SURVEY A.6 "input mean/var ... target mean/var", DECIDE 8).  Sources, in order:
+      1. `feature_stats` = (in_mean, in_std, out_mean, out_std) arrays or a path to an .npz holding the `stats/*` keys,
+      2. `stats/*` keys inside the model file (what synthetic.py writes),
+      3. `<model dir>/stats.npz` next to predictor.npz.
+    A bare Chainer predictor.npz has none of them: converting un-normalised features would run without any error and give
+    garbage, so that case RAISES instead of silently falling back to identity.  Pass feature_stats='identity' to opt in."""
+    def from_mapping(m):
+        return tuple(numpy.asarray(m[k], numpy.float32) for k in STATS_KEYS)
+    if isinstance(feature_stats, str) and feature_stats == 'identity':
+        st = (numpy.zeros(in_ch, numpy.float32), numpy.ones(in_ch, numpy.float32), numpy.zeros(out_ch, numpy.float32), numpy.ones(out_ch, numpy.float32))
+    elif isinstance(feature_stats, (str, Path)):
+        with numpy.load(str(feature_stats), allow_pickle=False) as z:
+            st = from_mapping(z)
+    elif feature_stats is not None:
+        st = tuple(numpy.asarray(a, numpy.float32) for a in feature_stats)
+    elif all(k in params for k in STATS_KEYS):
+        st = from_mapping(params)
+    elif (Path(model_path).parent / 'stats.npz').exists():
+        with numpy.load(str(Path(model_path).parent / 'stats.npz'), allow_pickle=False) as z:
+            st = from_mapping(z)
+    else:
+        raise ValueError(
+            f'{model_path}: no stage-1 feature normalisation statistics (keys {STATS_KEYS} in the model file, a stats.npz next to '
+            "it, or feature_stats=...). Upstream yukarin keeps them outside predictor.npz; pass feature_stats='identity' only if the "
+            'model was really trained on un-normalised mel-cepstra.')
+    if [len(a) for a in st] != [in_ch, in_ch, out_ch, out_ch]:
+        raise ValueError(f'stage-1 statistics have lengths {[len(a) for a in st]}, the model has {in_ch} input / {out_ch} output channels')
+    if not (numpy.all(st[1] > 0) and numpy.all(st[3] > 0)):
+        raise ValueError('stage-1 statistics: standard deviations must be positive')
+    return st
+
+
 class AcousticConverter(object):
     """Stage 1.  `gpu` is accepted for signature compatibility (converter/yukarin_converter.py:44);
     the engine always runs on the process's B200."""
 
     def __init__(self, config: Config, model_path: Path, gpu: int = None, f0_converter: F0Converter = None,
-                 out_sampling_rate: int = None, engine: Optional[Engine] = None) -> None:
+                 out_sampling_rate: int = None, engine: Optional[Engine] = None, feature_stats=None) -> None:
         self.config = config
         self.model_path = model_path
         self.gpu = gpu
@@ -110,11 +146,7 @@ class AcousticConverter(object):
         self.engine = engine or default_engine()
         params = load_npz(model_path)
         in_ch, out_ch, _ = upload_unet(self.engine, 1, params)
-        one, zero = numpy.ones(in_ch, numpy.float32), numpy.zeros(in_ch, numpy.float32)
-        self.in_mean = params.get('stats/in_mean', zero).astype(numpy.float32)
-        self.in_std = params.get('stats/in_std', one).astype(numpy.float32)
-        self.out_mean = params.get('stats/out_mean', numpy.zeros(out_ch, numpy.float32)).astype(numpy.float32)
-        self.out_std = params.get('stats/out_std', numpy.ones(out_ch, numpy.float32)).astype(numpy.float32)
+        self.in_mean, self.in_std, self.out_mean, self.out_std = load_stage1_stats(params, model_path, in_ch, out_ch, feature_stats)
         self.engine.stage1_set_stats(self.in_mean, self.in_std, self.out_mean, self.out_std)
         if f0_converter is not None:
             self.engine.f0_set_stats(*f0_converter.stats())

@@ -70,6 +70,7 @@ def run(config_path: Path, wav_in: Optional[Path] = None, wav_out: Optional[Path
                 return wave[a:a + config.in_audio_chunk]
 
             n = audio_loop(pipeline, read_chunk, out_chunks.append, max_chunks)
+            out_chunks.extend(pipeline.drain())      # chunks still in flight when the file ended
             if wav_out is not None:
                 wave_io.write_wav(wav_out, numpy.concatenate(out_chunks) if out_chunks else numpy.zeros(0, numpy.float32), config.output_rate)
             return n

@@ -114,9 +114,20 @@ class RealtimePipeline(object):
             self._finish_one()
         return self._done.popleft()
 
+    def _reap(self) -> None:
+        """Move every in-flight item the device has already finished to `_done` without blocking (cudaEventQuery on the
+        step's decode event and on the re-blocker event).  Chunks finish in submission order, so stop at the first busy one."""
+        while self._inflight:
+            _, ts, tr = self._inflight[0]
+            if not (self.engine.session_poll(self._sid, ts) and self.engine.reblock_poll(self._rid, tr)):
+                break
+            self._finish_one()
+
     def get_nowait(self) -> Optional[Item]:
-        """An Item whose processing has finished, else None.  (The device finishes chunks in submission order; the
-        reference's reorder buffer exists because its three processes finish out of order.)"""
+        """An Item whose processing has finished, else None -- as soon as the device is done with it, like the reference's
+        queue_output_wave.get_nowait() (run.py:176-182), not `depth` iterations later.  (The device finishes chunks in
+        submission order; the reference's reorder buffer exists because its three processes finish out of order.)"""
+        self._reap()
         return self._done.popleft() if self._done else None
 
     def flush(self) -> None:
@@ -132,6 +143,15 @@ class RealtimePipeline(object):
         self._index_input += 1
         if block:
             self.flush()
+        out_wave = self._next_output()
+        if out_wave is None:
+            out_wave = numpy.zeros(c.out_audio_chunk)
+        out_wave = out_wave * c.output_scale
+        return out_wave[:c.out_audio_chunk].astype(numpy.float32)
+
+    def _next_output(self) -> Optional[numpy.ndarray]:
+        """run.py:176-195: pop every finished item, take the ones whose index is next in order; silent items (None) are
+        skipped; returns the first real chunk or None when nothing (more) is ready."""
         out_wave = None
         while True:
             while True:
@@ -148,10 +168,20 @@ class RealtimePipeline(object):
             if out_wave is None:        # silence wave
                 continue
             break
-        if out_wave is None:
-            out_wave = numpy.zeros(c.out_audio_chunk)
-        out_wave = out_wave * c.output_scale
-        return out_wave[:c.out_audio_chunk].astype(numpy.float32)
+        return out_wave
+
+    def drain(self) -> List[numpy.ndarray]:
+        """End of a finite input (wav file): wait for everything in flight and return the output chunks not played yet, in
+        order (the reference's loop never ends; a file-driven run must not lose the tail that is still in the pipeline)."""
+        c = self.config
+        self.flush()
+        outs: List[numpy.ndarray] = []
+        while self._done or self._popped:
+            w = self._next_output()
+            if w is None:
+                break
+            outs.append((w * c.output_scale)[:c.out_audio_chunk].astype(numpy.float32))
+        return outs
 
     def close(self) -> None:
         if self._sid is not None:

@@ -159,3 +159,56 @@ def test_pair_kernel(engine, case):
     print('pair kernel', case, 'max err', err, '(one-CTA kernel', err_base, ') ms', ms)
     assert err < 3e-2, err
     assert np.abs(got - base).max() < 2e-2          # same fp16 operands, fp32 accumulation in a different order
+
+
+# The 14 k4 layers of the stage-2 U-Net exactly as the benchmarked forward runs them (base 64, Tp = 384 x 512 bins, batch 1):
+# same tile geometry, same split-K factor (ksplit is a function of the layer shape and the SM count only), same skip-concat
+# split of the decoder inputs.   name, transposed, H, W, C0, C1, Cout, act
+PRODUCTION_LAYERS = [
+    ('c1', 0, 384, 512, 64, 0, 128, 1), ('c2', 0, 192, 256, 128, 0, 256, 1), ('c3', 0, 96, 128, 256, 0, 512, 1),
+    ('c4', 0, 48, 64, 512, 0, 512, 1), ('c5', 0, 24, 32, 512, 0, 512, 1), ('c6', 0, 12, 16, 512, 0, 512, 1), ('c7', 0, 6, 8, 512, 0, 512, 1),
+    ('d0', 1, 3, 4, 512, 0, 512, 2), ('d1', 1, 6, 8, 512, 512, 512, 2), ('d2', 1, 12, 16, 512, 512, 512, 2),
+    ('d3', 1, 24, 32, 512, 512, 512, 2), ('d4', 1, 48, 64, 512, 512, 256, 2), ('d5', 1, 96, 128, 256, 256, 128, 2),
+    ('d6', 1, 192, 256, 128, 128, 64, 2),
+    # the batch-8 / Tp = 512 grouped shape (BASELINE config 5) for the two layers whose tiling changes most with M
+    ('c1_b2_512', 0, 512, 512, 64, 0, 128, 1), ('d6_512', 1, 256, 256, 128, 128, 64, 2),
+]
+
+
+def _ref32(in0, in1, W, scale, shift, transposed, act):
+    """float32 torch-CPU reference (oneDNN) for the large shapes: a float64 conv of 13-26 GFLOP would take minutes"""
+    x = in0 if in1 is None else np.concatenate([in0, in1], axis=3)
+    xt = torch.from_numpy(x).permute(0, 3, 1, 2).contiguous()
+    Wt = torch.from_numpy(W)
+    y = F.conv_transpose2d(xt, Wt, stride=2, padding=1) if transposed else F.conv2d(xt, Wt, stride=2, padding=1)
+    y = y * torch.from_numpy(scale)[None, :, None, None] + torch.from_numpy(shift)[None, :, None, None]
+    if act == 1:
+        y = torch.where(y > 0, y, 0.2 * y)
+    elif act == 2:
+        y = torch.relu(y)
+    return y.permute(0, 2, 3, 1).contiguous().numpy()
+
+
+@pytest.mark.parametrize('case', PRODUCTION_LAYERS, ids=[c[0] for c in PRODUCTION_LAYERS])
+def test_production_layer_shapes(engine, case):
+    """tcgen05 kernel (and, with RYK_TC_HALO default on, the halo kernel) on the shapes bench.py runs; inputs are fp16-representable
+    so that the only differences from the float32 reference are accumulation order and the fp16 output rounding."""
+    name, tr, H, W, C0, C1, Cout, act = case
+    B = 2 if name.endswith('_b2_512') else 1
+    rng = np.random.default_rng(sum(name.encode()) * 7919)
+    in0 = rng.standard_normal((B, H, W, C0)).astype(np.float16).astype(np.float32)
+    in1 = rng.standard_normal((B, H, W, C1)).astype(np.float16).astype(np.float32) if C1 else None
+    Cin = C0 + C1
+    shape = (Cin, Cout, 4, 4) if tr else (Cout, Cin, 4, 4)
+    Wt = (rng.standard_normal(shape) / np.sqrt(Cin * 16 / (4 if tr else 1))).astype(np.float16).astype(np.float32)
+    scale = rng.uniform(0.8, 1.2, Cout).astype(np.float32)
+    shift = (0.1 * rng.standard_normal(Cout)).astype(np.float32)
+    ref = _ref32(in0, in1, Wt, scale, shift, tr, act)
+    got, ms = engine.test_conv_layer(in0, in1, Wt, scale, shift, tr, 4, 2, 1, act, use_tc=1, repeat=5)
+    err = np.abs(got - ref)
+    flop = 2.0 * 16 * Cin * Cout * (B * H * W / 4 if not tr else B * H * W)
+    print(f'production layer {name}: max err {err.max():.2e} rms {np.sqrt((err ** 2).mean()):.2e} (|ref| max {np.abs(ref).max():.2f}); '
+          f'{ms * 1e3:.1f} us, {flop / (ms * 1e-3) / 1e12 if ms > 0 else 0:.0f} TFLOP/s')
+    # fp16 output rounding of |y| < 8 is 2^-9 * 4 = 8e-3; accumulation-order noise is ~1e-5
+    assert err.max() < 1.2e-2, err.max()
+    assert np.sqrt((err ** 2).mean()) < 1.5e-3

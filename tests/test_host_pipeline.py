@@ -51,3 +51,24 @@ def test_stream_classes_reproduce_oracle_stream(small_models, T, extra):
             assert np.allclose(y, r, atol=1e-9), k
     finally:
         eng_mod.set_default_engine(None)
+
+
+def test_stage1_checkpoint_without_statistics_is_rejected(tmp_path):
+    """a bare Chainer predictor.npz (encoder/decoder links only) must not silently convert un-normalised features."""
+    import numpy as np
+    import pytest
+    from realtime_yukarin_b200 import synthetic
+    from realtime_yukarin_b200.models import STATS_KEYS, load_stage1_stats
+    p = synthetic.make_stage1_params(0, base=8)
+    st = load_stage1_stats(p, tmp_path / 'predictor.npz', 9, 9)
+    assert np.array_equal(st[0], synthetic.MC_MEAN_IN) and np.array_equal(st[3], synthetic.MC_STD_OUT)
+    bare = {k: v for k, v in p.items() if k not in STATS_KEYS}
+    with pytest.raises(ValueError, match='normalisation statistics'):
+        load_stage1_stats(bare, tmp_path / 'predictor.npz', 9, 9)
+    ident = load_stage1_stats(bare, tmp_path / 'predictor.npz', 9, 9, feature_stats='identity')
+    assert not ident[0].any() and (ident[1] == 1).all()
+    np.savez(tmp_path / 'stats.npz', **{k: p[k] for k in STATS_KEYS})              # side file next to the model
+    side = load_stage1_stats(bare, tmp_path / 'predictor.npz', 9, 9)
+    assert np.array_equal(side[2], synthetic.MC_MEAN_OUT)
+    with pytest.raises(ValueError, match='lengths'):
+        load_stage1_stats(bare, tmp_path / 'predictor.npz', 8, 9)

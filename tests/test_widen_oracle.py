@@ -158,22 +158,50 @@ def test_realtime_pipeline_audio_loop_on_cpu(small_models):
     rb = opipe.OutputReblockOracle(cfg.out_audio_chunk, 80.0)
     expected = [rb.push(orc.push((x[k * n:(k + 1) * n] * cfg.input_scale).astype(np.float32)))[1] for k in range(K)]
 
+    def want(e):
+        return np.zeros(cfg.out_audio_chunk, np.float32) if e is None else (e * cfg.output_scale)[:cfg.out_audio_chunk].astype(np.float32)
+
+    # (a) a device that has finished by the time the loop asks (the stand-in computes inside submit; poll -> True): the chunk is played
+    #     in the SAME iteration, like the reference's get_nowait() once its workers are done -- not `depth` iterations later
     pipe = RealtimePipeline(cfg, engine=fake, depth=2)
     pipe.put(Item(item=x[:n] * cfg.input_scale, index=0))
-    assert pipe.get_nowait() is None                      # still in flight
-    it = pipe.get()
-    assert it.index == 0 and (it.item is None) == (expected[0] is None)
+    it = pipe.get_nowait()
+    assert it is not None and it.index == 0 and (it.item is None) == (expected[0] is None)
+    assert pipe.get_nowait() is None                      # nothing else in flight
     pipe.close()
 
     pipe = RealtimePipeline(cfg, engine=fake, depth=2)
     outs = [pipe.process(x[k * n:(k + 1) * n]) for k in range(K)]
     assert all(o.dtype == np.float32 and len(o) == cfg.out_audio_chunk for o in outs)
-    assert not outs[0].any() and not outs[1].any()        # depth 2: nothing has been collected yet -> the loop plays zeros
-    # from step `depth` on, iteration k plays item k - depth (or zeros when that item is None)
+    for k in range(K):
+        assert np.array_equal(outs[k], want(expected[k])), k
+    assert pipe.drain() == []                             # nothing left in the pipeline
+    pipe.close()
+
+    # (b) a device that is never done when polled: the loop plays zeros until `depth` forces a collect (iteration k plays item k - depth),
+    #     and drain() returns the tail that a finite (wav file) run would otherwise lose
+    class Lagging(OracleEngine):
+        def session_poll(self, sid, ticket):
+            return False
+
+        def reblock_poll(self, rid, ticket):
+            return False
+    lag = Lagging(small_models['stage1_model_path'], small_models['stage2_model_path'])
+    pipe = RealtimePipeline(cfg, engine=lag, depth=2)
+    pipe.put(Item(item=x[:n] * cfg.input_scale, index=0))
+    assert pipe.get_nowait() is None                      # still in flight
+    it = pipe.get()                                       # blocking get collects it
+    assert it.index == 0 and (it.item is None) == (expected[0] is None)
+    pipe.close()
+    pipe = RealtimePipeline(cfg, engine=lag, depth=2)
+    outs = [pipe.process(x[k * n:(k + 1) * n]) for k in range(K)]
+    assert not outs[0].any() and not outs[1].any()
     for k in range(2, K):
-        e = expected[k - 2]
-        want = np.zeros(cfg.out_audio_chunk, np.float32) if e is None else (e * cfg.output_scale)[:cfg.out_audio_chunk].astype(np.float32)
-        assert np.array_equal(outs[k], want), k
+        assert np.array_equal(outs[k], want(expected[k - 2])), k
+    tail = pipe.drain()
+    assert len(tail) == sum(e is not None for e in expected[K - 2:])
+    for w, e in zip(tail, [e for e in expected[K - 2:] if e is not None]):
+        assert np.array_equal(w, want(e))
     pipe.close()
 
 
