@@ -735,6 +735,7 @@ int ryk_test_conv_layer(ryk_engine* h, int transposed, int k, int stride, int pa
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, e->device);
     size_t ws = tc_splitk_ws_bytes(L, num_sms);
     if (ws) L.splitk_ws = (float*)A(ws);
+    if (tc_layer_wants_counter(L, num_sms)) { L.t3_ctr = (int*)A(16); RYK_CUDA(cudaMemsetAsync(L.t3_ctr, 0, 16, st)); }
     if (tc_layer_prepare(L, num_sms)) return -1;
     rc = conv_tc_run(L, st);
     if (!rc && repeat > 0) rc = timed_graph([&]() { return conv_tc_run(L, st); });

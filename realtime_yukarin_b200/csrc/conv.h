@@ -38,6 +38,10 @@ struct ConvLayer {
   // CTA-pair kernel (conv_tc2.cu): accumulator groups per pair (1 / 2 / 4 parity classes), N per group, half-tile weight map
   bool tc2 = false; int tc2_groups = 0, tc2_ng = 0;
   CUtensorMap tmB2;
+  // halo kernel (conv_tc3.cu): persistent, dynamically scheduled; tile = t3_mt stacked M tiles of t3_tile_w x t3_tile_h pixels
+  bool tc3 = false; int t3_tile_w = 0, t3_tile_h = 0, t3_mt = 0;
+  int* t3_ctr = nullptr;                   // tile counter (one zero-initialised int, owned by the plan; re-armed by the kernel itself)
+  CUtensorMap t3A0, t3A1, t3B, t3O;
 };
 
 // Weight repacking from the Chainer layouts the model files use:
@@ -58,5 +62,12 @@ int tc2_init();
 bool tc2_layer_config(const ConvLayer& L, int num_sms, int* groups, int* ng);     // needs L.tile_w / tile_h
 int tc2_layer_prepare(ConvLayer& L, PFN_cuTensorMapEncodeTiled_v12000 encode);
 int conv_tc2_run(const ConvLayer& L, cudaStream_t st, bool pdl);
+
+// conv_tc3.cu
+int tc3_init();
+bool tc3_layer_config(const ConvLayer& L, int num_sms, int* tile_w, int* tile_h, int* mt);
+int tc3_layer_prepare(ConvLayer& L, PFN_cuTensorMapEncodeTiled_v12000 encode);     // needs L.t3_ctr
+int conv_tc3_run(const ConvLayer& L, cudaStream_t st, bool pdl);
+bool tc_layer_wants_counter(const ConvLayer& L, int num_sms);                         // true: allocate L.t3_ctr before tc_layer_prepare
 
 }  // namespace ryk

@@ -130,8 +130,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
   pdl_wait();                       // the previous layer's outputs (our A operand) are complete from here on
   if (threadIdx.x == 0) TL(1);
 
-  if (warp == 4 && lane == 0) {
-    // ===== TMA producer =====
+  if (warp == 4) {
+    // ===== TMA producer (warp-uniform loop, one elected lane issues: see elect_one() in tc_ptx.cuh) =====
     for (int i = 0; i < my_chunks; ++i) {
       const int s = i % kStages;
       const uint32_t ph = (i / kStages) & 1;
@@ -146,35 +146,40 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
         ix = p.sw == 2 ? ox0 + tx - 1 + px : ox0;
         iy = p.sh == 2 ? oy0 + ty - 1 + py : oy0;
       }
-      mbar_expect_tx(&full_bar[s], kABytes + kBBytes);
-      if (cc < p.chunks0) tma_load_4d(smem_a + s * kABytes, &tmA0, &full_bar[s], cc * kBlockK, ix, iy, b);
-      else tma_load_4d(smem_a + s * kABytes, &tmA1, &full_bar[s], (cc - p.chunks0) * kBlockK, ix, iy, b);
-      tma_load_2d(smem_b + s * kBBytes, &tmB, &full_bar[s], kc * kBlockK, cls * p.Cout + n0);
+      if (elect_one()) {
+        mbar_expect_tx(&full_bar[s], kABytes + kBBytes);
+        if (cc < p.chunks0) tma_load_4d(smem_a + s * kABytes, &tmA0, &full_bar[s], cc * kBlockK, ix, iy, b);
+        else tma_load_4d(smem_a + s * kABytes, &tmA1, &full_bar[s], (cc - p.chunks0) * kBlockK, ix, iy, b);
+        tma_load_2d(smem_b + s * kBBytes, &tmB, &full_bar[s], kc * kBlockK, cls * p.Cout + n0);
+      }
     }
-  } else if (warp == 5 && lane == 0) {
-    // ===== MMA issuer =====
+  } else if (warp == 5) {
+    // ===== MMA issuer (warp-uniform loop, one elected lane issues) =====
     // instruction descriptor: D=F32, A=B=F16, both K-major, N = BLOCK_N, M = 128
     constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
     for (int i = 0; i < my_chunks; ++i) {
       const int s = i % kStages;
       const uint32_t ph = (i / kStages) & 1;
       mbar_wait(&full_bar[s], ph);
-      if (i == 0) TL(2);
+      if (i == 0 && lane == 0) TL(2);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint64_t adesc = make_sw128_desc(smem_u32(smem_a + s * kABytes));
       const uint64_t bdesc = make_sw128_desc(smem_u32(smem_b + s * kBBytes));
+      if (elect_one()) {
 #pragma unroll
-      for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-        // advance 32 bytes (16 fp16) inside the swizzle atom: +2 in the (addr >> 4) field
-        umma_f16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (i > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+          // advance 32 bytes (16 fp16) inside the swizzle atom: +2 in the (addr >> 4) field
+          umma_f16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
       }
-      umma_commit(&empty_bar[s]);
     }
-    umma_commit(tmem_full_bar);
-    TL(3);
+    if (elect_one()) umma_commit(tmem_full_bar);
+    if (lane == 0) TL(3);
   } else if (warp < 4) {
     // ===== epilogue =====
-    mbar_wait(tmem_full_bar, 0);
+    if (lane == 0) mbar_wait(tmem_full_bar, 0);        // one polling lane per warp
+    __syncwarp();
     if (threadIdx.x == 0) TL(4);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int row = warp * 32 + lane;                 // accumulator row == TMEM lane == pixel of the tile
@@ -602,6 +607,7 @@ int tc_init() {
     g_encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
   }
   if (tc2_init()) return -1;
+  if (tc3_init()) return -1;
   RYK_CUDA(cudaFuncSetAttribute(k_conv_tc<64, 6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<64, 6>()));
   RYK_CUDA(cudaFuncSetAttribute(k_conv_tc<128, 6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<128, 6>()));
   RYK_CUDA(cudaFuncSetAttribute(k_conv_tc<256, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<256, 4>()));
@@ -693,7 +699,13 @@ static void tc_geometry(const ConvLayer& L, int num_sms, int* tile_w, int* tile_
     ks = (total_chunks + cps - 1) / cps;                // every split owns at least one chunk
   }
   { ConvLayer T = L; T.tile_w = tw; T.tile_h = th; int g_, n_; if (tc2_layer_config(T, num_sms, &g_, &n_)) ks = 1; }   // pair kernel: no split-K
+  { int a_, b_, c_; if (tc3_layer_config(L, num_sms, &a_, &b_, &c_)) ks = 1; }                                             // halo kernel: no split-K
   *tile_w = tw; *tile_h = th; *block_n = bn; *ksplit = ks;
+}
+
+bool tc_layer_wants_counter(const ConvLayer& L, int num_sms) {
+  int a_, b_, c_;
+  return tc_layer_eligible(L) && tc3_layer_config(L, num_sms, &a_, &b_, &c_);
 }
 
 size_t tc_splitk_ws_bytes(const ConvLayer& L, int num_sms) {
@@ -719,6 +731,8 @@ int tc_layer_prepare(ConvLayer& L, int num_sms) {
   if (make_act_map(&L.tmO, L.out, L.Cout, L.Wout, L.Hout, L.B, L.tile_w, L.tile_h, L.transposed ? L.SW : 1, L.transposed ? L.SH : 1)) return -1;
   L.tc2 = tc2_layer_config(L, num_sms, &L.tc2_groups, &L.tc2_ng);
   if (L.tc2 && tc2_layer_prepare(L, g_encode)) return -1;
+  L.tc3 = !L.tc2 && tc3_layer_config(L, num_sms, &L.t3_tile_w, &L.t3_tile_h, &L.t3_mt);
+  if (L.tc3 && tc3_layer_prepare(L, g_encode)) return -1;
   RYK_CHECK(L.ksplit == 1 || L.splitk_ws != nullptr, "split-K layer without a workspace");
   if (L.ksplit > 1) {
     if (make_ws_map(&L.tmW, L.splitk_ws, L.Cout, L.Wout, L.Hout, L.B, L.ksplit, L.tile_w, L.tile_h, L.transposed ? L.SW : 1, L.transposed ? L.SH : 1)) return -1;
@@ -748,6 +762,7 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 int conv_tc_run(const ConvLayer& L, cudaStream_t st) {
   RYK_CHECK(L.tc_ready, "tc layer not prepared");
   if (L.tc2) return conv_tc2_run(L, st, pdl_enabled());
+  if (L.tc3) return conv_tc3_run(L, st, pdl_enabled());
   TcParams p;
   p.transposed = L.transposed; p.B = L.B; p.Hout = L.Hout; p.Wout = L.Wout; p.Cout = L.Cout;
   p.Hc = L.transposed ? L.Hin : L.Hout; p.Wc = L.transposed ? L.Win : L.Wout;

@@ -21,6 +21,16 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// One elected lane of a fully active warp.  The TMA / MMA issuing warps run their loops WARP-UNIFORMLY (all 32 lanes compute the same
+// coordinates and descriptors) and guard only the issuing instruction with elect_one(): ptxas then keeps the operands in uniform
+// registers.  Issuing from an `if (lane == 0)` region instead makes it wrap EVERY UTCHMMA / UTMALDG in an ELECT + 5 x R2UR.BROADCAST +
+// BRA.U.ANY loop (~100 clocks per instruction: the tensor pipe then runs at ~60 % behind its issuer -- profiles/r02_halo_timeline.txt).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }

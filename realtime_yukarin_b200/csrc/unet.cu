@@ -152,6 +152,7 @@ int unet_get_plan(Engine* e, UNet* n, int B, int H, int W, int precision, UNetPl
     if (precision == 1 && L.w_tc && tc_layer_eligible(L)) {
       size_t ws = tc_splitk_ws_bytes(L, num_sms);
       if (ws) { void* w = nullptr; if (alloc(ws, &w)) return -1; L.splitk_ws = (float*)w; }
+      if (tc_layer_wants_counter(L, num_sms)) { void* c = nullptr; if (alloc(16, &c)) return -1; L.t3_ctr = (int*)c; }
       if (tc_layer_prepare(L, num_sms)) return -1;
     }
   }

@@ -212,3 +212,57 @@ def test_production_layer_shapes(engine, case):
     # fp16 output rounding of |y| < 8 is 2^-9 * 4 = 8e-3; accumulation-order noise is ~1e-5
     assert err.max() < 1.2e-2, err.max()
     assert np.sqrt((err ** 2).mean()) < 1.5e-3
+
+
+HALO_CASES = [
+    # halo kernel (conv_tc3.cu), forced with RYK_TC3=2: transposed, B, H, W, C0, C1, Cout, act, MT, tile_w
+    (0, 1, 32, 64, 64, 0, 128, 1, 1, 8),        # conv: 16 x 32 outputs, one row of M tiles
+    (0, 1, 64, 64, 64, 0, 128, 1, 2, 8),        # conv, M = 256 CTA tiles (32 x 32 outputs)
+    (0, 2, 32, 32, 128, 0, 256, 1, 1, 16),      # conv, batch 2, two N tiles, 8 x 16 pixel tiles, two channel chunks
+    (0, 1, 48, 80, 64, 64, 128, 1, 2, 8),       # conv, two sources, ragged CTA tiles (24 x 40 outputs: 24 rows in 32-row tiles)
+    (0, 1, 80, 48, 64, 0, 128, 1, 1, 8),        # conv, 40 x 24 outputs: ragged 16-row tiles
+    (1, 1, 16, 32, 128, 0, 128, 2, 1, 8),       # deconv, one class per tile (N = 128)
+    (1, 2, 32, 16, 64, 64, 256, 2, 2, 8),       # deconv, batch 2, two sources, two N tiles, M = 256
+    (1, 1, 24, 32, 128, 128, 128, 2, 1, 16),    # deconv, d3-like class grid 24 x 32 with 8 x 16 tiles
+    (1, 1, 12, 24, 64, 0, 128, 2, 2, 8),        # deconv, ragged (12 rows in 32-row CTA tiles)
+    (1, 1, 16, 32, 128, 128, 64, 2, 1, 8),      # deconv Cout = 64: fused column classes (d6 family)
+    (1, 1, 32, 16, 64, 64, 64, 2, 2, 8),        # fused classes, M = 256
+    (1, 2, 20, 24, 64, 0, 64, 2, 2, 8),         # fused classes, ragged rows, batch 2
+    (1, 1, 16, 32, 64, 0, 64, 2, 1, 16),        # fused classes, 8 x 16 tiles
+]
+
+
+@pytest.mark.parametrize('case', HALO_CASES)
+def test_halo_kernel(engine, case):
+    """k_conv_halo: shared halo rows (two taps per A box), M = 128 / 256 per CTA, fused column classes, dynamic tile scheduler.
+    Same tolerance as the per-tap tcgen05 kernel, and the result must agree with it (same fp16 operands, fp32 accumulation)."""
+    import os
+    tr, B, H, W, C0, C1, Cout, act, mt, tw = case
+    rng = np.random.default_rng(sum(case) * 104729 + 7)
+    in0 = rng.standard_normal((B, H, W, C0)).astype(np.float32)
+    in1 = rng.standard_normal((B, H, W, C1)).astype(np.float32) if C1 else None
+    Cin = C0 + C1
+    shape = (Cin, Cout, 4, 4) if tr else (Cout, Cin, 4, 4)
+    Wt = (rng.standard_normal(shape) / np.sqrt(Cin * 16 / (4 if tr else 1))).astype(np.float32)
+    scale = rng.uniform(0.8, 1.2, Cout).astype(np.float32)
+    shift = (0.1 * rng.standard_normal(Cout)).astype(np.float32)
+    ref = _ref(in0, in1, Wt, scale, shift, tr, 4, 2, 1, act)
+    keys = ('RYK_TC3', 'RYK_TC3_MT', 'RYK_TC3_TW', 'RYK_TC3_DEPTH')
+    old = {k: os.environ.get(k) for k in keys}
+    try:
+        os.environ['RYK_TC3'] = '0'
+        base, _ = engine.test_conv_layer(in0, in1, Wt, scale, shift, tr, 4, 2, 1, act, use_tc=1)
+        os.environ.update(RYK_TC3='2', RYK_TC3_MT=str(mt), RYK_TC3_TW=str(tw))
+        for depth in (1, 0):
+            os.environ['RYK_TC3_DEPTH'] = str(depth)
+            got, ms = engine.test_conv_layer(in0, in1, Wt, scale, shift, tr, 4, 2, 1, act, use_tc=1, repeat=3)
+            err, err_base = np.abs(got - ref).max(), np.abs(base - ref).max()
+            print('halo kernel', case, 'depth', depth, 'max err', err, '(per-tap kernel', err_base, ') ms', ms)
+            assert err < 3e-2, err
+            assert np.abs(got - base).max() < 2e-2
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
