@@ -43,6 +43,8 @@ def lib():
         _lib.wo_synth_add.argtypes = [ctypes.c_void_p, c_double_p, ctypes.c_int, c_float_p, c_float_p]
         _lib.wo_synth_synthesis2.argtypes = [ctypes.c_void_p, c_double_p]
         _lib.wo_synth_destroy.argtypes = [ctypes.c_void_p]
+        _lib.wo_synth_set_mode.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        _lib.wo_synth_skip_randn.argtypes = [ctypes.c_void_p, ctypes.c_longlong]
         _lib.wo_synth_pulse_count.argtypes = [ctypes.c_void_p]
         _lib.wo_synth_pulse_count.restype = ctypes.c_longlong
         _lib.wo_synth_get_pulses.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, c_ll_p, c_double_p, c_int_p]
@@ -165,10 +167,19 @@ class RealtimeSynthesizer:
     """Restatement of world4py's WorldSynthesizer + _InitializeSynthesizer/_AddParameters/_Synthesis2
     (call sites: realtime_voice_conversion/yukarin_wrapper/vocoder.py:79-103)."""
 
-    def __init__(self, fs, frame_period, fft_size, buffer_size, ring_frames=4096):
+    CANON_RANDN, CANON_PHASE = 1, 2
+
+    def __init__(self, fs, frame_period, fft_size, buffer_size, ring_frames=4096, canonical: int = 0):
+        """canonical: bit 0 = WORLD's sequential randn() consumption, bit 1 = WORLD's single running-sum phase (DECIDE 10 / 11 undone);
+        0 (default) = the variants the CUDA path reproduces bit for bit.  Only tests/test_oracle_canonical.py uses non-zero values."""
         self.buffer_size = buffer_size
         self.fft_size = fft_size
         self._h = lib().wo_synth_create(int(fs), float(frame_period), int(fft_size), int(buffer_size), int(ring_frames))
+        if canonical:
+            lib().wo_synth_set_mode(self._h, int(canonical))
+
+    def skip_randn(self, n: int):
+        lib().wo_synth_skip_randn(self._h, int(n))
 
     def add_parameters(self, f0, sp, ap) -> int:
         f0 = _f64(np.asarray(f0).ravel())

@@ -758,6 +758,7 @@ typedef struct {
   double *dc_remover;       /* [fft/2] */
   wo_rng rng;
   long long rng_pos;        /* stream position of the next draw */
+  int mode;                 /* WO_CANON_* bits: 0 = the GPU-friendly DECIDE 10 / 11 variants (default), see wo_synth_set_mode */
 } wo_synth;
 
 void *wo_synth_create(int fs, double frame_period_ms, int fft_size, int buffer_size, int ring_frames) {
@@ -787,6 +788,17 @@ void *wo_synth_create(int fs, double frame_period_ms, int fft_size, int buffer_s
   wo_rng_seed(&s->rng);
   return s;
 }
+
+/* Canonical-WORLD switches, used ONLY to quantify how far DECIDE 10 / 11 move the oracle from synthesisrealtime.cpp
+ * (tests/test_oracle_canonical.py):
+ *   bit 0 (WO_CANON_RANDN): randn() consumed sequentially, noise_size draws per pulse and nothing skipped, as GetNoiseSpectrum does
+ *                           (instead of addressing the stream by the pulse's absolute sample position);
+ *   bit 1 (WO_CANON_PHASE): total phase as ONE running sum over the samples (instead of the fixed 256-sample blocked order). */
+#define WO_CANON_RANDN 1
+#define WO_CANON_PHASE 2
+void wo_synth_set_mode(void *h, int mode) { ((wo_synth *)h)->mode = mode; }
+/* discard n draws (tests: the position-addressed stream == the sequential stream advanced to the first pulse's sample index) */
+void wo_synth_skip_randn(void *h, long long n) { wo_synth *s = (wo_synth *)h; for (long long i = 0; i < n; ++i) wo_randn(&s->rng); }
 
 void wo_synth_destroy(void *h) {
   wo_synth *s = (wo_synth *)h;
@@ -852,6 +864,10 @@ int wo_synth_add(void *h, const double *f0, int n, const float *sp, const float 
     double tp0 = hf == 1 ? s->handoff_phase : 2.0 * WO_PI * if0[0] / s->fs;
     const int BLK = 256;
     double base = tp0;
+    if (s->mode & WO_CANON_PHASE) {      /* WORLD: total_phase[i] = total_phase[i - 1] + 2 pi f0 / fs, one running sum from the hand-off phase */
+      tp[0] = tp0;
+      for (int i = 1; i < np_; ++i) tp[i] = tp[i - 1] + 2.0 * WO_PI * if0[i - hf] / s->fs;
+    } else
     for (int b0 = 0; b0 < np_; b0 += BLK) {
       int b1 = b0 + BLK < np_ ? b0 + BLK : np_;
       double local = 0.0;
@@ -910,7 +926,7 @@ static double safe_ap(double x) { return dmax(0.001, dmin(0.999999999999, x)); }
 /* one pulse -> impulse response [fft_size] */
 static void synth_one_pulse(wo_synth *s, long long p, int noise_size, double *response) {
   long long qpos = s->p_index[p % s->cap_pulses] < 0 ? 0 : s->p_index[p % s->cap_pulses];
-  while (s->rng_pos < qpos) { wo_randn(&s->rng); s->rng_pos++; }
+  if (!(s->mode & WO_CANON_RANDN)) while (s->rng_pos < qpos) { wo_randn(&s->rng); s->rng_pos++; }
   int n = s->fft_size, nb = n / 2 + 1;
   int slot = (int)(p % s->cap_pulses);
   double t = s->p_time[slot];

@@ -72,7 +72,7 @@ def install(force: bool = True) -> None:
     _module(f'{rvc}.yukarin_wrapper.acoustic_feature_wrapper', AcousticFeatureWrapper=feature.AcousticFeatureWrapper,
             CrepeAcousticFeatureWrapper=vocoder.CrepeAcousticFeatureWrapper)
     _module(f'{rvc}.worker')
-    _module(f'{rvc}.worker.utility', Item=worker.Item)
+    _module(f'{rvc}.worker.utility', Item=worker.Item, init_logger=worker.init_logger)
     _module(f'{rvc}.converter')
     _module(f'{rvc}.converter.yukarin_converter', YukarinConverter=converter.YukarinConverter)
 

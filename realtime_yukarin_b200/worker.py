@@ -15,6 +15,9 @@ index (run.py:152-199).  Here the three stages are CUDA streams of one device-re
 Start offsets: the reference starts every worker at `start_time = extra_time` (encode_worker.py:31); the session
 pre-fills its windows with silence for exactly those offsets.
 """
+import logging
+import os
+import time
 from collections import deque
 from typing import Any, Deque, List, Optional, Tuple
 
@@ -30,6 +33,23 @@ class Item(object):
     def __init__(self, item: Any, index: int):
         self.item = item
         self.index = index
+
+
+def init_logger(logger=None, filename: Optional[str] = None):
+    """worker/utility.py:16-29: level from $LOG_LEVEL (default WARNING), '%(levelname)s\\t%(name)s\\t%(asctime)s\\t%(message)s' on the
+    console and -- when `filename` is given (the reference always writes ./log.txt) -- to that file."""
+    if logger is None:
+        logger = logging.getLogger()
+    fmt = logging.Formatter('%(levelname)s\t%(name)s\t%(asctime)s\t%(message)s')
+    logger.setLevel(os.getenv('LOG_LEVEL', 'WARNING'))
+    if filename:
+        handler = logging.FileHandler(filename)
+        handler.setFormatter(fmt)
+        logger.addHandler(handler)
+    handler = logging.StreamHandler()
+    handler.setFormatter(fmt)
+    logger.addHandler(handler)
+    return logger
 
 
 class OutputReblocker(object):
@@ -76,7 +96,20 @@ class RealtimePipeline(object):
             threshold_db=float(config.input_silent_threshold), vocoder_buffer_size=int(config.vocoder_buffer_size))
         assert config.input_rate == config.output_rate, 'the accelerated path runs analysis and synthesis at one rate'
         self.depth = max(1, min(int(depth), 5))
+        # per-item stage timing at DEBUG, as the reference's workers log it (encode_worker.py:34,44, convert_worker.py:47,59,
+        # decode_worker.py:42,66: `logger.debug(f'{item.index}: {time.time() - start}')` on loggers 'encode' / 'convert' / 'decode').
+        # Here the stages are CUDA streams, so the figures are device times between CUDA events (ryk_session_stage_times).
+        self._loggers = {k: logging.getLogger(k) for k in ('encode', 'convert', 'decode')}
+        self._timing = any(lg.isEnabledFor(logging.DEBUG) for lg in self._loggers.values())
+        if self._timing:
+            prev = os.environ.get('RYK_STAGE_TIMES')
+            os.environ['RYK_STAGE_TIMES'] = '1'
         self._sid = self.engine.session_create(cfg)
+        if self._timing:
+            if prev is None:
+                os.environ.pop('RYK_STAGE_TIMES', None)
+            else:
+                os.environ['RYK_STAGE_TIMES'] = prev
         # capacity of one step's synthesizer output, as the session sizes it: (decode-window samples // block + 4) blocks
         rate = round(1000 / float(config.frame_period))
         hop = round(config.output_rate * float(config.frame_period) / 1000)
@@ -84,7 +117,7 @@ class RealtimePipeline(object):
         n_out_cap = (td * hop // config.vocoder_buffer_size + 4) * config.vocoder_buffer_size
         self._scratch = numpy.empty(n_out_cap, dtype=numpy.float64)
         self._rid = self.engine.reblock_create(config.out_audio_chunk, n_out_cap, float(config.output_silent_threshold))
-        self._inflight: Deque[Tuple[Item, int, int]] = deque()      # (item, session ticket, re-blocker ticket)
+        self._inflight: Deque[Tuple[Item, int, int, float]] = deque()      # (item, session ticket, re-blocker ticket, host time of put)
         self._done: Deque[Item] = deque()
         # audio-loop state (run.py:155-157)
         self._index_input = 0
@@ -97,14 +130,29 @@ class RealtimePipeline(object):
             self._finish_one()
         ts = self.engine.session_submit(self._sid, numpy.asarray(item.item, dtype=numpy.float32))
         tr = self.engine.reblock_push_device(self._rid, self._sid)        # consumes the step's blocks in place, on its decode stream
-        self._inflight.append((item, ts, tr))
+        self._inflight.append((item, ts, tr, time.time()))
 
     def _finish_one(self) -> None:
-        item, ts, tr = self._inflight.popleft()
+        item, ts, tr, t_put = self._inflight.popleft()
         self.engine.session_collect(self._sid, ts, self._scratch)         # the raw blocks are not needed on the host
         _, chunk, _ = self.engine.reblock_collect(self._rid, tr)
         item.item = chunk                                                 # None: no chunk yet, or a silent one
         self._done.append(item)
+        if self._timing:
+            self._log_item(item.index, t_put)
+
+    def _log_item(self, index: int, t_put: float) -> None:
+        """DEBUG lines in the reference's format, one per stage logger: `<index>: <seconds>`; device time of the newest step's
+        analysis (encode), gate + stage 1 + stage 2 (convert) and synthesis (decode), plus the host-side put -> collect latency."""
+        try:
+            st, en = self.engine.session_stage_times(self._sid)
+            d = (en[-1] - st[-1]) * 1e-3
+            enc, conv, dec = d[1], d[0] + d[2] + d[3], d[4]
+        except Exception:                                                 # engines without stage timing (test doubles)
+            enc = conv = dec = float('nan')
+        self._loggers['encode'].debug(f'{index}: {enc}')
+        self._loggers['convert'].debug(f'{index}: {conv}')
+        self._loggers['decode'].debug(f'{index}: {dec} (put -> collect on the host: {time.time() - t_put})')
 
     # ---- queue_output_wave.get / get_nowait -----------------------------------------------------------------
     def get(self) -> Item:
@@ -118,7 +166,7 @@ class RealtimePipeline(object):
         """Move every in-flight item the device has already finished to `_done` without blocking (cudaEventQuery on the
         step's decode event and on the re-blocker event).  Chunks finish in submission order, so stop at the first busy one."""
         while self._inflight:
-            _, ts, tr = self._inflight[0]
+            _, ts, tr, _t = self._inflight[0]
             if not (self.engine.session_poll(self._sid, ts) and self.engine.reblock_poll(self._rid, tr)):
                 break
             self._finish_one()

@@ -326,3 +326,37 @@ def test_run_module_wav_mode_matches_the_audio_loop(tmp_path, small_models):
         assert np.array_equal(got, ref) and np.abs(got).max() > 0
     finally:
         eng_mod.set_default_engine(None)
+
+
+def test_pipeline_logs_per_item_stage_times_at_debug(small_models, caplog):
+    """SURVEY section 5 "Metrics/logging": the reference's workers log `<index>: <seconds>` per item at DEBUG on the loggers
+    'encode' / 'convert' / 'decode' (worker/encode_worker.py:44, convert_worker.py:59, decode_worker.py:66); init_logger sets the
+    level from $LOG_LEVEL (worker/utility.py:16-29)."""
+    import logging
+    from realtime_yukarin_b200.config import Config, VocodeMode
+    from realtime_yukarin_b200.worker import RealtimePipeline, init_logger
+    fake = OracleEngine(small_models['stage1_model_path'], small_models['stage2_model_path'])
+    cfg = Config(input_device_name=None, output_device_name=None, input_rate=24000, output_rate=24000, frame_period=5.0, buffer_time=0.3,
+                 extract_f0_mode=VocodeMode.WORLD, vocoder_buffer_size=1024, input_scale=1.0, output_scale=1.0, input_silent_threshold=60.0,
+                 output_silent_threshold=80.0, encode_extra_time=0.0, convert_extra_time=0.5, decode_extra_time=0.0,
+                 **{k: small_models[k] for k in ('input_statistics_path', 'target_statistics_path', 'stage1_model_path', 'stage1_config_path',
+                                                 'stage2_model_path', 'stage2_config_path')})
+    lg = logging.getLogger('rykprobe')
+    n_handlers = len(lg.handlers)
+    init_logger(lg)                                         # console handler, level from $LOG_LEVEL (WARNING by default), no file
+    assert len(lg.handlers) == n_handlers + 1 and lg.level == logging.WARNING
+    x = synthetic.synthetic_speech(0.7, stream=3)
+    n = cfg.in_audio_chunk
+    with caplog.at_level(logging.DEBUG):
+        for name in ('encode', 'convert', 'decode'):
+            logging.getLogger(name).setLevel(logging.DEBUG)
+        try:
+            pipe = RealtimePipeline(cfg, engine=fake, depth=2)
+            pipe.process(x[:n]); pipe.process(x[n:2 * n])
+            pipe.close()
+        finally:
+            for name in ('encode', 'convert', 'decode'):
+                logging.getLogger(name).setLevel(logging.NOTSET)
+    for name in ('encode', 'convert', 'decode'):
+        msgs = [r.getMessage() for r in caplog.records if r.name == name and r.levelno == logging.DEBUG]
+        assert len(msgs) == 2 and msgs[0].startswith('0: ') and msgs[1].startswith('1: '), (name, msgs)
