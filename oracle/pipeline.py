@@ -117,6 +117,7 @@ class StreamOracle:
         self.e_conv = round(extra[1] * self.rate)
         self.e_dec = round(extra[2] * self.rate)
         self.k = 0
+        self.wave_base = self.enc_base = self.conv_base = 0       # rows already dropped from the front of the histories (long soak runs)
         self.wave_hist = np.zeros(0, np.float32)
         nb = cfg.fft_length // 2 + 1
         self.enc_hist = dict(f0=np.zeros((0, 1), np.float32), ap=np.zeros((0, nb), np.float32),
@@ -141,7 +142,7 @@ class StreamOracle:
         assert len(chunk) == self.n_wave
         # ---- encode ----
         self.wave_hist = np.concatenate([self.wave_hist, np.asarray(chunk, np.float32)])
-        win = self._window(self.wave_hist, k * self.n_wave - 2 * self.e_wave, self.n_wave + 2 * self.e_wave, 0.0)
+        win = self._window(self.wave_hist, k * self.n_wave - 2 * self.e_wave - self.wave_base, self.n_wave + 2 * self.e_wave, 0.0)
         f = extract_features(win, cfg)
         pad = round(self.extra[0] * self.rate)
         aligned = win
@@ -153,7 +154,7 @@ class StreamOracle:
         self.enc_hist['wave'] = np.concatenate([self.enc_hist['wave'], aligned])
         # ---- convert ----
         Tw = self.n_feat + 2 * self.e_conv
-        first = k * self.n_feat - 2 * self.e_conv
+        first = k * self.n_feat - 2 * self.e_conv - self.enc_base
         silent_mc = np.zeros((1, cfg.order + 1), np.float32)
         silent_mc[0, 0] = SILENT_MC0
         wfeat = dict(f0=self._window(self.enc_hist['f0'], first, Tw, 0.0), ap=self._window(self.enc_hist['ap'], first, Tw, 0.0),
@@ -166,7 +167,7 @@ class StreamOracle:
             self.conv_hist[kk] = np.concatenate([self.conv_hist[kk], conv[kk]])
         # ---- decode ----
         Td = self.n_feat + 2 * self.e_dec
-        firstd = k * self.n_feat - 2 * self.e_dec
+        firstd = k * self.n_feat - 2 * self.e_dec - self.conv_base
         df0 = self._window(self.conv_hist['f0'], firstd, Td, 0.0)
         dsp = self._window(self.conv_hist['sp'], firstd, Td, 0.0)
         dap = self._window(self.conv_hist['ap'], firstd, Td, 0.0)
@@ -175,6 +176,21 @@ class StreamOracle:
         y[np.isnan(y)] = 0
         self.k += 1
         self.last = dict(encoded=f, converted=conv)
+        # drop history no window can reach any more (rows before the next step's first row); negative window indices stay "silent"
+        keep_w = (self.k * self.n_wave - 2 * self.e_wave) - self.wave_base
+        if keep_w > 8 * (self.n_wave + 2 * self.e_wave):
+            self.wave_hist = self.wave_hist[keep_w:]; self.wave_base += keep_w
+        keep_e = (self.k * self.n_feat - 2 * self.e_conv) - self.enc_base
+        if keep_e > 8 * (self.n_feat + 2 * self.e_conv):
+            for kk in ('f0', 'ap', 'mc', 'voiced'):
+                self.enc_hist[kk] = self.enc_hist[kk][keep_e:]
+            self.enc_hist['wave'] = self.enc_hist['wave'][keep_e * hop:]
+            self.enc_base += keep_e
+        keep_c = (self.k * self.n_feat - 2 * self.e_dec) - self.conv_base
+        if keep_c > 8 * (self.n_feat + 2 * self.e_dec):
+            for kk in ('f0', 'ap', 'sp'):
+                self.conv_hist[kk] = self.conv_hist[kk][keep_c:]
+            self.conv_base += keep_c
         return y
 
 

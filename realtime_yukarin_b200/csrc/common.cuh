@@ -75,21 +75,34 @@ __device__ inline double block_sum(double v, double* scratch) {
 
 // In-place inclusive prefix sum over smem array a[0..n) (doubles). scratch >= blockDim.x doubles.
 __device__ inline void block_inclusive_scan(double* a, int n, double* scratch) {
-  int T = blockDim.x;
+  const int T = blockDim.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (T + 31) >> 5;
   int per = (n + T - 1) / T;
   int lo = threadIdx.x * per, hi = min(lo + per, n);
   double s = 0.0;
   for (int i = lo; i < hi; ++i) { s += a[i]; a[i] = s; }
-  scratch[threadIdx.x] = s;
-  __syncthreads();
-  // exclusive scan of partial sums (T <= 1024): simple Hillis-Steele on scratch
-  for (int off = 1; off < T; off <<= 1) {
-    double v = threadIdx.x >= off ? scratch[threadIdx.x - off] : 0.0;
-    __syncthreads();
-    scratch[threadIdx.x] += v;
-    __syncthreads();
+  // scan of the per-thread sums: shuffles inside a warp, one pass over the <= 32 warp totals (3 block barriers; the Hillis-Steele
+  // form over all threads took 2 log2(T) + 2 of them, and these per-frame kernels are chains of barriers)
+  double incl = s;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const double t = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += t;
   }
-  double base = threadIdx.x > 0 ? scratch[threadIdx.x - 1] : 0.0;
+  double excl = __shfl_up_sync(0xffffffffu, incl, 1);      // exclusive prefix inside the warp (exact: no incl - s cancellation)
+  if (lane == 0) excl = 0.0;
+  if (lane == 31) scratch[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    double t = lane < nw ? scratch[lane] : 0.0;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const double u = __shfl_up_sync(0xffffffffu, t, off);
+      if (lane >= off) t += u;
+    }
+    if (lane < nw) scratch[lane] = t;
+  }
+  __syncthreads();
+  const double base = excl + (w > 0 ? scratch[w - 1] : 0.0);
   for (int i = lo; i < hi; ++i) a[i] += base;
   __syncthreads();
 }

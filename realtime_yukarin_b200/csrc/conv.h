@@ -56,6 +56,7 @@ int tc_init();                                           // resolves cuTensorMap
 int tc_layer_prepare(ConvLayer& L, int num_sms);         // builds tensor maps, picks tiles / split-K (needs final pointers)
 int conv_tc_run(const ConvLayer& L, cudaStream_t st);
 size_t tc_splitk_ws_bytes(const ConvLayer& L, int num_sms);
+void tc_force_pdl(int v);                                // -1 environment default, 0 / 1 forced
 
 // conv_tc2.cu
 int tc2_init();

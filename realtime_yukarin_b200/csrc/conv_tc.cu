@@ -614,6 +614,8 @@ int tc_init() {
   RYK_CUDA(cudaFuncSetAttribute(k_conv_tc<64, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<64, 4>()));
   RYK_CUDA(cudaFuncSetAttribute(k_conv_tc<128, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<128, 3>()));
   RYK_CUDA(cudaFuncSetAttribute(k_conv_tc<256, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<256, 2>()));
+  RYK_CUDA(cudaFuncSetAttribute(k_conv_tc<128, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<128, 2>()));
+  RYK_CUDA(cudaFuncSetAttribute(k_conv_tc<64, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<64, 3>()));
   RYK_CUDA(cudaFuncSetAttribute(k_conv_tc_persist<64, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcp_smem_bytes<64, 8, 1>()));
   RYK_CUDA(cudaFuncSetAttribute(k_conv_tc_persist<128, 6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcp_smem_bytes<128, 6, 1>()));
   RYK_CUDA(cudaFuncSetAttribute(k_conv_tc_persist<256, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcp_smem_bytes<256, 3, 1>()));
@@ -679,7 +681,7 @@ static void tc_geometry(const ConvLayer& L, int num_sms, int* tile_w, int* tile_
   int tw = pow2_floor(Wc < kBlockM ? Wc : kBlockM);
   int th = kBlockM / tw;
   int bn = L.Cout >= 256 ? 256 : (L.Cout >= 128 ? 128 : 64);
-  if ((tc_variant() == 1 || tc_variant() == 2) && bn == 256) bn = 128;   // non-persistent 2-CTAs/SM kernels: N <= 128 tiles (the epilogue staging must fit the stage buffers)
+  if ((tc_variant() == 1 || tc_variant() == 2 || tc_variant() == 6) && bn == 256) bn = 128;   // non-persistent 2-CTAs/SM kernels: N <= 128 tiles (the epilogue staging must fit the stage buffers)
   if (tc_variant() == 4 && bn == 256) bn = 128;        // variant 4: persistent with N <= 128
   int classes = L.transposed ? L.SH * L.SW : 1;
   int tiles_mn_ = L.B * ((Wc + tw - 1) / tw) * ((Hc + th - 1) / th);
@@ -688,7 +690,7 @@ static void tc_geometry(const ConvLayer& L, int num_sms, int* tile_w, int* tile_
   int ntaps = L.transposed ? (L.KH / L.SH) * (L.KW / L.SW) : L.KH * L.KW;
   int total_chunks = ntaps * (L.C0 + L.C1) / kBlockK;
   int ks = 1;
-  int slots = num_sms * ((tc_variant() == 0 || tc_variant() >= 3) ? 1 : 2);
+  int slots = num_sms * (tc_variant() == 6 ? 3 : ((tc_variant() == 0 || tc_variant() >= 3) ? 1 : 2));
   if (tiles < slots) {
     ks = slots / tiles;
     static int min_chunks = -1;
@@ -743,10 +745,12 @@ int tc_layer_prepare(ConvLayer& L, int num_sms) {
 
 // Launch with the programmatic-stream-serialization attribute (see pdl_trigger / pdl_wait); RYK_NO_PDL=1 falls back to
 // plain stream order (the device-side instructions are then no-ops).
+static int g_pdl_force = -1;                       // -1: environment decides; 0 / 1: forced (captures that must not carry programmatic edges)
+void tc_force_pdl(int v) { g_pdl_force = v; }
 static bool pdl_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("RYK_NO_PDL"); v = (e && atoi(e) != 0) ? 0 : 1; }
-  return v != 0;
+  return g_pdl_force >= 0 ? g_pdl_force != 0 : v != 0;
 }
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
@@ -788,7 +792,10 @@ int conv_tc_run(const ConvLayer& L, cudaStream_t st) {
   size_t out_elems = (size_t)L.B * L.Hout * L.Wout * L.Cout;
   dim3 grid(L.B * p.tiles_w * p.tiles_h, L.Cout / L.block_n, classes * L.ksplit);
   const int variant = tc_variant();
-  if (variant >= 3) {
+  if (variant == 6) {
+    if (L.block_n == 128) RYK_CUDA(launch_pdl(k_conv_tc<128, 2, 3>, grid, dim3(kTcThreads), tc_smem_bytes<128, 2>(), st, L.tmA0, L.tmA1, L.tmB, L.tmO, L.tmW, p));
+    else RYK_CUDA(launch_pdl(k_conv_tc<64, 3, 3>, grid, dim3(kTcThreads), tc_smem_bytes<64, 3>(), st, L.tmA0, L.tmA1, L.tmB, L.tmO, L.tmW, p));
+  } else if (variant >= 3) {
     int num_sms = 148;
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, 0);
     const int tiles_mn = L.B * p.tiles_w * p.tiles_h, n_tiles_n = L.Cout / L.block_n;

@@ -25,20 +25,45 @@ __device__ inline void fft_smem(double2* a, int n, int log2n, int sign, const do
     if (j > i) { double2 t = a[i]; a[i] = a[j]; a[j] = t; }
   }
   __syncthreads();
-  for (int s = 1; s <= log2n; ++s) {
-    int half = 1 << (s - 1);
-    int tstep = kTwiddleN >> s;          // kTwiddleN / len
+  // Stages are taken two at a time: a thread owns the quad {i, i + h, i + 2h, i + 3h} (h = half length of stage s), does stage s on
+  // (i, i + h) and (i + 2h, i + 3h) and stage s + 1 on (i, i + 2h) and (i + h, i + 3h) in registers -- the SAME butterflies with the
+  // SAME table twiddles in the same order as the one-stage-per-barrier form (results are bit-identical), at half the block barriers
+  // and half the shared-memory round trips.  These kernels are latency chains of barriers: k_d4c ran ~300 of them per frame.
+  auto bfly = [&](double2& va, double2& vb, const double2 w) {
+    const double wi = sign < 0 ? w.y : -w.y;
+    const double xr = vb.x * w.x - vb.y * wi;
+    const double xi = vb.x * wi + vb.y * w.x;
+    vb = make_double2(va.x - xr, va.y - xi);
+    va = make_double2(va.x + xr, va.y + xi);
+  };
+  int s = 1;
+  for (; s + 1 <= log2n; s += 2) {
+    const int half = 1 << (s - 1);
+    const int t1 = kTwiddleN >> s, t2 = kTwiddleN >> (s + 1);
+    for (int j = threadIdx.x; j < (n >> 2); j += T) {
+      const int k = j & (half - 1);
+      const int i0 = ((j >> (s - 1)) << (s + 1)) + k;
+      const int i1 = i0 + half, i2 = i0 + 2 * half, i3 = i0 + 3 * half;
+      double2 a0 = a[i0], a1 = a[i1], a2 = a[i2], a3 = a[i3];
+      const double2 w1 = __ldg(&tw[k * t1]);
+      bfly(a0, a1, w1);
+      bfly(a2, a3, w1);
+      bfly(a0, a2, __ldg(&tw[k * t2]));
+      bfly(a1, a3, __ldg(&tw[(k + half) * t2]));
+      a[i0] = a0; a[i1] = a1; a[i2] = a2; a[i3] = a3;
+    }
+    __syncthreads();
+  }
+  if (s == log2n) {
+    const int half = 1 << (s - 1);
+    const int tstep = kTwiddleN >> s;          // kTwiddleN / len
     for (int j = threadIdx.x; j < (n >> 1); j += T) {
-      int k = j & (half - 1);
-      int ia = ((j >> (s - 1)) << s) + k;
-      int ib = ia + half;
-      double2 w = __ldg(&tw[k * tstep]);
-      double wi = sign < 0 ? w.y : -w.y;
-      double2 vb = a[ib], va = a[ia];
-      double xr = vb.x * w.x - vb.y * wi;
-      double xi = vb.x * wi + vb.y * w.x;
-      a[ib] = make_double2(va.x - xr, va.y - xi);
-      a[ia] = make_double2(va.x + xr, va.y + xi);
+      const int k = j & (half - 1);
+      const int ia = ((j >> (s - 1)) << s) + k;
+      const int ib = ia + half;
+      double2 va = a[ia], vb = a[ib];
+      bfly(va, vb, __ldg(&tw[k * tstep]));
+      a[ia] = va; a[ib] = vb;
     }
     __syncthreads();
   }

@@ -79,6 +79,10 @@ struct Session {
   bool merge_s2 = false;           // this step: stage-2 prologue + 16 layers + epilogue replayed as ONE graph (no profiling events in between)
   bool host_prof = false; double host_wait_us = 0.0, host_total_us = 0.0; long long host_steps = 0;   // RYK_HOST_PROF=1
   std::map<int, StageGraph> graphs;
+  // stage 1 with the padded-length bucket chosen ON THE DEVICE: one graph per chunk parity = {k_set_bucket -> SWITCH conditional node
+  // whose body i is the stage-1 sequence for the padded length 128 i (0: no effective frame)}; no host sync on the submit path
+  cudaGraphExec_t s1_switch[2] = {nullptr, nullptr}; long long s1_switch_launches[2][16]; int s1_buckets = 0; int last_bucket = 0;
+  bool device_buckets = false;
   Synth* synth = nullptr;
   DioPlan* dio[2] = {nullptr, nullptr};     // one analysis plan per chunk parity
   std::vector<void*> allocs, pinned;
@@ -231,6 +235,7 @@ static void session_free(Session* s) {
   for (int i = 0; i < kRing; ++i)
     for (cudaEvent_t ev : {s->ev_gate[i], s->ev_pro[i], s->ev_count[i], s->ev_enc[i], s->ev_cslide[i], s->ev_s1[i], s->ev_conv[i], s->ev_dslide[i], s->ev_dec[i]}) if (ev) cudaEventDestroy(ev);
   for (auto& kv : s->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  for (int b = 0; b < 2; ++b) if (s->s1_switch[b]) cudaGraphExecDestroy(s->s1_switch[b]);
   if (s->stage_times) for (int a = 0; a < 5; ++a) for (int w = 0; w < 2; ++w) for (int i = 0; i < kRing; ++i) cudaEventDestroy(s->tev[a][w][i]);
   for (void* p : s->allocs) cudaFree(p);
   for (void* p : s->pinned) cudaFreeHost(p);
@@ -340,6 +345,64 @@ static int run_stage(Engine* e, Session* s, int key, cudaStream_t st, F&& body, 
 enum { G_E1 = 0, G_E2 = 2, G_S1 = 4 /* + 2 * bucket + parity; bucket 0 = no effective frame, else padded length / 128 (1..15) */,
        G_S2A = 40, G_S2B = 42, G_S2C = 44, G_D = 46, G_D1 = 48, G_S2M = 50 };
 
+// value of the SWITCH node = padded effective length / 128 (count[1] / 128), 0 when no frame is effective (count[0] == 0)
+__global__ void k_set_bucket(cudaGraphConditionalHandle handle, const int* __restrict__ count, int n_buckets) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int v = count[0] > 0 ? count[1] / 128 : 0;
+    if (v < 0 || v >= n_buckets) v = n_buckets - 1;        // cannot happen (count[1] <= Tw + 128); keeps the node in range
+    cudaGraphSetConditional(handle, (unsigned)v);
+  }
+}
+
+static int stage1_enqueue(Engine* e, Session* s, int b, int tp1, bool capture_only);
+
+// Build the per-parity stage-1 graph with a device-side switch over the padded-length buckets (CUDA conditional nodes, 12.8+).
+static int stage1_build_switch(Engine* e, Session* s, int b) {
+  const int n_buckets = (s->Tw + (128 - s->Tw % 128)) / 128 + 1;
+  RYK_CHECK(n_buckets <= 16, "window too long for the stage-1 graph table");
+  s->s1_buckets = n_buckets;
+  cudaGraph_t graph = nullptr;
+  RYK_CUDA(cudaGraphCreate(&graph, 0));
+  cudaGraphConditionalHandle handle;
+  RYK_CUDA(cudaGraphConditionalHandleCreate(&handle, graph, 0, cudaGraphCondAssignDefault));
+  // node 1: the setter
+  cudaGraphNode_t set_node = nullptr;
+  {
+    cudaKernelNodeParams kp = {};
+    const int* cnt = s->d_count[b];
+    int nb_ = n_buckets;
+    void* args[3] = {(void*)&handle, (void*)&cnt, (void*)&nb_};
+    kp.func = (void*)k_set_bucket; kp.gridDim = dim3(1); kp.blockDim = dim3(32); kp.sharedMemBytes = 0; kp.kernelParams = args; kp.extra = nullptr;
+    RYK_CUDA(cudaGraphAddKernelNode(&set_node, graph, nullptr, 0, &kp));
+  }
+  // node 2: SWITCH
+  cudaGraphNodeParams cp = {};
+  cp.type = cudaGraphNodeTypeConditional;
+  cp.conditional.handle = handle;
+  cp.conditional.type = cudaGraphCondTypeSwitch;
+  cp.conditional.size = (unsigned)n_buckets;
+  cudaGraphNode_t sw = nullptr;
+  RYK_CUDA(cudaGraphAddNode(&sw, graph, &set_node, 1, &cp));
+  const bool saved = s->use_graphs;
+  for (int i = 0; i < n_buckets; ++i) {
+    cudaGraph_t body = cp.conditional.phGraph_out[i];
+    const long long before = e->launches;
+    RYK_CUDA(cudaStreamBeginCaptureToGraph(s->sC, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    s->use_graphs = false;                               // run the body's kernels straight into the capture
+    int rc = stage1_enqueue(e, s, b, i * 128, false);
+    s->use_graphs = saved;
+    cudaGraph_t out = nullptr;
+    cudaError_t err = cudaStreamEndCapture(s->sC, &out);
+    if (rc) return rc;
+    RYK_CUDA(err);
+    s->s1_switch_launches[b][i] = e->launches - before + 1;     // + the setter
+    e->launches = before;
+  }
+  RYK_CUDA(cudaGraphInstantiate(&s->s1_switch[b], graph, 0));
+  RYK_CUDA(cudaGraphDestroy(graph));
+  return 0;
+}
+
 // Stage 1 of a chunk of parity b: slide the feature window, (gather ->) 1-D U-Net at padded length tp1 (0: no effective frame,
 // voice_changer.py:32-35 skips the net) -> scatter into the silent template + f0 map, mc2sp.  One graph per (tp1 bucket, parity);
 // all of them are captured when the session is created so that no chunk ever pays for a capture in the middle of a stream.
@@ -425,15 +488,24 @@ static int session_front(Engine* e, Session* s, const float* d_chunk_user) {
     RYK_CUDA(cudaStreamWaitEvent(s->sC, s->ev_dslide[(k - 2) % kRing], 0));   // cv_{f0,ap,voiced}_out[b] consumed by decode k-2
     RYK_CUDA(cudaStreamWaitEvent(s->sC, s->ev_conv[(k - 2) % kRing], 0));     // cv_sp_mid[b] consumed by stage 2 of k-2
   }
-  {
-    const auto t0 = std::chrono::steady_clock::now();
-    RYK_CUDA(cudaEventSynchronize(s->ev_count[r]));                            // effective-frame count of THIS step
-    if (s->host_prof) s->host_wait_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
-  }
-  const int t_eff = s->h_count[r][0], tp1 = s->h_count[r][1];
-  RYK_CHECK(tp1 / 128 < 16, "window too long for the stage-1 graph table");
   TSTAMP(2, 0, s->sC);
-  if (stage1_enqueue(e, s, b, t_eff > 0 ? tp1 : 0, false)) return -1;
+  if (s->device_buckets) {
+    // launch-count bookkeeping only (never waits): the newest count that has already arrived tells which body ran last
+    for (int back = 1; back <= 3 && k - back >= 0; ++back) {
+      const int rr = (int)((k - back) % kRing);
+      if (cudaEventQuery(s->ev_count[rr]) == cudaSuccess) { s->last_bucket = s->h_count[rr][0] > 0 ? s->h_count[rr][1] / 128 : 0; break; }
+    }
+    if (s->last_bucket < 0 || s->last_bucket >= s->s1_buckets) s->last_bucket = s->s1_buckets - 1;
+    RYK_CUDA(cudaGraphLaunch(s->s1_switch[b], s->sC));
+    e->launches += s->s1_switch_launches[b][s->last_bucket];
+  } else {
+    const auto t0 = std::chrono::steady_clock::now();
+    RYK_CUDA(cudaEventSynchronize(s->ev_count[r]));                            // effective-frame count of THIS step (RYK_NO_GRAPH / RYK_HOST_BUCKETS path)
+    if (s->host_prof) s->host_wait_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+    const int t_eff = s->h_count[r][0], tp1 = s->h_count[r][1];
+    RYK_CHECK(tp1 / 128 < 16, "window too long for the stage-1 graph table");
+    if (stage1_enqueue(e, s, b, t_eff > 0 ? tp1 : 0, false)) return -1;
+  }
   // NB: enc_*[b] may be overwritten by encode k+2 once this stage's slides ran; the stage-1 graph is short, so the
   // guard event is simply the end of the stage.
   TSTAMP(2, 1, s->sC);
@@ -718,7 +790,16 @@ int ryk_session_create(ryk_engine* h, const ryk_session_config* cfg, int* sessio
   // (the stage-2 plan is created on first use: a session that joins a group never needs its own)
   RYK_CUDA(cudaStreamSynchronize(e->stream));
   RYK_CUDA(cudaDeviceSynchronize());
-  if (s->use_graphs) {
+  { const char* hb = getenv("RYK_HOST_BUCKETS"); s->device_buckets = s->use_graphs && !(hb && atoi(hb) != 0); }
+  if (s->device_buckets) {
+    const char* sp = getenv("RYK_S1_PDL");
+    const bool pdl_bodies = !(sp && atoi(sp) == 0);
+    if (!pdl_bodies) tc_force_pdl(0);
+    int rc = 0;
+    for (int b = 0; b < 2 && !rc; ++b) rc = stage1_build_switch(e, s, b);
+    if (!pdl_bodies) tc_force_pdl(-1);
+    if (rc) return rc;
+  } else if (s->use_graphs) {
     const long long before = e->launches;
     for (int b = 0; b < 2; ++b)
       for (int tp1 = 0; tp1 <= s->Tw + (128 - s->Tw % 128); tp1 += 128)

@@ -183,3 +183,41 @@ def test_fp16_full_model_convert_window_spectra(engine, full_models):
     l2, mx = _logspec_err(out['sp'], ref['sp'])
     print(f'HEADLINE convert window Tw=260 fp16 base-64: per-frame log-L2 {l2:.2e}, max {mx:.2e}')
     assert l2 <= 1e-2 and mx <= 6e-2, (l2, mx)
+
+
+def test_soak_1200_chunks_ring_wraps(engine, small_models):
+    """One session, 1200 consecutive 0.3 s chunks (6 minutes of audio) through submit / collect with 3 in flight, compared with the
+    oracle stream chunk by chunk: crosses the synthesizer's noise-ring refills (every 2^21 samples = 87 s), wraps the pulse ring
+    (2^15 pulses) and the 8-slot event / staging rings 150 times."""
+    ac, sr, f0c = _load(engine, small_models)
+    p1, p2 = onets.load_npz(small_models['stage1_model_path']), onets.load_npz(small_models['stage2_model_path'])
+    engine.set_precision('fp16')
+    T, extra, nchunks = 0.3, (0.0, 0.5, 0.0), 1200
+    sid = engine.session_create(_session_cfg(T, extra))
+    orc = opipe.StreamOracle(CFG, p1, p2, f0c.stats(), buffer_time=T, extra=extra, backend='torch')
+    n = round(T * 24000)
+    base = synthetic.synthetic_speech(30.0, stream=55)          # 100 chunks of audio, cycled
+    per = len(base) // n
+    buf = np.empty(65536)
+    tickets, worst, total_sq, total_n, sig_sq = [], 0.0, 0.0, 0, 0.0
+
+    def check(k_out, y):
+        nonlocal worst, total_sq, total_n, sig_sq
+        r = orc.push(base[(k_out % per) * n:(k_out % per + 1) * n])
+        assert len(y) == len(r), (k_out, len(y), len(r))
+        if len(r):
+            e = float(np.sqrt(np.mean((y - r) ** 2)))
+            worst = max(worst, e)
+            total_sq += float(np.sum((y - r) ** 2)); total_n += len(r); sig_sq += float(np.sum(r ** 2))
+            assert e <= 2e-3, (k_out, e)                       # per chunk; the whole-run RMSE is asserted below
+    k_out = 0
+    for k in range(nchunks):
+        tickets.append(engine.session_submit(sid, base[(k % per) * n:(k % per + 1) * n]))
+        if len(tickets) > 3:
+            check(k_out, engine.session_collect(sid, tickets.pop(0), buf).copy()); k_out += 1
+    while tickets:
+        check(k_out, engine.session_collect(sid, tickets.pop(0), buf).copy()); k_out += 1
+    engine.session_destroy(sid)
+    rmse, rms = (total_sq / total_n) ** 0.5, (sig_sq / total_n) ** 0.5
+    print(f'SOAK {nchunks} chunks ({nchunks * T:.0f} s of audio, {total_n} samples): sample RMSE {rmse:.3e} (signal RMS {rms:.3e}), worst chunk {worst:.3e}')
+    assert rmse <= 1e-3

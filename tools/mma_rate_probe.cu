@@ -30,7 +30,15 @@ k_probe(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtenso
   __shared__ uint64_t done_bar;
   __shared__ uint32_t tmem_ptr;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (mode & 1) for (int i = threadIdx.x; i < 2 * 49152 / 4; i += blockDim.x) ((uint32_t*)ops)[i] = 0x3c003c00u;      // fp16 1.0
+  if (mode & 1) for (int i = threadIdx.x; i < 2 * 49152 / 4; i += blockDim.x) {
+    // bit 10: random fp16 operands in (-1, 1) (a real workload's toggling) instead of the constant 1.0
+    uint32_t v = 0x3c003c00u;
+    if (mode & 1024) {
+      uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 40503u; h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+      v = (h & 0x83ff83ffu) | 0x38003800u;            // sign + 10 mantissa bits, exponent 14: |x| in [0.5, 1)
+    }
+    ((uint32_t*)ops)[i] = v;
+  }
   if (threadIdx.x == 0) { for (int w = 0; w < 4; ++w) for (int i = 0; i < 8; ++i) mbar_init(&full[w][i], 1); mbar_init(&done_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   if (warp == 4) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr)), "r"(512u) : "memory");
@@ -141,6 +149,10 @@ int main() {
   run<128>(tm, 1, 0, 0, d_out, sms, "MMA only, N = 128");
   run<256>(tm, 1, 0, 0, d_out, sms, "MMA only, N = 256");
   run<128>(tm, 1, 0, 1024, d_out, sms, "MMA only, N = 128, A start +1024 B on odd groups");
+  run<128>(tm, 1 | 1024, 0, 0, d_out, sms, "MMA only, N = 128, RANDOM operands");
+  run<256>(tm, 1 | 1024, 0, 0, d_out, sms, "MMA only, N = 256, RANDOM operands");
+  run<128>(tm, 1 | 1024, 0, 0, d_out, 16, "MMA only, N = 128, RANDOM operands, 16 CTAs");
+  run<128>(tm, 3 | 1024 | (2 << 4), 2, 0, d_out, sms, "MMA N = 128 RANDOM + TMA 2 issuers x 2 stages");
   run<128>(tm, 2, 2, 0, d_out, sms, "TMA only, 2 stages in flight");
   run<128>(tm, 2, 4, 0, d_out, sms, "TMA only, 4 stages in flight");
   run<128>(tm, 2, 1, 0, d_out, sms, "TMA only, 1 stage in flight (latency)");
