@@ -75,7 +75,12 @@ __device__ inline double block_sum(double v, double* scratch) {
 
 // In-place inclusive prefix sum over smem array a[0..n) (doubles). scratch >= blockDim.x doubles.
 __device__ inline void block_inclusive_scan(double* a, int n, double* scratch) {
-  const int T = blockDim.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (T + 31) >> 5;
+  const int T = blockDim.x, lane = threadIdx.x & 31, nw = (T + 31) >> 5;
+  // nvcc 12.9 miscompiles &scratch[threadIdx.x >> 5] here when block_sum() was inlined earlier in the same kernel: it re-uses block_sum's
+  // address register, strength-reduced to base + (tid >> 2) under block_sum's `lane == 0` predicate, for accesses made by ALL lanes
+  // (compute-sanitizer: misaligned shared accesses at base + 8 w + (lane >> 2)).  The empty asm makes the warp index opaque to that CSE.
+  int w = threadIdx.x >> 5;
+  asm volatile("" : "+r"(w));
   int per = (n + T - 1) / T;
   int lo = threadIdx.x * per, hi = min(lo + per, n);
   double s = 0.0;
@@ -90,7 +95,8 @@ __device__ inline void block_inclusive_scan(double* a, int n, double* scratch) {
   }
   double excl = __shfl_up_sync(0xffffffffu, incl, 1);      // exclusive prefix inside the warp (exact: no incl - s cancellation)
   if (lane == 0) excl = 0.0;
-  if (lane == 31) scratch[w] = incl;
+  const double wtot = __shfl_sync(0xffffffffu, incl, 31);
+  if (lane == 0) scratch[w] = wtot;
   __syncthreads();
   if (w == 0) {
     double t = lane < nw ? scratch[lane] : 0.0;
