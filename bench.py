@@ -337,7 +337,7 @@ def run_gpu(args):
         for k in range(warmup):
             push_dev(k)
         barrier()
-        eng.profile_read()                           # discard the warm-up timings
+        eng.profile_read2()                          # discard the warm-up timings
         sampler = ClockSampler(local_rank)
         sampler.start()
         sampler.ready.wait(timeout=5)
@@ -354,11 +354,11 @@ def run_gpu(args):
         t_host = time.perf_counter() - t_host0          # host time to queue the K steps (launch overhead view)
         t_dev = eng.timer_stop() * 1e-3          # CUDA events on the stream the kernels are launched on
         barrier()
-        s2_ms, s2_runs = eng.profile_read()
+        s2_sum, s2_ms, s2_runs = eng.profile_read2()   # s2_ms = union of the per-forward intervals (consecutive forwards overlap on two streams)
         eng.profile(False)
         clocks = sampler.stop()
         launches = eng.launch_count - launches0
-        res = dict(T=T, B=B, Tw=Tw, Tp=Tp, n=n, t_dev=max_over_ranks(t_dev), t_host=t_host, s2_ms=s2_ms, s2_runs=s2_runs, launches=launches, clocks=clocks)
+        res = dict(T=T, B=B, Tw=Tw, Tp=Tp, n=n, t_dev=max_over_ranks(t_dev), t_host=t_host, s2_ms=s2_ms, s2_sum=s2_sum, s2_runs=s2_runs, launches=launches, clocks=clocks)
 
         # ---- sustained: the same K-step block repeated back to back for >= sustain_s seconds (thermal / power steady state) ----
         if sustain_s > 0:
@@ -375,7 +375,7 @@ def run_gpu(args):
                     push_dev(k)
                     k += 1
                 dt = eng.timer_stop() * 1e-3
-                a, b_ = eng.profile_read()
+                _sum, a, b_ = eng.profile_read2()
                 s2_tot += a; s2_n += b_
                 rates.append(B * steps / dt)
             eng.profile(False)
@@ -473,7 +473,11 @@ def run_gpu(args):
                       unit='TFLOP/s', frac=(ach / peaks['tflops']) if ach else None, traffic=traffic, traffic_source=traffic_src,
                       peak_source=peaks['source'], peak_burst=peaks['burst'], peak_sustained=peaks['sustained'],
                       flop_per_step=fl, ms_per_step_in_kernel=(main['s2_ms'] / main['s2_runs']) if main['s2_runs'] else None,
-                      timed='CUDA events on the stage-2 stream around the 14-layer graph, inside the pipelined timed region (co-running stages included)'),
+                      ms_per_forward_wall=(main['s2_sum'] / main['s2_runs']) if main['s2_runs'] else None,
+                      timed='CUDA events around the 14-layer graph of every forward on the stream it runs on, inside the pipelined timed region (co-running '
+                            'stages included).  A session alternates its forwards between two streams, so consecutive forwards overlap: '
+                            'ms_per_step_in_kernel = union of the intervals / forwards (time during which the block runs, per forward; `achieved` uses it), '
+                            'ms_per_forward_wall = mean first-kernel-start to last-kernel-end of ONE forward'),
     )
     if 'sustained' in main:
         su = main['sustained']

@@ -55,6 +55,8 @@ int ryk_engine_timer_start(ryk_engine* e);                    /* cudaEventRecord
 int ryk_engine_timer_stop(ryk_engine* e, float* elapsed_ms);  /* record + synchronize + elapsed */
 int ryk_engine_profile(ryk_engine* e, int enable);
 int ryk_engine_profile_read(ryk_engine* e, double* stage2_ms_total, int* stage2_runs);
+/* as above plus the UNION of the per-forward intervals (a session alternates its stage-2 forwards between two streams, so they overlap) */
+int ryk_engine_profile_read2(ryk_engine* e, double* stage2_ms_total, double* stage2_ms_union, int* stage2_runs);
 
 /* ---- WORLD analysis (encode) -------------------------------------------------------------- */
 /* wave_host: n float32 samples.  Outputs are n_frames = n / hop rows (hop = fs * frame_period / 1000):

@@ -5,6 +5,7 @@
 #include <stddef.h>
 #include <string.h>
 #include <mutex>
+#include <algorithm>
 #include <vector>
 
 #include "../../include/ryk.h"
@@ -189,20 +190,38 @@ long long ryk_engine_launch_count(ryk_engine* h) { return E(h)->launches; }
 int ryk_engine_synchronize(ryk_engine* h) { RYK_CUDA(cudaSetDevice(E(h)->device)); RYK_CUDA(cudaDeviceSynchronize()); return 0; }
 
 int ryk_engine_profile(ryk_engine* h, int enable) { E(h)->profile = enable != 0; return 0; }
-// total device time (ms) of the stage-2 k4 (tensor-core) layer block over all forwards since the last read
-int ryk_engine_profile_read(ryk_engine* h, double* stage2_ms_total, int* stage2_runs) {
+// Device time (ms) of the stage-2 k4 (tensor-core) layer block over all forwards since the last read:
+//   *stage2_ms_total = sum of the per-forward durations (CUDA events on the stream each forward runs on),
+//   *stage2_ms_union = length of the union of those intervals.  A single session alternates its forwards between two streams, so
+//   consecutive forwards overlap: the sum then counts the shared time twice; the union is the time during which the block was running.
+int ryk_engine_profile_read2(ryk_engine* h, double* stage2_ms_total, double* stage2_ms_union, int* stage2_runs) {
   Engine* e = E(h);
   RYK_CUDA(cudaDeviceSynchronize());
-  double tot = 0.0;
+  double tot = 0.0, uni = 0.0;
+  std::vector<std::pair<double, double>> iv;
   for (auto& pr : e->prof_events) {
-    float ms = 0.f;
+    float ms = 0.f, off = 0.f;
     RYK_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+    RYK_CUDA(cudaEventElapsedTime(&off, e->prof_events.front().first, pr.first));
     tot += ms;
-    cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+    iv.emplace_back((double)off, (double)off + (double)ms);
   }
-  *stage2_ms_total = tot; *stage2_runs = (int)e->prof_events.size();
+  std::sort(iv.begin(), iv.end());
+  double cur0 = 0.0, cur1 = -1.0;
+  for (auto& x : iv) {
+    if (cur1 < cur0 || x.first > cur1) { if (cur1 >= cur0) uni += cur1 - cur0; cur0 = x.first; cur1 = x.second; }
+    else if (x.second > cur1) cur1 = x.second;
+  }
+  if (cur1 >= cur0 && !iv.empty()) uni += cur1 - cur0;
+  for (auto& pr : e->prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  if (stage2_ms_total) *stage2_ms_total = tot;
+  if (stage2_ms_union) *stage2_ms_union = uni;
+  if (stage2_runs) *stage2_runs = (int)e->prof_events.size();
   e->prof_events.clear();
   return 0;
+}
+int ryk_engine_profile_read(ryk_engine* h, double* stage2_ms_total, int* stage2_runs) {
+  return ryk_engine_profile_read2(h, stage2_ms_total, nullptr, stage2_runs);
 }
 
 // device-side stopwatch on the engine's stream (bench.py brackets its timed region with it)

@@ -46,6 +46,8 @@ struct TcParams {
   float* ws;                     // split-K workspace [ksplit][pixels][Cout] or nullptr
   size_t out_pixels;             // B * Hout * Wout
   int debug;                     // RYK_TC_DEBUG bit 1 (perf experiments only): skip the output stores
+  int cluster_k;                 // split-K partial sums are reduced INSIDE the kernel: the ksplit CTAs of a tile form a thread-block cluster
+                                 // (cluster rank == split) and read each other's FP32 partial tiles through distributed shared memory
 };
 
 #ifdef RYK_TC_TIMELINE
@@ -66,6 +68,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
   constexpr uint32_t kBBytes = BLOCK_N * kBlockK * 2;
+  constexpr uint32_t kCkPitch = BLOCK_N * 4 + 16;          // row pitch of the FP32 partial tile of the in-cluster split-K reduction
+  constexpr bool kCkOk = (size_t)kBlockM * kCkPitch <= (size_t)kStages * (kABytes + kBBytes);      // partial tile fits the stage buffers (host side: variant 1 only)
   // carve: 1024-aligned stage buffers first, barriers after
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
@@ -199,7 +203,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       {
-        if (p.ws) {
+        if (kCkOk && p.cluster_k) {
+          // raw FP32 partial sums -> plain [pixel][channel] tile in the (idle) stage buffers, row pitch kCkPitch; the cluster reduces below
+          uint8_t* dst = smem + (size_t)row * kCkPitch + c0 * 4;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(dst + j * 16) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        } else if (p.ws) {
           // split-K partial tile (raw FP32 sums) -> swizzled staging, one [128 pixels][32 channels] block per iteration;
           // stored below by TMA into this split's slice of the workspace; k_splitk_reduce sums the slices
           uint8_t* blk = smem + (c0 >> 5) * (kBlockM * 128) + row * 128;
@@ -233,7 +242,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
         }
       }
     }
-    if (!p.ws && my_chunks > 0) {
+    if (!p.ws && !p.cluster_k && my_chunks > 0) {
       // generic-proxy smem writes -> visible to the async proxy; one thread hands the tile to the TMA unit
       // (out-of-range pixels are clipped by the tensor map, so no masking is needed)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -265,6 +274,42 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
       }
     }
+  }
+  if (kCkOk && p.cluster_k) {
+    // ===== in-cluster split-K reduction (replaces the FP32 workspace round trip + k_splitk_reduce launch) =====
+    // CTA r of the cluster (= split r) owns tile rows r, r + ksplit, ...; it sums the ksplit partial rows in split order (fixed:
+    // deterministic), applies scale / shift / activation and writes FP16 NHWC directly.  All threads take both cluster barriers.
+    cluster_barrier();                                   // every split's partial tile is in its CTA's shared memory
+    if (warp < 4) {
+      constexpr int kTpr = BLOCK_N / 4;                  // threads per row (one float4 each)
+      constexpr int kRpp = 128 / kTpr;                   // rows per pass
+      const int sub = threadIdx.x / kTpr, c4 = threadIdx.x % kTpr;
+      const uint32_t my_base = smem_u32(smem);
+      const float4 sc = *reinterpret_cast<const float4*>(s_scale + c4 * 4), sh = *reinterpret_cast<const float4*>(s_shift + c4 * 4);
+      for (int i = sub; ; i += kRpp) {
+        const int row = split + i * p.ksplit;
+        if (row >= kBlockM) break;
+        const int hl = row / p.tile_w, wl = row - hl * p.tile_w;
+        const int my = oy0 + hl, mx = ox0 + wl;
+        if (my >= p.Hc || mx >= p.Wc) continue;
+        const uint32_t off = (uint32_t)row * kCkPitch + (uint32_t)c4 * 16u;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < p.ksplit; ++q) {
+          const float4 v = ld_cluster_f4(cluster_map_rank(my_base + off, (uint32_t)q));
+          a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        float v4[4] = {fmaf(a.x, sc.x, sh.x), fmaf(a.y, sc.y, sh.y), fmaf(a.z, sc.z, sh.z), fmaf(a.w, sc.w, sh.w)};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (p.act == ACT_LEAKY) v4[j] = v4[j] > 0.f ? v4[j] : 0.2f * v4[j]; else if (p.act == ACT_RELU) v4[j] = fmaxf(v4[j], 0.f);
+        }
+        const int oy = p.transposed ? my * p.sh + py : my, ox = p.transposed ? mx * p.sw + px : mx;
+        __half2 h0 = __floats2half2_rn(v4[0], v4[1]), h1 = __floats2half2_rn(v4[2], v4[3]);
+        __half* dst = p.out + ((size_t)(b * p.Hout + oy) * p.Wout + ox) * p.Cout + n0 + c4 * 4;
+        *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+      }
+    }
+    cluster_barrier();                                   // nobody exits (and frees its shared memory) while a peer may still read it
   }
   if (threadIdx.x == 0) TL(5);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -635,6 +680,17 @@ bool tc_layer_eligible(const ConvLayer& L) {
   return true;
 }
 
+// RYK_TC_CLUSTERK: 1 = split-K layers reduce their partial sums inside the kernel (thread-block cluster + distributed shared memory),
+// 0 (default) = FP32 workspace + k_splitk_reduce launch.  Measured (profiles/r02_layer_bench_cluster_splitk.txt): the DSMEM reduction
+// costs as much as the separate reduce launch on the bottleneck layers (c5 11.2 vs 10.3 us, d1 10.3 vs 11.1) and almost doubles c3 / d3
+// (32.9 vs 18.0 us: 43 rows x 3 remote reads per CTA at ~20 B/clk of DSMEM bandwidth) -- kept as an opt-in.
+static bool tc_clusterk() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("RYK_TC_CLUSTERK"); v = (e && atoi(e) != 0) ? 1 : 0; }
+  return v != 0 && tc_variant() == 1;
+}
+bool tc_layer_clusterk(const ConvLayer& L) { return tc_clusterk() && L.ksplit > 1 && !L.tc2 && !L.tc3 && L.block_n <= 128; }
+
 static int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
 
 static int make_act_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int B, int box_w, int box_h, int stride_w, int stride_h) {
@@ -697,23 +753,24 @@ static void tc_geometry(const ConvLayer& L, int num_sms, int* tile_w, int* tile_
     if (min_chunks < 0) { const char* v = getenv("RYK_TC_MIN_CHUNKS"); min_chunks = v ? atoi(v) : 8; if (min_chunks < 1) min_chunks = 1; }
     if (ks > total_chunks / min_chunks) ks = total_chunks / min_chunks;   // at least min_chunks chunks per split
     if (ks < 1) ks = 1;
+    if (tc_clusterk() && ks > 8) ks = 8;                // in-cluster reduction: the splits of a tile form one (portable-size) cluster
     int cps = (total_chunks + ks - 1) / ks;
     ks = (total_chunks + cps - 1) / cps;                // every split owns at least one chunk
   }
   { ConvLayer T = L; T.tile_w = tw; T.tile_h = th; int g_, n_; if (tc2_layer_config(T, num_sms, &g_, &n_)) ks = 1; }   // pair kernel: no split-K
-  { int a_, b_, c_; if (tc3_layer_config(L, num_sms, &a_, &b_, &c_)) ks = 1; }                                             // halo kernel: no split-K
+  { int a_, b_, c_; bool o_; if (tc3_layer_config(L, num_sms, &a_, &b_, &c_, &o_)) ks = 1; }                                             // halo kernel: no split-K
   *tile_w = tw; *tile_h = th; *block_n = bn; *ksplit = ks;
 }
 
 bool tc_layer_wants_counter(const ConvLayer& L, int num_sms) {
-  int a_, b_, c_;
-  return tc_layer_eligible(L) && tc3_layer_config(L, num_sms, &a_, &b_, &c_);
+  int a_, b_, c_; bool o_;
+  return tc_layer_eligible(L) && tc3_layer_config(L, num_sms, &a_, &b_, &c_, &o_);
 }
 
 size_t tc_splitk_ws_bytes(const ConvLayer& L, int num_sms) {
   int tw, th, bn, ks;
   tc_geometry(L, num_sms, &tw, &th, &bn, &ks);
-  return ks > 1 ? (size_t)ks * L.B * L.Hout * L.Wout * L.Cout * sizeof(float) : 0;
+  return (ks > 1 && !tc_clusterk()) ? (size_t)ks * L.B * L.Hout * L.Wout * L.Cout * sizeof(float) : 0;
 }
 
 int tc_layer_prepare(ConvLayer& L, int num_sms) {
@@ -733,10 +790,10 @@ int tc_layer_prepare(ConvLayer& L, int num_sms) {
   if (make_act_map(&L.tmO, L.out, L.Cout, L.Wout, L.Hout, L.B, L.tile_w, L.tile_h, L.transposed ? L.SW : 1, L.transposed ? L.SH : 1)) return -1;
   L.tc2 = tc2_layer_config(L, num_sms, &L.tc2_groups, &L.tc2_ng);
   if (L.tc2 && tc2_layer_prepare(L, g_encode)) return -1;
-  L.tc3 = !L.tc2 && tc3_layer_config(L, num_sms, &L.t3_tile_w, &L.t3_tile_h, &L.t3_mt);
+  L.tc3 = !L.tc2 && tc3_layer_config(L, num_sms, &L.t3_tile_w, &L.t3_tile_h, &L.t3_mt, &L.t3_one);
   if (L.tc3 && tc3_layer_prepare(L, g_encode)) return -1;
-  RYK_CHECK(L.ksplit == 1 || L.splitk_ws != nullptr, "split-K layer without a workspace");
-  if (L.ksplit > 1) {
+  RYK_CHECK(L.ksplit == 1 || tc_layer_clusterk(L) || L.splitk_ws != nullptr, "split-K layer without a workspace");
+  if (L.ksplit > 1 && !tc_layer_clusterk(L)) {
     if (make_ws_map(&L.tmW, L.splitk_ws, L.Cout, L.Wout, L.Hout, L.B, L.ksplit, L.tile_w, L.tile_h, L.transposed ? L.SW : 1, L.transposed ? L.SH : 1)) return -1;
   } else L.tmW = L.tmO;
   L.tc_ready = true;
@@ -752,14 +809,16 @@ static bool pdl_enabled() {
   if (v < 0) { const char* e = getenv("RYK_NO_PDL"); v = (e && atoi(e) != 0) ? 0 : 1; }
   return g_pdl_force >= 0 ? g_pdl_force != 0 : v != 0;
 }
+static int g_cluster_z = 1;                        // cluster dimension along grid z of the next launch_pdl (in-cluster split-K)
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (pdl_enabled()) { attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[n].val.programmaticStreamSerializationAllowed = 1; ++n; }
+  if (g_cluster_z > 1) { attr[n].id = cudaLaunchAttributeClusterDimension; attr[n].val.clusterDim.x = 1; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = (unsigned)g_cluster_z; ++n; }
+  cfg.attrs = attr; cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
@@ -782,7 +841,10 @@ int conv_tc_run(const ConvLayer& L, cudaStream_t st) {
   int total_chunks = p.ntaps * (p.chunks0 + p.chunks1);
   p.chunks_per_split = (total_chunks + L.ksplit - 1) / L.ksplit;
   p.act = L.act; p.scale = L.scale; p.shift = L.shift; p.out = (__half*)L.out;
-  p.ws = L.ksplit > 1 ? L.splitk_ws : nullptr;
+  const bool ck = tc_layer_clusterk(L);
+  p.ws = (L.ksplit > 1 && !ck) ? L.splitk_ws : nullptr;
+  p.cluster_k = ck ? 1 : 0;
+  g_cluster_z = ck ? L.ksplit : 1;
   p.out_pixels = (size_t)L.B * L.Hout * L.Wout;
 #ifdef RYK_DIAG
   { static int dbg = -1; if (dbg < 0) { const char* v = getenv("RYK_TC_DEBUG"); dbg = v ? atoi(v) : 0; } p.debug = dbg; }   // diagnostics builds only
@@ -818,6 +880,7 @@ int conv_tc_run(const ConvLayer& L, cudaStream_t st) {
     else if (L.block_n == 128) RYK_CUDA(launch_pdl(k_conv_tc<128, 3, 2>, grid, dim3(kTcThreads), tc_smem_bytes<128, 3>(), st, L.tmA0, L.tmA1, L.tmB, L.tmO, L.tmW, p));
     else RYK_CUDA(launch_pdl(k_conv_tc<64, 4, 2>, grid, dim3(kTcThreads), tc_smem_bytes<64, 4>(), st, L.tmA0, L.tmA1, L.tmB, L.tmO, L.tmW, p));
   }
+  g_cluster_z = 1;
   RYK_CUDA(cudaGetLastError());
 #ifdef RYK_TC_TIMELINE
   cudaStreamCaptureStatus cap_ = cudaStreamCaptureStatusNone;

@@ -44,7 +44,7 @@ struct Session {
   // optional per-stage device timing (RYK_STAGE_TIMES=1): [stage E1,E2,S1,S2,D][begin/end][ring]
   cudaEvent_t tev[5][2][kRing]; bool stage_times = false;
   int owner = 0;                               // plan-cache owner id (activation buffers are private to the session)
-  float* d_colmin = nullptr;
+  float* d_colmin[2] = {nullptr, nullptr};
   Group* group = nullptr; int slot = 0;        // member of a batched stage-2 group (config 5), else nullptr
   cudaEvent_t ev_pro[kRing];                   // stage-2 prologue of step r done (group members only)
   ryk_session_config cfg;
@@ -52,7 +52,10 @@ struct Session {
   int Lw, Tw, Td, nb, C;
   long long step = 0;              // chunks submitted
   long long collected = 0;         // chunks collected through the host API
-  cudaStream_t sE = nullptr, sC = nullptr, sC2 = nullptr, sD = nullptr;     // gate | stage 1 | stage 2 | decode
+  cudaStream_t sE = nullptr, sC = nullptr, sD = nullptr;     // gate | stage 1 | decode
+  // stage 2 of even / odd chunks on two streams with two activation plans (RYK_S2_ALT=0: one): the latency-bound bottleneck layers
+  // (c4-d2: 30 % of a forward's time, a few CTAs each) of one chunk overlap the GPU-filling layers of its neighbour
+  cudaStream_t sC2s[2] = {nullptr, nullptr}; bool two_s2 = false;
   cudaStream_t sA[2] = {nullptr, nullptr};   // WORLD analysis of even / odd chunks: two chunks' analyses may be in flight
   cudaEvent_t ev_gate[kRing];
   cudaEvent_t ev_count[kRing], ev_enc[kRing], ev_cslide[kRing], ev_s1[kRing], ev_conv[kRing], ev_dslide[kRing], ev_dec[kRing];
@@ -231,7 +234,7 @@ static void session_free(Session* s) {
   if (s->host_prof && s->host_steps > 0)
     fprintf(stderr, "[ryk host prof] %lld steps: %.1f us per step on the host, of which %.1f us waiting for the gate count\n", s->host_steps,
             s->host_total_us / s->host_steps, s->host_wait_us / s->host_steps);
-  for (cudaStream_t st : {s->sE, s->sA[0], s->sA[1], s->sC, s->sC2, s->sD}) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+  for (cudaStream_t st : {s->sE, s->sA[0], s->sA[1], s->sC, s->sC2s[0], s->sC2s[1], s->sD}) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
   for (int i = 0; i < kRing; ++i)
     for (cudaEvent_t ev : {s->ev_gate[i], s->ev_pro[i], s->ev_count[i], s->ev_enc[i], s->ev_cslide[i], s->ev_s1[i], s->ev_conv[i], s->ev_dslide[i], s->ev_dec[i]}) if (ev) cudaEventDestroy(ev);
   for (auto& kv : s->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
@@ -271,7 +274,7 @@ void session_destroy_all(Engine* e) {
 int session_streams_fork(Engine* e, cudaEvent_t ev) {
   for (Session* s : e->sessions) {
     if (!s) continue;
-    for (cudaStream_t st : {s->sE, s->sA[0], s->sA[1], s->sC, s->sC2, s->sD}) RYK_CUDA(cudaStreamWaitEvent(st, ev, 0));
+    for (cudaStream_t st : {s->sE, s->sA[0], s->sA[1], s->sC, s->sC2s[0], s->sC2s[1], s->sD}) RYK_CUDA(cudaStreamWaitEvent(st, ev, 0));
   }
   for (Group* G : e->groups) if (G) RYK_CUDA(cudaStreamWaitEvent(G->sG, ev, 0));
   return 0;
@@ -280,7 +283,7 @@ int session_streams_fork(Engine* e, cudaEvent_t ev) {
 int session_streams_join(Engine* e) {
   for (Session* s : e->sessions) {
     if (!s) continue;
-    for (cudaStream_t st : {s->sE, s->sA[0], s->sA[1], s->sC, s->sC2, s->sD}) {
+    for (cudaStream_t st : {s->sE, s->sA[0], s->sA[1], s->sC, s->sC2s[0], s->sC2s[1], s->sD}) {
       cudaEvent_t ev;
       RYK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
       RYK_CUDA(cudaEventRecord(ev, st));
@@ -445,8 +448,11 @@ static int stage1_enqueue(Engine* e, Session* s, int b, int tp1, bool capture_on
 
 #define TSTAMP(stage, which, stream) do { if (s->stage_times) RYK_CUDA(cudaEventRecord(s->tev[stage][which][r], stream)); } while (0)
 
+#define S2_LOCALS cudaStream_t sC2 = s->sC2s[(s->two_s2 && !s->group) ? b : 0]; const int s2_owner = s->owner + ((s->two_s2 && !s->group && b) ? 3000000 : 0); float* d_colmin = s->d_colmin[(s->two_s2 && !s->group) ? b : 0]; (void)s2_owner; (void)d_colmin;
+
 static int session_front(Engine* e, Session* s, const float* d_chunk_user) {
   STEP_LOCALS
+  S2_LOCALS
 
   // ================= stream E: gate + WORLD analysis =================
   RYK_CUDA(cudaMemcpyAsync(s->d_chunk_fixed, d_chunk_user, sizeof(float) * s->n_wave, cudaMemcpyDeviceToDevice, s->sE));
@@ -513,22 +519,22 @@ static int session_front(Engine* e, Session* s, const float* d_chunk_user) {
   RYK_CUDA(cudaEventRecord(s->ev_s1[r], s->sC));
 
   // ================= stream C2: stage-2 prologue =================
-  RYK_CUDA(cudaStreamWaitEvent(s->sC2, s->ev_s1[r], 0));
-  if (k >= 2) RYK_CUDA(cudaStreamWaitEvent(s->sC2, s->ev_dslide[(k - 2) % kRing], 0));  // cv_sp_out[b] consumed by decode k-2
+  RYK_CUDA(cudaStreamWaitEvent(sC2, s->ev_s1[r], 0));
+  if (k >= 2) RYK_CUDA(cudaStreamWaitEvent(sC2, s->ev_dslide[(k - 2) % kRing], 0));  // cv_sp_out[b] consumed by decode k-2
   const int Tp = s->Tw + (128 - s->Tw % 128);
-  TSTAMP(3, 0, s->sC2);
+  TSTAMP(3, 0, sC2);
   if (s->group) {
     Group* G = s->group;
-    if (G->step >= 1) RYK_CUDA(cudaStreamWaitEvent(s->sC2, G->ev_fwd[(G->step - 1) % kRing], 0));   // batched input read by forward k-1
+    if (G->step >= 1) RYK_CUDA(cudaStreamWaitEvent(sC2, G->ev_fwd[(G->step - 1) % kRing], 0));   // batched input read by forward k-1
     float* dst = (float*)G->p2->d_in + (size_t)s->slot * Tp * 512;
-    if (run_stage(e, s, G_S2A + b, s->sC2, [&]() -> int { return sr_prologue_run(e, s->cv_sp_mid[b], s->Tw, Tp, s->nb, dst, s->sC2, s->d_colmin); })) return -1;
-    RYK_CUDA(cudaEventRecord(s->ev_pro[r], s->sC2));
+    if (run_stage(e, s, G_S2A + b, sC2, [&]() -> int { return sr_prologue_run(e, s->cv_sp_mid[b], s->Tw, Tp, s->nb, dst, sC2, d_colmin); })) return -1;
+    RYK_CUDA(cudaEventRecord(s->ev_pro[r], sC2));
   } else {
     UNetPlan* p2 = nullptr;
-    if (unet_get_plan(e, e->stage2, 1, Tp, 512, e->precision, &p2, s->owner)) return -1;
-    if (!s->merge_s2 && run_stage(e, s, G_S2A + b, s->sC2, [&]() -> int {
-          if (sr_prologue_run(e, s->cv_sp_mid[b], s->Tw, Tp, s->nb, (float*)p2->d_in, s->sC2, s->d_colmin)) return -1;
-          return unet_forward(e, p2, s->sC2, 0, 0);
+    if (unet_get_plan(e, e->stage2, 1, Tp, 512, e->precision, &p2, s2_owner)) return -1;
+    if (!s->merge_s2 && run_stage(e, s, G_S2A + b, sC2, [&]() -> int {
+          if (sr_prologue_run(e, s->cv_sp_mid[b], s->Tw, Tp, s->nb, (float*)p2->d_in, sC2, d_colmin)) return -1;
+          return unet_forward(e, p2, sC2, 0, 0);
         })) return -1;
   }
   return 0;
@@ -537,42 +543,44 @@ static int session_front(Engine* e, Session* s, const float* d_chunk_user) {
 // single session: stage-2 layers 1..14 (the tcgen05 layers) on the session's own stream
 static int session_mid_single(Engine* e, Session* s, bool was_profiling) {
   STEP_LOCALS
+  S2_LOCALS
   const int Tp = s->Tw + (128 - s->Tw % 128);
   UNetPlan* p2 = nullptr;
-  if (unet_get_plan(e, e->stage2, 1, Tp, 512, e->precision, &p2, s->owner)) return -1;
+  if (unet_get_plan(e, e->stage2, 1, Tp, 512, e->precision, &p2, s2_owner)) return -1;
   cudaEvent_t pe0 = nullptr, pe1 = nullptr;
-  if (was_profiling) { RYK_CUDA(cudaEventCreate(&pe0)); RYK_CUDA(cudaEventCreate(&pe1)); RYK_CUDA(cudaEventRecord(pe0, s->sC2)); }
+  if (was_profiling) { RYK_CUDA(cudaEventCreate(&pe0)); RYK_CUDA(cudaEventCreate(&pe1)); RYK_CUDA(cudaEventRecord(pe0, sC2)); }
   if (s->merge_s2) {
     // whole stage 2 as one graph: no launch gaps between prologue, the 16 layers and the epilogue (PDL chains through)
-    return run_stage(e, s, G_S2M + b, s->sC2, [&]() -> int {
-      if (sr_prologue_run(e, s->cv_sp_mid[b], s->Tw, Tp, s->nb, (float*)p2->d_in, s->sC2, s->d_colmin)) return -1;
-      if (unet_forward(e, p2, s->sC2, 0, 15)) return -1;
-      return sr_epilogue_run(e, (const float*)p2->d_out, s->Tw, s->nb, s->cv_sp_out[b], s->sC2);
+    return run_stage(e, s, G_S2M + b, sC2, [&]() -> int {
+      if (sr_prologue_run(e, s->cv_sp_mid[b], s->Tw, Tp, s->nb, (float*)p2->d_in, sC2, d_colmin)) return -1;
+      if (unet_forward(e, p2, sC2, 0, 15)) return -1;
+      return sr_epilogue_run(e, (const float*)p2->d_out, s->Tw, s->nb, s->cv_sp_out[b], sC2);
     });
   }
-  if (run_stage(e, s, G_S2B + b, s->sC2, [&]() -> int { return unet_forward(e, p2, s->sC2, 1, 14); })) return -1;
-  if (was_profiling) { RYK_CUDA(cudaEventRecord(pe1, s->sC2)); e->prof_events.emplace_back(pe0, pe1); }
+  if (run_stage(e, s, G_S2B + b, sC2, [&]() -> int { return unet_forward(e, p2, sC2, 1, 14); })) return -1;
+  if (was_profiling) { RYK_CUDA(cudaEventRecord(pe1, sC2)); e->prof_events.emplace_back(pe0, pe1); }
   return 0;
 }
 
 static int session_back(Engine* e, Session* s) {
   STEP_LOCALS
+  S2_LOCALS
   const int Tp = s->Tw + (128 - s->Tw % 128);
   if (s->group) {
     Group* G = s->group;
-    RYK_CUDA(cudaStreamWaitEvent(s->sC2, G->ev_fwd[G->step % kRing], 0));
+    RYK_CUDA(cudaStreamWaitEvent(sC2, G->ev_fwd[G->step % kRing], 0));
     const float* src = (const float*)G->p2->d_out + (size_t)s->slot * Tp * 512;
-    if (run_stage(e, s, G_S2C + b, s->sC2, [&]() -> int { return sr_epilogue_run(e, src, s->Tw, s->nb, s->cv_sp_out[b], s->sC2); })) return -1;
+    if (run_stage(e, s, G_S2C + b, sC2, [&]() -> int { return sr_epilogue_run(e, src, s->Tw, s->nb, s->cv_sp_out[b], sC2); })) return -1;
   } else {
     UNetPlan* p2 = nullptr;
-    if (unet_get_plan(e, e->stage2, 1, Tp, 512, e->precision, &p2, s->owner)) return -1;
-    if (!s->merge_s2 && run_stage(e, s, G_S2C + b, s->sC2, [&]() -> int {
-          if (unet_forward(e, p2, s->sC2, 15, 15)) return -1;
-          return sr_epilogue_run(e, (const float*)p2->d_out, s->Tw, s->nb, s->cv_sp_out[b], s->sC2);
+    if (unet_get_plan(e, e->stage2, 1, Tp, 512, e->precision, &p2, s2_owner)) return -1;
+    if (!s->merge_s2 && run_stage(e, s, G_S2C + b, sC2, [&]() -> int {
+          if (unet_forward(e, p2, sC2, 15, 15)) return -1;
+          return sr_epilogue_run(e, (const float*)p2->d_out, s->Tw, s->nb, s->cv_sp_out[b], sC2);
         })) return -1;
   }
-  TSTAMP(3, 1, s->sC2);
-  RYK_CUDA(cudaEventRecord(s->ev_conv[r], s->sC2));
+  TSTAMP(3, 1, sC2);
+  RYK_CUDA(cudaEventRecord(s->ev_conv[r], sC2));
 
   // ================= stream D: realtime synthesizer =================
   RYK_CUDA(cudaStreamWaitEvent(s->sD, s->ev_conv[r], 0));
@@ -717,7 +725,8 @@ int ryk_session_create(ryk_engine* h, const ryk_session_config* cfg, int* sessio
   RYK_CUDA(cudaStreamCreateWithPriority(&s->sE, cudaStreamNonBlocking, PR(0)));
   for (int i = 0; i < 2; ++i) RYK_CUDA(cudaStreamCreateWithPriority(&s->sA[i], cudaStreamNonBlocking, PR(1)));
   RYK_CUDA(cudaStreamCreateWithPriority(&s->sC, cudaStreamNonBlocking, PR(2)));
-  RYK_CUDA(cudaStreamCreateWithPriority(&s->sC2, cudaStreamNonBlocking, PR(3)));
+  for (int i = 0; i < 2; ++i) RYK_CUDA(cudaStreamCreateWithPriority(&s->sC2s[i], cudaStreamNonBlocking, PR(3)));
+  { const char* v = getenv("RYK_S2_ALT"); s->two_s2 = !(v && atoi(v) == 0); }
   RYK_CUDA(cudaStreamCreateWithPriority(&s->sD, cudaStreamNonBlocking, PR(4)));
   for (int i = 0; i < kRing; ++i) {
     cudaEvent_t* evs[] = {&s->ev_gate[i], &s->ev_pro[i], &s->ev_count[i], &s->ev_enc[i], &s->ev_cslide[i], &s->ev_s1[i], &s->ev_conv[i], &s->ev_dslide[i], &s->ev_dec[i]};
@@ -759,7 +768,7 @@ int ryk_session_create(ryk_engine* h, const ryk_session_config* cfg, int* sessio
     if (A((void**)&s->cv_sp_mid[i], sizeof(float) * (size_t)s->Tw * s->nb)) return -1;
   }
   if (A((void**)&s->d_mse, sizeof(double) * s->Tw)) return -1;
-  if (A((void**)&s->d_colmin, sizeof(float) * kColminFloats)) return -1;
+  for (int i = 0; i < 2; ++i) if (A((void**)&s->d_colmin[i], sizeof(float) * kColminFloats)) return -1;
   if (A((void**)&s->dec_f0_f64, sizeof(double) * s->Td)) return -1;
   if (A((void**)&s->d_chunk_fixed, sizeof(float) * s->n_wave)) return -1;
   { const char* ng = getenv("RYK_NO_GRAPH"); s->use_graphs = !(ng && atoi(ng) != 0); }
@@ -821,6 +830,7 @@ int ryk_session_destroy(ryk_engine* h, int id) {
   session_free(s);                         // synchronises the session's streams
   unet_release_owner(e->stage1, owner);
   unet_release_owner(e->stage2, owner);
+  unet_release_owner(e->stage2, owner + 3000000);
   e->sessions[id] = nullptr;
   return 0;
 }

@@ -50,7 +50,7 @@ EXPORTED_SYMBOLS = [
     'ryk_group_size', 'ryk_session_stage_times', 'ryk_group_submit', 'ryk_group_collect', 'ryk_group_push_device', 'ryk_test_conv_layer', 'ryk_debug_dio', 'ryk_debug_synth_pulses', 'ryk_debug_synth_timebase', 'ryk_engine_profile', 'ryk_engine_profile_read', 'ryk_engine_timer_start', 'ryk_engine_timer_stop',
     'ryk_world_synthesize_length', 'ryk_world_synthesize', 'ryk_output_gate', 'ryk_reblock_create', 'ryk_reblock_destroy',
     'ryk_reblock_push', 'ryk_reblock_push_device', 'ryk_reblock_collect', 'ryk_reblock_result_device', 'ryk_resample_length',
-    'ryk_resample_poly', 'ryk_session_poll', 'ryk_reblock_poll',
+    'ryk_resample_poly', 'ryk_session_poll', 'ryk_reblock_poll', 'ryk_engine_profile_read2',
 ]
 
 
@@ -143,6 +143,12 @@ class Engine(object):
         ms, runs = ctypes.c_double(), ctypes.c_int()
         self._check(self.lib.ryk_engine_profile_read(self._h, ctypes.byref(ms), ctypes.byref(runs)))
         return ms.value, runs.value
+
+    def profile_read2(self):
+        """(sum of per-forward durations ms, union of the intervals ms, forwards) of the stage-2 k4 block since the last read."""
+        tot, uni, runs = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
+        self._check(self.lib.ryk_engine_profile_read2(self._h, ctypes.byref(tot), ctypes.byref(uni), ctypes.byref(runs)))
+        return tot.value, uni.value, runs.value
 
     def synchronize(self):
         self._check(self.lib.ryk_engine_synchronize(self._h))

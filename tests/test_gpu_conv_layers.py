@@ -247,14 +247,18 @@ def test_halo_kernel(engine, case):
     scale = rng.uniform(0.8, 1.2, Cout).astype(np.float32)
     shift = (0.1 * rng.standard_normal(Cout)).astype(np.float32)
     ref = _ref(in0, in1, Wt, scale, shift, tr, 4, 2, 1, act)
-    keys = ('RYK_TC3', 'RYK_TC3_MT', 'RYK_TC3_TW', 'RYK_TC3_DEPTH')
+    keys = ('RYK_TC3', 'RYK_TC3_MT', 'RYK_TC3_TW', 'RYK_TC3_DEPTH', 'RYK_TC3_ONE')
     old = {k: os.environ.get(k) for k in keys}
     try:
         os.environ['RYK_TC3'] = '0'
         base, _ = engine.test_conv_layer(in0, in1, Wt, scale, shift, tr, 4, 2, 1, act, use_tc=1)
-        os.environ.update(RYK_TC3='2', RYK_TC3_MT=str(mt), RYK_TC3_TW=str(tw))
-        for depth in (1, 0):
-            os.environ['RYK_TC3_DEPTH'] = str(depth)
+        os.environ.update(RYK_TC3='2', RYK_TC3_MT=str(mt), RYK_TC3_TW=str(tw), RYK_TC3_ONE='0')
+        # depth 1 / 0: persistent CTAs with 3 / 2 stages; 'one': one tile per CTA, two CTAs per SM, staging aliased to stage 0
+        for depth in (1, 0, 'one'):
+            if depth == 'one':
+                os.environ.update(RYK_TC3='1', RYK_TC3_ONE='2')
+            else:
+                os.environ['RYK_TC3_DEPTH'] = str(depth)
             got, ms = engine.test_conv_layer(in0, in1, Wt, scale, shift, tr, 4, 2, 1, act, use_tc=1, repeat=3)
             err, err_base = np.abs(got - ref).max(), np.abs(base - ref).max()
             print('halo kernel', case, 'depth', depth, 'max err', err, '(per-tap kernel', err_base, ') ms', ms)

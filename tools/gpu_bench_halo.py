@@ -15,13 +15,12 @@ for d in range(7):
     c1 = 0 if d == 0 else base * enc[7 - d]
     layers.append((f'd{d}', 1, Tp >> (7 - d), 512 >> (7 - d), c0, c1, base * dec[d]))
 only = os.environ.get('LAYERS')
-configs = [('per-tap', dict(RYK_TC3='0'))]
-for depth in (0, 1, 2):
-    configs.append((f'halo d{depth}', dict(RYK_TC3='1', RYK_TC3_DEPTH=str(depth))))
+configs = [('per-tap', dict(RYK_TC3='0')), ('default', dict())]
+for tw in (8, 16):
+    configs.append((f'one-tile tw{tw}', dict(RYK_TC3='1', RYK_TC3_ONE='2', RYK_TC3_TW=str(tw))))
 for mt in (1, 2):
-    for tw in (8, 16):
-        configs.append((f'halo mt{mt} tw{tw}', dict(RYK_TC3='2', RYK_TC3_DEPTH='1', RYK_TC3_MT=str(mt), RYK_TC3_TW=str(tw))))
-keys = ('RYK_TC3', 'RYK_TC3_MT', 'RYK_TC3_TW', 'RYK_TC3_DEPTH')
+    configs.append((f'persist mt{mt}', dict(RYK_TC3='2', RYK_TC3_ONE='0', RYK_TC3_DEPTH='1', RYK_TC3_MT=str(mt))))
+keys = ('RYK_TC3', 'RYK_TC3_MT', 'RYK_TC3_TW', 'RYK_TC3_DEPTH', 'RYK_TC3_ONE')
 print('layer      GFLOP ' + ' '.join(f'{n:>13s}' for n, _ in configs))
 tot = np.zeros(len(configs)); totf = 0.0
 for name, tr, H, W, C0, C1, Cout in layers:
