@@ -48,6 +48,10 @@ int ryk_engine_destroy(ryk_engine* e);
  * 1: FP16 operands + FP32 accumulate on tcgen05 tensor cores for the stage-2 k4 layers (default) */
 int ryk_engine_set_precision(ryk_engine* e, int mode);
 int ryk_engine_get_precision(ryk_engine* e);
+/* FP16 mode: run the stage-1 1-D U-Net (AcousticConverter.convert_from_feature, voice_changer.py:36) as ONE thread-block-cluster
+ * kernel (default, s1_fused.cu) or as 16 layer launches (enable = 0).  Returns the cluster size in use, <= 0 when the kernel is
+ * unavailable.  Sessions capture their stage-1 graphs at creation, so switch before ryk_session_create. */
+int ryk_engine_set_stage1_fused(ryk_engine* e, int enable);
 long long ryk_engine_launch_count(ryk_engine* e);        /* kernels launched by this engine so far */
 int ryk_engine_synchronize(ryk_engine* e);
 /* CUDA-event timing of the stage-2 k4-layer block (layers 1..14, the tcgen05 kernels) on the engine's stream */

@@ -158,6 +158,8 @@ int ryk_engine_create(int device, ryk_engine** out) {
   RYK_CUDA(cudaMemcpy(e->d_twiddle, tw.data(), sizeof(double2) * tw.size(), cudaMemcpyHostToDevice));
   if (analysis_kernels_init()) return -1;
   if (tc_init()) return -1;
+  if (s1_fused_init()) return -1;
+  { const char* ev = getenv("RYK_S1_FUSED"); e->s1_fused = !(ev && atoi(ev) == 0); }
   RYK_CUDA(cudaMalloc(&e->d_colmin, sizeof(float) * 64 * 512));   // stage-2 prologue scratch (never allocated inside a graph capture)
   *out = h;
   return 0;
@@ -186,6 +188,9 @@ int ryk_engine_set_precision(ryk_engine* h, int mode) {
   return 0;
 }
 int ryk_engine_get_precision(ryk_engine* h) { return E(h)->precision; }
+// Stage 1 as one cluster kernel (default) or as the 16-layer sequence; returns the cluster size in use (<= 0: kernel unavailable).
+// Sessions capture their stage-1 graphs at creation: switch before creating them.
+int ryk_engine_set_stage1_fused(ryk_engine* h, int enable) { E(h)->s1_fused = enable != 0; return s1_fused_cluster_size(); }
 long long ryk_engine_launch_count(ryk_engine* h) { return E(h)->launches; }
 int ryk_engine_synchronize(ryk_engine* h) { RYK_CUDA(cudaSetDevice(E(h)->device)); RYK_CUDA(cudaDeviceSynchronize()); return 0; }
 

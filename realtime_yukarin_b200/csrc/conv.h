@@ -29,6 +29,7 @@ struct ConvLayer {
   float host_scale = 1.f, host_shift = 0.f;
   // tensor-core path (filled by tc_layer_prepare)
   const __half* w_tc = nullptr;           // conv: [Cout][KH*KW*Cin]; deconv: [4 classes][Cout][4*Cin]
+  const __half* w_frag = nullptr;         // 1-D k4 layers: mma.sync B-fragment order for the fused stage-1 kernel (s1_map.h)
   float* splitk_ws = nullptr;             // [pixels][Cout] fp32 when ksplit > 1
   int ksplit = 1;
   CUtensorMap tmA0, tmA1, tmB, tmO, tmW;     // inputs, weights, fp16 output, fp32 split-K workspace
@@ -58,6 +59,11 @@ int conv_tc_run(const ConvLayer& L, cudaStream_t st);
 size_t tc_splitk_ws_bytes(const ConvLayer& L, int num_sms);
 bool tc_layer_clusterk(const ConvLayer& L);                 // split-K layer whose partial sums are reduced inside the kernel (no reduce launch)
 void tc_force_pdl(int v);                                // -1 environment default, 0 / 1 forced
+
+// s1_fused.cu: the whole 1-D U-Net as one cluster kernel
+int s1_pack_weights(const float* d_w_chainer, int transposed, int Cin, int Cout, __half* d_out, cudaStream_t st);
+int s1_fused_init();
+int s1_fused_cluster_size();                             // CTAs of the cluster the kernel runs on (<= 0: unavailable)
 
 // conv_tc2.cu
 int tc2_init();

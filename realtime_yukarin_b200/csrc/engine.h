@@ -21,6 +21,7 @@ struct Engine {
   int device = 0;
   cudaStream_t stream = nullptr;
   int precision = 1;                 // 0: FP32 CUDA-core convs everywhere, 1: FP16 tcgen05 tensor-core convs where eligible
+  bool s1_fused = true;              // FP16 mode: stage 1 as ONE cluster kernel (s1_fused.cu) instead of 16 layer launches
   // FFT twiddles
   double2* d_twiddle = nullptr;
   // xorshift128 jump-ahead matrices (synthesis noise stream)

@@ -50,6 +50,7 @@ void unet_destroy(UNet* n) {
   for (auto& L : n->layers) {
     if (L.d_w_direct) cudaFree(L.d_w_direct);
     if (L.d_w_tc) cudaFree(L.d_w_tc);
+    if (L.d_w_frag) cudaFree(L.d_w_frag);
     if (L.d_scale) cudaFree(L.d_scale);
     if (L.d_shift) cudaFree(L.d_shift);
   }
@@ -81,6 +82,10 @@ int unet_set_layer(Engine* e, UNet* n, int idx, const float* W, const float* sca
   if (tc_shape) {
     if (!L.d_w_tc) RYK_CUDA(cudaMalloc(&L.d_w_tc, nw * sizeof(__half)));
     if (pack_weights_tc(d_tmp, L.transposed, L.cin, L.cout, KH, KW, n->ndim == 2 ? L.s : 1, L.s, L.d_w_tc, e->stream)) return -1;
+  }
+  if (n->ndim == 1 && L.k == 4 && L.s == 2 && L.cin % 64 == 0 && L.cout % 16 == 0) {
+    if (!L.d_w_frag) RYK_CUDA(cudaMalloc(&L.d_w_frag, nw * sizeof(__half)));
+    if (s1_pack_weights(d_tmp, L.transposed, L.cin, L.cout, L.d_w_frag, e->stream)) return -1;
   }
   if (!L.d_scale) RYK_CUDA(cudaMalloc(&L.d_scale, L.cout * sizeof(float)));
   if (!L.d_shift) RYK_CUDA(cudaMalloc(&L.d_shift, L.cout * sizeof(float)));
@@ -129,7 +134,7 @@ int unet_get_plan(Engine* e, UNet* n, int B, int H, int W, int precision, UNetPl
     L.KH = n->ndim == 2 ? LW.k : 1; L.KW = LW.k;
     L.SH = n->ndim == 2 ? LW.s : 1; L.SW = LW.s;
     L.PH = n->ndim == 2 ? LW.p : 0; L.PW = LW.p;
-    L.w_direct = LW.d_w_direct; L.w_tc = LW.d_w_tc; L.scale = LW.d_scale; L.shift = LW.d_shift;
+    L.w_direct = LW.d_w_direct; L.w_tc = LW.d_w_tc; L.w_frag = LW.d_w_frag; L.scale = LW.d_scale; L.shift = LW.d_shift;
     L.host_scale_valid = true; L.host_scale = LW.h_scale0; L.host_shift = LW.h_shift0;
     L.in_dtype = act_dt; L.out_dtype = act_dt;
     if (i == 0) {
@@ -157,6 +162,7 @@ int unet_get_plan(Engine* e, UNet* n, int B, int H, int W, int precision, UNetPl
     }
   }
   RYK_CUDA(cudaStreamSynchronize(e->stream));
+  p->fused = s1_fused_eligible(n, p);
   n->plans[key] = p;
   *out = p;
   return 0;
@@ -164,6 +170,7 @@ int unet_get_plan(Engine* e, UNet* n, int B, int H, int W, int precision, UNetPl
 
 // d_in / d_out live in the plan (p->d_in, p->d_out); callers fill / read them stream-ordered.
 int unet_forward(Engine* e, UNetPlan* p, cudaStream_t st, int first_layer, int last_layer) {
+  if (p->fused && e->s1_fused && first_layer == 0 && last_layer == 15) return s1_fused_run(e, p, st);
   const bool prof = e->profile && p->H > 1;        // time the k4 layers (1..14) of the 2-D (stage-2) net
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   for (int i = first_layer; i <= last_layer; ++i) {

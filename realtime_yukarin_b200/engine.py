@@ -50,7 +50,7 @@ EXPORTED_SYMBOLS = [
     'ryk_group_size', 'ryk_session_stage_times', 'ryk_group_submit', 'ryk_group_collect', 'ryk_group_push_device', 'ryk_test_conv_layer', 'ryk_debug_dio', 'ryk_debug_synth_pulses', 'ryk_debug_synth_timebase', 'ryk_engine_profile', 'ryk_engine_profile_read', 'ryk_engine_timer_start', 'ryk_engine_timer_stop',
     'ryk_world_synthesize_length', 'ryk_world_synthesize', 'ryk_output_gate', 'ryk_reblock_create', 'ryk_reblock_destroy',
     'ryk_reblock_push', 'ryk_reblock_push_device', 'ryk_reblock_collect', 'ryk_reblock_result_device', 'ryk_resample_length',
-    'ryk_resample_poly', 'ryk_session_poll', 'ryk_reblock_poll', 'ryk_engine_profile_read2',
+    'ryk_resample_poly', 'ryk_session_poll', 'ryk_reblock_poll', 'ryk_engine_profile_read2', 'ryk_engine_set_stage1_fused',
 ]
 
 
@@ -119,6 +119,10 @@ class Engine(object):
 
     def set_precision(self, mode: str):
         self._check(self.lib.ryk_engine_set_precision(self._h, {'fp32': 0, 'fp16': 1}[mode]))
+
+    def set_stage1_fused(self, enable: bool) -> int:
+        """Stage 1 as one cluster kernel (default) or as 16 layer launches; returns the cluster size (<= 0: unavailable)."""
+        return int(self.lib.ryk_engine_set_stage1_fused(self._h, 1 if enable else 0))
 
     @property
     def precision(self) -> str:
