@@ -73,6 +73,11 @@ int ryk_world_analyze(ryk_engine* e, const float* wave_host, int n, int fs, doub
 int ryk_world_f0(ryk_engine* e, const float* wave_host, int n, int fs, double frame_period_ms,
                  double f0_floor, double f0_ceil, double* f0, double* t);
 int ryk_world_num_frames(int n, int fs, double frame_period_ms);
+/* f0 extractor behind ryk_world_f0 / ryk_world_analyze and sessions created afterwards -- the f0 hook of yukarin's
+ * AcousticFeature.extract (acoustic_feature_wrapper.py:28-33; f0_estimating_method):
+ *   0 = pyworld.dio + pyworld.stonemask (default), 1 = pyworld.harvest + pyworld.stonemask. */
+int ryk_engine_set_f0_method(ryk_engine* e, int method);
+int ryk_engine_get_f0_method(ryk_engine* e);
 
 /* ---- silence gate --------------------------------------------------------------------------- */
 /* mask[n_frames] (0/1); threshold_db < 0 disables the gate (all frames effective). */
@@ -219,6 +224,14 @@ int ryk_debug_synth_timebase(ryk_engine* e, int synth_id, int n, double* if0, do
  * of the most recent analysis that used the (n, fs, frame_period, f0_floor, f0_ceil) plan. */
 int ryk_debug_dio(ryk_engine* e, int n, int fs, double frame_period_ms, double f0_floor, double f0_ceil,
                   double* f0_raw, double* cand, double* score, int* counts);
+/* Harvest internals of the most recent analysis with this plan (engine in f0 method 1): info = {channels, 1 ms frames, decimated
+ * length, fft size, candidate columns, decimation ratio, used columns}; y [info[2]], raw [channels][frames], cand / score
+ * [frames][columns] (after refinement and removal), best / basic [frames], f0_raw [n / hop + 1] (before StoneMask).  Any may be NULL. */
+int ryk_debug_harvest(ryk_engine* e, int n, int fs, double frame_period_ms, double f0_floor, double f0_ceil, int* info, double* y,
+                      double* raw, double* cand, double* score, double* best, double* basic, double* f0_raw);
+/* Stage-1 forward of padded length Tp stand-alone: ms per forward as one cluster kernel / as 16 layer launches, and the fused
+ * kernel's phase timeline (31 doubles, us). */
+int ryk_debug_stage1_bench(ryk_engine* e, int Tp, int iters, float* ms_fused, float* ms_layered, double* timeline_us);
 /* One conv (transposed = 0) or transposed-conv layer of the U-Nets in isolation, host fp32 NHWC tensors in and
  * out, weights in the Chainer layout; use_tc selects the FP16 tcgen05 kernel (1) or the FP32 CUDA-core kernel (0).
  * `repeat` extra timed runs report the mean device time per run (ms) -- used by the unit parity tests and ncu. */

@@ -32,6 +32,7 @@ class PathConfig:
     alpha: float = 0.466
     threshold_db: Optional[float] = 60.0
     vocoder_buffer_size: int = 1024
+    f0_method: str = 'dio'        # 'dio' | 'harvest' (yukarin's f0_estimating_method; both are followed by StoneMask)
 
     @property
     def hop(self) -> int:
@@ -45,7 +46,10 @@ def extract_features(wave: np.ndarray, cfg: PathConfig) -> Dict[str, np.ndarray]
     if n_out == 0:
         return dict(f0=np.zeros((0, 1), np.float32), sp=np.zeros((0, nb), np.float32), ap=np.zeros((0, nb), np.float32),
                     mc=np.zeros((0, cfg.order + 1), np.float32), voiced=np.zeros((0, 1), bool))
-    f0, t = W.dio(x, cfg.fs, cfg.frame_period, cfg.f0_floor, cfg.f0_ceil)
+    if cfg.f0_method == 'harvest':
+        f0, t = W.harvest(x, cfg.fs, cfg.frame_period, cfg.f0_floor, cfg.f0_ceil)
+    else:
+        f0, t = W.dio(x, cfg.fs, cfg.frame_period, cfg.f0_floor, cfg.f0_ceil)
     f0 = W.stonemask(x, cfg.fs, t, f0)
     sp = W.cheaptrick(x, cfg.fs, t, f0, cfg.fft_length)
     ap = W.d4c(x, cfg.fs, t, f0, cfg.fft_length)

@@ -100,6 +100,40 @@ def dio(x, fs, frame_period=5.0, f0_floor=71.0, f0_ceil=800.0, debug=False):
     return f0, t
 
 
+def harvest_geometry(n, fs, f0_floor=71.0, f0_ceil=800.0):
+    """(channels, basic 1 ms frames, decimated length, fft size, candidate columns, decimation ratio) of HarvestGeneral."""
+    info = (ctypes.c_int * 6)()
+    lib().wo_harvest_geometry(ctypes.c_int(int(n)), ctypes.c_int(int(fs)), ctypes.c_double(f0_floor), ctypes.c_double(f0_ceil), info)
+    return tuple(int(v) for v in info)
+
+
+def harvest(x, fs, frame_period=5.0, f0_floor=71.0, f0_ceil=800.0, debug=False):
+    """pyworld.harvest restated (world_oracle.c, Harvest section).  debug=True also returns the intermediate arrays
+    dict(y, raw, cand, score, best, basic, nc) used to localise a GPU mismatch stage by stage."""
+    x = _f64(x)
+    n = lib().wo_harvest_num_frames(int(fs), len(x), ctypes.c_double(frame_period))
+    t, f0 = np.empty(n), np.empty(n)
+    ch, nf, ylen, fft_size, maxc, ratio = harvest_geometry(len(x), fs, f0_floor, f0_ceil)
+    dbg = dict(y=np.zeros(ylen), raw=np.zeros((ch, nf)), cand=np.zeros((nf, maxc)), score=np.zeros((nf, maxc)), best=np.zeros(nf),
+               basic=np.zeros(nf))
+    nc = ctypes.c_int(0)
+    lib().wo_harvest_ex(_dp(x), ctypes.c_int(len(x)), ctypes.c_int(int(fs)), ctypes.c_double(frame_period), ctypes.c_double(f0_floor),
+                        ctypes.c_double(f0_ceil), _dp(t), _dp(f0), _dp(dbg['y']), _dp(dbg['raw']), _dp(dbg['cand']), _dp(dbg['score']),
+                        _dp(dbg['best']), _dp(dbg['basic']), ctypes.byref(nc))
+    if debug:
+        dbg['nc'] = int(nc.value)
+        return f0, t, dbg
+    return f0, t
+
+
+def decimate(x, r):
+    """matlabfunctions.cpp decimate() (zero-phase Chebyshev I of order 3, every r-th sample)."""
+    x = _f64(x)
+    y = np.zeros((len(x) - 1) // r + 1 + 16)      # the C loop also emits ceil(9 / r) - 1 samples of the reflected tail
+    lib().wo_decimate(_dp(x), ctypes.c_int(len(x)), ctypes.c_int(int(r)), _dp(y))
+    return y[:(len(x) - 1) // r + 1]
+
+
 def stonemask(x, fs, t, f0):
     x, t, f0 = _f64(x), _f64(t), _f64(f0)
     out = np.empty_like(f0)

@@ -1222,3 +1222,507 @@ double wo_stft_power_db_mean(const double *wave, int n, int n_fft, int hop, doub
   free(win); free(buf); free(re); free(im); free(db);
   return acc / ((double)frames * nb);
 }
+
+/* ================================================================== Harvest (harvest.cpp, WORLD v0.2.3+)
+ * f0 extractor of `pyworld.harvest(x, fs, f0_floor, f0_ceil, frame_period)`; the row the round-1 review added because
+ * BASELINE.json's north_star names "DIO/Harvest f0" (call site: realtime_voice_conversion/yukarin_wrapper/
+ * acoustic_feature_wrapper.py:28-33 -> yukarin.AcousticFeature.extract_f0; become-yukarin's dataset parameter
+ * f0_estimating_method='harvest').  PARITY UNPINNED like the rest of this file: restated from the published
+ * algorithm (M. Morise, "Harvest: A high-performance fundamental frequency estimator from speech signals", Interspeech 2017;
+ * harvest.cpp / matlabfunctions.cpp decimate()).  Structure:
+ *   decimate to ~8 kHz (zero-phase 3rd-order Chebyshev I, cheby1(3, 0.05 dB, 0.8 / r): the table below reproduces WORLD's
+ *   hard-coded FilterForDecimate coefficients -- r = 2, 11, 12 were checked against the digits of the published source),
+ *   DC removal -> 40 channels / octave of Nuttall x cosine band-pass filters over [0.9 floor, 1.1 ceil] -> four zero-crossing
+ *   interval trains per channel -> raw candidates at a 1 ms basic period -> candidates = mean over >= 10 consecutive agreeing
+ *   channels -> overlap +-3 frames -> refinement by instantaneous frequency (StoneMask-like) with a score -> removal of
+ *   candidates unsupported by a neighbouring frame (5 %) -> FixStep1..4 contour tracking -> zero-phase 2nd-order Butterworth
+ *   smoothing of each voiced section -> sub-sampling to frame_period.
+ * DECIDE H1: the output array is zero-initialised before SmoothF0Contour writes the voiced sections.
+ * DECIDE H2: ExtendSub's running `mean_f0` is NOT reset between sections (as in the published source).                      */
+static const double kDecA[13][3] = {{0, 0, 0}, {0, 0, 0},
+  {0.041156734567757161, -0.42599112459189592, 0.041037215479961149},
+  {0.95039378983237421, -0.67429146741526802, 0.15412211621346472},
+  {1.4499664446880223, -0.98943497080950538, 0.24578252340690199},
+  {1.761093965428056, -1.255491484385977, 0.32371865077882145},
+  {1.9715352749512141, -1.4686795689225343, 0.38939084349657005},
+  {2.1225239019534698, -1.6395144861046296, 0.44469707800587344},
+  {2.2357462340187593, -1.7780899984041356, 0.49152555365968698},
+  {2.3236003491759578, -1.89215456174636, 0.53148928133729068},
+  {2.3936475118069382, -1.9873904075111852, 0.56588799790270516},
+  {2.450743295230728, -2.0679490460197805, 0.59574774438332112},
+  {2.4981398605924205, -2.1368928194784025, 0.62187513816221485}};
+static const double kDecB[13][2] = {{0, 0}, {0, 0},
+  {0.16797464681802221, 0.50392394045406663},
+  {0.071221945171178622, 0.21366583551353585},
+  {0.03671075033932264, 0.11013225101796792},
+  {0.021334858522387451, 0.064004575567162353},
+  {0.013469181309343806, 0.04040754392803142},
+  {0.0090366882681607811, 0.027110064804482345},
+  {0.0063522763407111793, 0.019056829022133539},
+  {0.0046331164041389242, 0.013899349212416773},
+  {0.0034818622251927374, 0.010445586675578211},
+  {0.0026822508007164039, 0.0080467524021492123},
+  {0.0021097275904708771, 0.0063291827714126309}};
+
+void wo_decimate_coefficients(int r, double *a3, double *b2) {
+  for (int i = 0; i < 3; ++i) a3[i] = kDecA[r][i];
+  for (int i = 0; i < 2; ++i) b2[i] = kDecB[r][i];
+}
+
+static void filter_for_decimate(const double *x, int n, int r, double *y) {
+  const double *a = kDecA[r], *b = kDecB[r];
+  double w[3] = {0.0, 0.0, 0.0};
+  for (int i = 0; i < n; ++i) {
+    double wt = x[i] + a[0] * w[0] + a[1] * w[1] + a[2] * w[2];
+    y[i] = b[0] * wt + b[1] * w[0] + b[1] * w[1] + b[0] * w[2];
+    w[2] = w[1]; w[1] = w[0]; w[0] = wt;
+  }
+}
+
+/* matlabfunctions.cpp decimate(): reflect 9 samples, filter forwards and backwards, keep every r-th sample */
+void wo_decimate(const double *x, int x_length, int r, double *y) {
+  const int nf = 9, n = x_length + nf * 2;
+  double *t1 = (double *)malloc(sizeof(double) * n), *t2 = (double *)malloc(sizeof(double) * n);
+  for (int i = 0; i < nf; ++i) t1[i] = 2 * x[0] - x[nf - i];
+  for (int i = nf; i < nf + x_length; ++i) t1[i] = x[i - nf];
+  for (int i = nf + x_length; i < n; ++i) t1[i] = 2 * x[x_length - 1] - x[x_length - 2 - (i - (nf + x_length))];
+  filter_for_decimate(t1, n, r, t2);
+  for (int i = 0; i < n; ++i) t1[i] = t2[n - i - 1];
+  filter_for_decimate(t1, n, r, t2);
+  for (int i = 0; i < n; ++i) t1[i] = t2[n - i - 1];
+  int nout = (x_length - 1) / r + 1;
+  int nbeg = r - r * nout + x_length;
+  int count = 0;
+  for (int i = nbeg; i < x_length + nf; i += r) y[count++] = t1[i + nf - 1];
+  free(t1); free(t2);
+}
+
+int wo_harvest_num_frames(int fs, int x_length, double frame_period) { return (int)(1000.0 * x_length / fs / frame_period) + 1; }
+
+/* geometry of HarvestGeneral for a given input: info = {channels, basic frames, y_length, fft_size, max_candidates, decimation ratio} */
+void wo_harvest_geometry(int x_length, int fs, double f0_floor, double f0_ceil, int *info) {
+  const double channels_in_octave = 40.0;
+  int ratio = wo_matlab_round(fs / 8000.0);
+  double lo = f0_floor * 0.9, hi = f0_ceil * 1.1;
+  int channels = 1 + (int)(log(hi / lo) / WO_LOG2 * channels_in_octave);
+  double b0 = lo * pow(2.0, 1.0 / channels_in_octave);
+  int y_length = (int)ceil((double)x_length / ratio);
+  double actual_fs = (double)fs / ratio;
+  info[0] = channels;
+  info[1] = wo_harvest_num_frames(fs, x_length, 1.0);
+  info[2] = y_length;
+  info[3] = wo_suitable_fft_size(y_length + 5 + 2 * (int)(2.0 * actual_fs / b0));
+  info[4] = wo_matlab_round(channels / 10.0) * 7;
+  info[5] = ratio;
+}
+
+/* GetWaveformAndSpectrumSub + DC removal: y[0..y_length) */
+static void harvest_waveform(const double *x, int x_length, int y_length, int ratio, double *y) {
+  if (ratio == 1) { for (int i = 0; i < x_length; ++i) y[i] = x[i]; }
+  else {
+    int lag = (int)(ceil(140.0 / ratio) * ratio);
+    int nx = x_length + lag * 2;
+    double *nx_ = (double *)malloc(sizeof(double) * nx), *ny = (double *)calloc(nx, sizeof(double));
+    for (int i = 0; i < lag; ++i) nx_[i] = x[0];
+    for (int i = lag; i < lag + x_length; ++i) nx_[i] = x[i - lag];
+    for (int i = lag + x_length; i < nx; ++i) nx_[i] = x[x_length - 1];
+    wo_decimate(nx_, nx, ratio, ny);
+    for (int i = 0; i < y_length; ++i) y[i] = ny[lag / ratio + i];
+    free(nx_); free(ny);
+  }
+  double mean_y = 0.0;
+  for (int i = 0; i < y_length; ++i) mean_y += y[i];
+  mean_y /= y_length;
+  for (int i = 0; i < y_length; ++i) y[i] -= mean_y;
+}
+
+/* GetRefinedF0 = GetMeanF0 + FixF0 + acceptance test */
+static void harvest_refine(const double *x, int x_length, double fs, double pos, double f0_cur, double f0_floor, double f0_ceil,
+                           double *refined, double *score_out) {
+  *refined = 0.0; *score_out = 0.0;
+  if (f0_cur <= 0.0) return;
+  int half = (int)(1.5 * fs / f0_cur + 1.0);
+  double wlen_time = (2.0 * half + 1.0) / fs;
+  int blen = half * 2 + 1;
+  int fft_size = (int)pow(2.0, 2.0 + (int)(log(half * 2.0 + 1.0) / WO_LOG2));
+  double *mainw = (double *)malloc(sizeof(double) * blen), *diffw = (double *)malloc(sizeof(double) * blen);
+  double *buf = (double *)calloc(fft_size, sizeof(double));
+  double *mr = (double *)malloc(sizeof(double) * fft_size), *mi = (double *)malloc(sizeof(double) * fft_size);
+  double *dr = (double *)malloc(sizeof(double) * fft_size), *di = (double *)malloc(sizeof(double) * fft_size);
+  int basic_index = wo_matlab_round((pos + (double)(-half) / fs) * fs + 0.001);
+  for (int i = 0; i < blen; ++i) {
+    double tmp = ((basic_index + i) - 1.0) / fs - pos;
+    mainw[i] = 0.42 + 0.5 * cos(2.0 * WO_PI * tmp / wlen_time) + 0.08 * cos(4.0 * WO_PI * tmp / wlen_time);
+  }
+  diffw[0] = -mainw[1] / 2.0;
+  for (int i = 1; i < blen - 1; ++i) diffw[i] = -(mainw[i + 1] - mainw[i - 1]) / 2.0;
+  diffw[blen - 1] = mainw[blen - 2] / 2.0;
+  for (int i = 0; i < blen; ++i) buf[i] = x[imax(0, imin(x_length - 1, basic_index + i - 1))] * mainw[i];
+  rfft(buf, fft_size, mr, mi);
+  for (int i = 0; i < blen; ++i) buf[i] = x[imax(0, imin(x_length - 1, basic_index + i - 1))] * diffw[i];
+  rfft(buf, fft_size, dr, di);
+  int nh = imin((int)(fs / 2.0 / f0_cur), 6);
+  double numerator = 0.0, denominator = 0.0, score = 0.0;
+  for (int i = 0; i < nh; ++i) {
+    int index = imin(wo_matlab_round(f0_cur * fft_size / fs * (i + 1)), fft_size / 2);
+    double power = mr[index] * mr[index] + mi[index] * mi[index];
+    double numer_i = mr[index] * di[index] - mi[index] * dr[index];
+    double inst = power == 0.0 ? 0.0 : (double)index * fs / fft_size + numer_i / power * fs / 2.0 / WO_PI;
+    double amp = sqrt(power);
+    numerator += amp * inst;
+    denominator += amp * (i + 1.0);
+    score += fabs((inst / (i + 1.0) - f0_cur) / f0_cur);
+  }
+  double rf = numerator / (denominator + WO_SAFE_MIN);
+  double sc = 1.0 / (score / nh + WO_SAFE_MIN);
+  free(mainw); free(diffw); free(buf); free(mr); free(mi); free(dr); free(di);
+  if (rf < f0_floor || rf > f0_ceil || sc < 2.5) return;
+  *refined = rf; *score_out = sc;
+}
+
+static double select_best_f0(double reference_f0, const double *cands, int n, double allowed_range, double *best_error) {
+  double best_f0 = 0.0;
+  *best_error = allowed_range;
+  for (int i = 0; i < n; ++i) {
+    double tmp = fabs(reference_f0 - cands[i]) / reference_f0;
+    if (tmp > *best_error) continue;
+    best_f0 = cands[i];
+    *best_error = tmp;
+  }
+  return best_f0;
+}
+
+static int get_boundary_list(const double *f0, int n, int *boundary_list) {
+  int nb = 0;
+  int *vuv = (int *)malloc(sizeof(int) * n);
+  for (int i = 0; i < n; ++i) vuv[i] = f0[i] > 0 ? 1 : 0;
+  vuv[0] = vuv[n - 1] = 0;
+  for (int i = 1; i < n; ++i)
+    if (vuv[i] - vuv[i - 1] != 0) { boundary_list[nb] = i - nb % 2; nb++; }
+  free(vuv);
+  return nb;
+}
+
+static void get_multi_channel_f0(const double *f0, int n, const int *bl, int nb, double **mc) {
+  for (int i = 0; i < nb / 2; ++i) {
+    for (int j = 0; j < bl[i * 2]; ++j) mc[i][j] = 0.0;
+    for (int j = bl[i * 2]; j <= bl[i * 2 + 1]; ++j) mc[i][j] = f0[j];
+    for (int j = bl[i * 2 + 1] + 1; j < n; ++j) mc[i][j] = 0.0;
+  }
+}
+
+static int extend_f0(int origin, int last_point, int shift, const double *cand, int nc_stride, int nc, double allowed_range, double *ext) {
+  const int threshold = 4;
+  double tmp_f0 = ext[origin];
+  int shifted_origin = origin;
+  int distance = abs(last_point - origin);
+  int count = 0;
+  double dummy;
+  for (int i = 0; i <= distance; ++i) {
+    int idx = origin + shift * i + shift;
+    ext[idx] = select_best_f0(tmp_f0, cand + (size_t)idx * nc_stride, nc, allowed_range, &dummy);
+    if (ext[idx] == 0.0) count++;
+    else { tmp_f0 = ext[idx]; count = 0; shifted_origin = idx; }
+    if (count == threshold) break;
+  }
+  return shifted_origin;
+}
+
+static double search_score(double f0, const double *cands, const double *scores, int n) {
+  double score = 0.0;
+  for (int i = 0; i < n; ++i)
+    if (f0 == cands[i] && score < scores[i]) score = scores[i];
+  return score;
+}
+
+static int merge_f0_sub(const double *f0_1, int st1, int ed1, const double *f0_2, int st2, int ed2, const double *cand, const double *score,
+                        int stride, int nc, double *merged) {
+  if (st1 <= st2 && ed1 >= ed2) return ed1;
+  double score1 = 0.0, score2 = 0.0;
+  for (int i = st2; i <= ed1; ++i) {
+    score1 += search_score(f0_1[i], cand + (size_t)i * stride, score + (size_t)i * stride, nc);
+    score2 += search_score(f0_2[i], cand + (size_t)i * stride, score + (size_t)i * stride, nc);
+  }
+  if (score1 > score2) { for (int i = ed1; i <= ed2; ++i) merged[i] = f0_2[i]; }
+  else { for (int i = st2; i <= ed2; ++i) merged[i] = f0_2[i]; }
+  return ed2;
+}
+
+/* FixF0Contour: cand / score are [nf][stride] with nc valid columns */
+static void harvest_fix_contour(const double *cand, const double *score, int nf, int stride, int nc, double *best) {
+  double *c1 = (double *)calloc(nf, sizeof(double)), *c2 = (double *)calloc(nf, sizeof(double));
+  int *bl = (int *)malloc(sizeof(int) * (nf + 2));
+  /* SearchF0Base */
+  for (int i = 0; i < nf; ++i) {
+    double best_score = 0.0;
+    c1[i] = 0.0;
+    for (int j = 0; j < nc; ++j)
+      if (score[(size_t)i * stride + j] > best_score) { c1[i] = cand[(size_t)i * stride + j]; best_score = score[(size_t)i * stride + j]; }
+  }
+  /* FixStep1: rapid changes -> 0 (allowed range 0.008) */
+  for (int i = 0; i < nf; ++i) c2[i] = 0.0;
+  for (int i = 2; i < nf; ++i) {
+    if (c1[i] == 0.0) continue;
+    double ref = c1[i - 1] * 2 - c1[i - 2];
+    c2[i] = (fabs((c1[i] - ref) / ref) > 0.008 && fabs((c1[i] - c1[i - 1])) / c1[i - 1] > 0.008) ? 0.0 : c1[i];
+  }
+  /* FixStep2: short voiced sections (< 6 frames) removed */
+  for (int i = 0; i < nf; ++i) c1[i] = c2[i];
+  int nb = get_boundary_list(c2, nf, bl);
+  for (int i = 0; i < nb / 2; ++i) {
+    if (bl[i * 2 + 1] - bl[i * 2] >= 6) continue;
+    for (int j = bl[i * 2]; j <= bl[i * 2 + 1]; ++j) c1[j] = 0.0;
+  }
+  /* FixStep3: extend sections along the candidates (18 %), keep long ones, merge */
+  for (int i = 0; i < nf; ++i) c2[i] = c1[i];
+  nb = get_boundary_list(c1, nf, bl);
+  int ns = nb / 2;
+  if (ns > 0) {
+    double **mc = (double **)malloc(sizeof(double *) * ns);
+    for (int i = 0; i < ns; ++i) mc[i] = (double *)malloc(sizeof(double) * nf);
+    get_multi_channel_f0(c1, nf, bl, nb, mc);
+    for (int i = 0; i < ns; ++i) {      /* Extend */
+      int ed = extend_f0(bl[i * 2 + 1], imin(nf - 2, bl[i * 2 + 1] + 100), 1, cand, stride, nc, 0.18, mc[i]);
+      int st = extend_f0(bl[i * 2], imax(1, bl[i * 2] - 100), -1, cand, stride, nc, 0.18, mc[i]);
+      bl[i * 2 + 1] = ed; bl[i * 2] = st;
+    }
+    int count = 0;                      /* ExtendSub (DECIDE H2: mean_f0 carries over) */
+    double mean_f0 = 0.0;
+    for (int i = 0; i < ns; ++i) {
+      int st = bl[i * 2], ed = bl[i * 2 + 1];
+      for (int j = st; j < ed; ++j) mean_f0 += mc[i][j];
+      mean_f0 /= ed - st;
+      if (2200.0 / mean_f0 < ed - st) {
+        double *tp = mc[count]; mc[count] = mc[i]; mc[i] = tp;
+        int t = bl[count * 2]; bl[count * 2] = bl[i * 2]; bl[i * 2] = t;
+        t = bl[count * 2 + 1]; bl[count * 2 + 1] = bl[i * 2 + 1]; bl[i * 2 + 1] = t;
+        count++;
+      }
+    }
+    if (count != 0) {                   /* MergeF0 */
+      int *order = (int *)malloc(sizeof(int) * count);
+      for (int i = 0; i < count; ++i) order[i] = i;
+      for (int i = 1; i < count; ++i)
+        for (int j = i - 1; j >= 0; --j) {
+          if (bl[order[j] * 2] > bl[order[i] * 2]) { int t = order[i]; order[i] = order[j]; order[j] = t; }
+          else break;
+        }
+      for (int i = 0; i < nf; ++i) c2[i] = mc[0][i];
+      for (int i = 1; i < count; ++i) {
+        if (bl[order[i] * 2] - bl[1] > 0) {
+          for (int j = bl[order[i] * 2]; j <= bl[order[i] * 2 + 1]; ++j) c2[j] = mc[order[i]][j];
+          bl[0] = bl[order[i] * 2];
+          bl[1] = bl[order[i] * 2 + 1];
+        } else {
+          bl[1] = merge_f0_sub(c2, bl[0], bl[1], mc[order[i]], bl[order[i] * 2], bl[order[i] * 2 + 1], cand, score, stride, nc, c2);
+        }
+      }
+      free(order);
+    }
+    for (int i = 0; i < ns; ++i) free(mc[i]);
+    free(mc);
+  }
+  /* FixStep4: unvoiced gaps shorter than 9 frames are bridged linearly */
+  for (int i = 0; i < nf; ++i) best[i] = c2[i];
+  nb = get_boundary_list(c2, nf, bl);
+  for (int i = 0; i < nb / 2 - 1; ++i) {
+    int distance = bl[(i + 1) * 2] - bl[i * 2 + 1] - 1;
+    if (distance >= 9) continue;
+    double tmp0 = c2[bl[i * 2 + 1]] + 1, tmp1 = c2[bl[(i + 1) * 2]] - 1;
+    double coefficient = (tmp1 - tmp0) / (distance + 1.0);
+    int count = 1;
+    for (int j = bl[i * 2 + 1] + 1; j <= bl[(i + 1) * 2] - 1; ++j) best[j] = tmp0 + coefficient * count++;
+  }
+  free(c1); free(c2); free(bl);
+}
+
+/* FilteringF0: x is padded with its edge values outside [st, ed]; 2nd-order Butterworth forwards then backwards */
+static void harvest_filtering_f0(double *x, int n, int st, int ed, double *y) {
+  const double b[2] = {0.0078202080334971724, 0.015640416066994345};
+  const double a[2] = {1.7347257688092754, -0.76600660094326412};
+  double w[2] = {0.0, 0.0};
+  double *tmp_x = (double *)malloc(sizeof(double) * n);
+  for (int i = 0; i < st; ++i) x[i] = x[st];
+  for (int i = ed + 1; i < n; ++i) x[i] = x[ed];
+  for (int i = 0; i < n; ++i) {
+    double wt = x[i] + a[0] * w[0] + a[1] * w[1];
+    tmp_x[n - i - 1] = b[0] * wt + b[1] * w[0] + b[0] * w[1];
+    w[1] = w[0]; w[0] = wt;
+  }
+  w[0] = w[1] = 0.0;
+  for (int i = 0; i < n; ++i) {
+    double wt = tmp_x[i] + a[0] * w[0] + a[1] * w[1];
+    y[n - i - 1] = b[0] * wt + b[1] * w[0] + b[0] * w[1];
+    w[1] = w[0]; w[0] = wt;
+  }
+  free(tmp_x);
+}
+
+static void harvest_smooth(const double *f0, int nf, double *smoothed) {
+  const int lag = 300;
+  int n = nf + lag * 2;
+  double *contour = (double *)calloc(n, sizeof(double));
+  for (int i = 0; i < nf; ++i) contour[lag + i] = f0[i];
+  int *bl = (int *)malloc(sizeof(int) * (n + 2));
+  int nb = get_boundary_list(contour, n, bl);
+  int ns = nb / 2;
+  for (int i = 0; i < nf; ++i) smoothed[i] = 0.0;        /* DECIDE H1 */
+  if (ns > 0) {
+    double **mc = (double **)malloc(sizeof(double *) * ns);
+    for (int i = 0; i < ns; ++i) mc[i] = (double *)malloc(sizeof(double) * n);
+    get_multi_channel_f0(contour, n, bl, nb, mc);
+    for (int i = 0; i < ns; ++i) {
+      harvest_filtering_f0(mc[i], n, bl[i * 2], bl[i * 2 + 1], contour);
+      for (int j = bl[i * 2]; j <= bl[i * 2 + 1]; ++j) smoothed[j - lag] = contour[j];
+    }
+    for (int i = 0; i < ns; ++i) free(mc[i]);
+    free(mc);
+  }
+  free(contour); free(bl);
+}
+
+/* Harvest().  Optional dumps (NULL to skip): dbg_y [y_length], dbg_raw [channels][nf1], dbg_cand / dbg_score [nf1][max_candidates]
+ * (after refinement and RemoveUnreliableCandidates), dbg_best [nf1] (FixF0Contour), dbg_basic [nf1] (smoothed, 1 ms), dbg_nc [1]. */
+void wo_harvest_ex(const double *x, int x_length, int fs, double frame_period, double f0_floor, double f0_ceil,
+                   double *temporal_positions, double *f0, double *dbg_y, double *dbg_raw, double *dbg_cand, double *dbg_score,
+                   double *dbg_best, double *dbg_basic, int *dbg_nc) {
+  int info[6];
+  wo_harvest_geometry(x_length, fs, f0_floor, f0_ceil, info);
+  const int channels = info[0], nf = info[1], y_length = info[2], fft_size = info[3], max_cand = info[4], ratio = info[5];
+  const double actual_fs = (double)fs / ratio;
+  const double lo = f0_floor * 0.9;
+  double *boundary = (double *)malloc(sizeof(double) * channels);
+  for (int i = 0; i < channels; ++i) boundary[i] = lo * pow(2.0, (i + 1) / 40.0);
+  double *tpos = (double *)malloc(sizeof(double) * nf);
+  for (int i = 0; i < nf; ++i) tpos[i] = i * 1.0 / 1000.0;
+
+  double *y = (double *)calloc(fft_size, sizeof(double));
+  harvest_waveform(x, x_length, y_length, ratio, y);
+  if (dbg_y) memcpy(dbg_y, y, sizeof(double) * y_length);
+  double *yr = (double *)malloc(sizeof(double) * fft_size), *yi = (double *)malloc(sizeof(double) * fft_size);
+  rfft(y, fft_size, yr, yi);
+
+  /* GetRawF0Candidates */
+  double *raw = (double *)calloc((size_t)channels * nf, sizeof(double));
+  double *bp = (double *)malloc(sizeof(double) * fft_size), *filtered = (double *)malloc(sizeof(double) * fft_size);
+  double *fr = (double *)malloc(sizeof(double) * fft_size), *fi = (double *)malloc(sizeof(double) * fft_size);
+  double *loc[4], *itv[4], *interp[4];
+  for (int e = 0; e < 4; ++e) {
+    loc[e] = (double *)malloc(sizeof(double) * y_length);
+    itv[e] = (double *)malloc(sizeof(double) * y_length);
+    interp[e] = (double *)malloc(sizeof(double) * nf);
+  }
+  for (int b = 0; b < channels; ++b) {
+    /* GetFilteredSignal */
+    int flh = wo_matlab_round(actual_fs / boundary[b] * 2.0);
+    nuttall_window(flh * 2 + 1, bp);
+    for (int i = -flh; i <= flh; ++i) bp[i + flh] *= cos(2 * WO_PI * boundary[b] * i / actual_fs);
+    for (int i = flh * 2 + 1; i < fft_size; ++i) bp[i] = 0.0;
+    rfft(bp, fft_size, fr, fi);
+    for (int i = 0; i <= fft_size / 2; ++i) {
+      double tmp = yr[i] * fr[i] - yi[i] * fi[i];
+      fi[i] = yr[i] * fi[i] + yi[i] * fr[i];
+      fr[i] = tmp;
+    }
+    irfft_unnorm(fr, fi, fft_size, filtered);
+    int index_bias = flh + 1;
+    for (int i = 0; i < y_length; ++i) filtered[i] = filtered[i + index_bias];
+    /* GetFourZeroCrossingIntervals */
+    int cnt[4];
+    cnt[0] = zero_crossing_engine(filtered, y_length, actual_fs, loc[0], itv[0]);
+    for (int i = 0; i < y_length; ++i) filtered[i] = -filtered[i];
+    cnt[1] = zero_crossing_engine(filtered, y_length, actual_fs, loc[1], itv[1]);
+    for (int i = 0; i < y_length - 1; ++i) filtered[i] = filtered[i] - filtered[i + 1];
+    cnt[2] = zero_crossing_engine(filtered, y_length - 1, actual_fs, loc[2], itv[2]);
+    for (int i = 0; i < y_length - 1; ++i) filtered[i] = -filtered[i];
+    cnt[3] = zero_crossing_engine(filtered, y_length - 1, actual_fs, loc[3], itv[3]);
+    /* GetF0CandidateContour */
+    double *c = raw + (size_t)b * nf;
+    if (!(cnt[0] > 2 && cnt[1] > 2 && cnt[2] > 2 && cnt[3] > 2)) continue;      /* row stays 0 */
+    for (int e = 0; e < 4; ++e) wo_interp1(loc[e], itv[e], cnt[e], tpos, nf, interp[e]);
+    double upper = boundary[b] * 1.1, lower = boundary[b] * 0.9;
+    for (int i = 0; i < nf; ++i) {
+      c[i] = (interp[0][i] + interp[1][i] + interp[2][i] + interp[3][i]) / 4.0;
+      if (c[i] > upper || c[i] < lower || c[i] > f0_ceil || c[i] < f0_floor) c[i] = 0.0;
+    }
+  }
+  if (dbg_raw) memcpy(dbg_raw, raw, sizeof(double) * (size_t)channels * nf);
+
+  /* DetectOfficialF0Candidates */
+  double *cand = (double *)calloc((size_t)nf * max_cand, sizeof(double));
+  double *score = (double *)calloc((size_t)nf * max_cand, sizeof(double));
+  int *vuv = (int *)malloc(sizeof(int) * channels), *st = (int *)malloc(sizeof(int) * channels), *ed = (int *)malloc(sizeof(int) * channels);
+  int n_cand = 0;
+  for (int i = 0; i < nf; ++i) {
+    for (int j = 0; j < channels; ++j) vuv[j] = raw[(size_t)j * nf + i] > 0 ? 1 : 0;
+    vuv[0] = vuv[channels - 1] = 0;
+    int nsec = 0;
+    for (int j = 1; j < channels; ++j) {
+      int tmp = vuv[j] - vuv[j - 1];
+      if (tmp == 1) st[nsec] = j;
+      if (tmp == -1) ed[nsec++] = j;
+    }
+    int nc = 0;
+    for (int s = 0; s < nsec; ++s) {
+      if (ed[s] - st[s] < 10) continue;
+      double tmp_f0 = 0.0;
+      for (int j = st[s]; j < ed[s]; ++j) tmp_f0 += raw[(size_t)j * nf + i];
+      tmp_f0 /= (ed[s] - st[s]);
+      if (nc < max_cand / 7) cand[(size_t)i * max_cand + nc++] = tmp_f0;   /* 7 x base columns must fit (never binds: <= 13 runs of >= 10 channels) */
+    }
+    n_cand = imax(n_cand, nc);
+  }
+  /* OverlapF0Candidates (+-3 frames) */
+  const int n_ov = 3;
+  for (int i = 1; i <= n_ov; ++i)
+    for (int j = 0; j < n_cand; ++j) {
+      for (int k = i; k < nf; ++k) cand[(size_t)k * max_cand + j + n_cand * i] = cand[(size_t)(k - i) * max_cand + j];
+      for (int k = 0; k < nf - i; ++k) cand[(size_t)k * max_cand + j + n_cand * (i + n_ov)] = cand[(size_t)(k + i) * max_cand + j];
+    }
+  const int nc_all = n_cand * 7;
+  if (dbg_nc) *dbg_nc = nc_all;
+  /* RefineF0Candidates */
+  for (int i = 0; i < nf; ++i)
+    for (int j = 0; j < nc_all; ++j) {
+      double rf, sc;
+      harvest_refine(y, y_length, actual_fs, tpos[i], cand[(size_t)i * max_cand + j], f0_floor, f0_ceil, &rf, &sc);
+      cand[(size_t)i * max_cand + j] = rf; score[(size_t)i * max_cand + j] = sc;
+    }
+  /* RemoveUnreliableCandidates */
+  {
+    double *tmpc = (double *)malloc(sizeof(double) * (size_t)nf * max_cand);
+    memcpy(tmpc, cand, sizeof(double) * (size_t)nf * max_cand);
+    for (int i = 1; i < nf - 1; ++i)
+      for (int j = 0; j < nc_all; ++j) {
+        double ref = cand[(size_t)i * max_cand + j], e1, e2;
+        if (ref == 0) continue;
+        select_best_f0(ref, tmpc + (size_t)(i + 1) * max_cand, nc_all, 1.0, &e1);
+        select_best_f0(ref, tmpc + (size_t)(i - 1) * max_cand, nc_all, 1.0, &e2);
+        if (dmin(e1, e2) <= 0.05) continue;
+        cand[(size_t)i * max_cand + j] = 0; score[(size_t)i * max_cand + j] = 0;
+      }
+    free(tmpc);
+  }
+  if (dbg_cand) memcpy(dbg_cand, cand, sizeof(double) * (size_t)nf * max_cand);
+  if (dbg_score) memcpy(dbg_score, score, sizeof(double) * (size_t)nf * max_cand);
+
+  double *best = (double *)malloc(sizeof(double) * nf), *basic = (double *)malloc(sizeof(double) * nf);
+  harvest_fix_contour(cand, score, nf, max_cand, nc_all, best);
+  if (dbg_best) memcpy(dbg_best, best, sizeof(double) * nf);
+  harvest_smooth(best, nf, basic);
+  if (dbg_basic) memcpy(dbg_basic, basic, sizeof(double) * nf);
+
+  int f0_length = wo_harvest_num_frames(fs, x_length, frame_period);
+  for (int i = 0; i < f0_length; ++i) {
+    temporal_positions[i] = i * frame_period / 1000.0;
+    f0[i] = basic[imin(nf - 1, wo_matlab_round(temporal_positions[i] * 1000.0))];
+  }
+  for (int e = 0; e < 4; ++e) { free(loc[e]); free(itv[e]); free(interp[e]); }
+  free(boundary); free(tpos); free(y); free(yr); free(yi); free(raw); free(bp); free(filtered); free(fr); free(fi);
+  free(cand); free(score); free(vuv); free(st); free(ed); free(best); free(basic);
+}
+
+void wo_harvest(const double *x, int x_length, int fs, double frame_period, double f0_floor, double f0_ceil,
+                double *temporal_positions, double *f0) {
+  wo_harvest_ex(x, x_length, fs, frame_period, f0_floor, f0_ceil, temporal_positions, f0, 0, 0, 0, 0, 0, 0, 0);
+}

@@ -66,11 +66,12 @@ static size_t arena_need(std::initializer_list<size_t> sizes) {
 }
 
 int dio_get_plan(Engine* e, int n, int fs, double frame_period, double f0_floor, double f0_ceil, DioPlan** out) {
-  auto key = std::make_tuple(n, fs, (int)lround(frame_period * 1000), (int)lround(f0_floor * 1000), (int)lround(f0_ceil * 1000));
+  // the f0 method is part of the key: switching it never reuses a plan built for the other extractor
+  auto key = std::make_tuple(n, fs + 1000000 * e->f0_method, (int)lround(frame_period * 1000), (int)lround(f0_floor * 1000), (int)lround(f0_ceil * 1000));
   auto it = e->dio_plans.find(key);
   if (it != e->dio_plans.end()) { *out = it->second; return 0; }
   DioPlan* p = nullptr;
-  if (dio_plan_create(e, n, fs, frame_period, f0_floor, f0_ceil, &p)) return -1;
+  if (dio_plan_create(e, n, fs, frame_period, f0_floor, f0_ceil, &p, e->f0_method)) return -1;
   e->dio_plans[key] = p;
   *out = p;
   return 0;
@@ -685,6 +686,37 @@ int ryk_debug_synth_timebase(ryk_engine* h, int id, int n, double* if0, double* 
   RYK_CUDA(cudaMemcpy(ivuv, s->dev.ivuv, sizeof(double) * n, cudaMemcpyDeviceToHost));
   RYK_CUDA(cudaMemcpy(tp, s->dev.tp, sizeof(double) * n, cudaMemcpyDeviceToHost));
   return 0;
+}
+
+// f0 extractor behind ryk_world_f0 / ryk_world_analyze / new sessions: 0 = DIO + StoneMask (default), 1 = Harvest + StoneMask.
+int ryk_engine_set_f0_method(ryk_engine* h, int method) {
+  RYK_CHECK(method == 0 || method == 1, "f0 method must be 0 (DIO) or 1 (Harvest)");
+  E(h)->f0_method = method;
+  return 0;
+}
+int ryk_engine_get_f0_method(ryk_engine* h) { return E(h)->f0_method; }
+
+// ---- diagnostics: Harvest internals of the last analysis that used this plan (engine in f0 method 1)
+int ryk_debug_harvest(ryk_engine* h, int n, int fs, double fp, double f0_floor, double f0_ceil, int* info, double* y, double* raw,
+                      double* cand, double* score, double* best, double* basic, double* f0_raw) {
+  Engine* e = E(h);
+  RYK_CUDA(cudaSetDevice(e->device));
+  RYK_CHECK(e->f0_method == 1, "engine is not in Harvest mode");
+  DioPlan* plan = nullptr;
+  if (dio_get_plan(e, n, fs, fp, f0_floor, f0_ceil, &plan)) return -1;
+  if (f0_raw) RYK_CUDA(cudaMemcpyAsync(f0_raw, dio_plan_f0_raw(plan), sizeof(double) * dio_plan_frames(plan), cudaMemcpyDeviceToHost, e->stream));
+  return harvest_plan_debug_copy(dio_plan_harvest(plan), info, y, raw, cand, score, best, basic, e->stream);
+}
+
+// ---- diagnostics: stage-1 forward of padded length Tp as one cluster kernel vs 16 layer launches (ms per forward, stand-alone),
+// and the fused kernel's phase timeline (31 values in us: start, after layer 0, {tasks done, barrier passed} x 14, end)
+int ryk_debug_stage1_bench(ryk_engine* h, int Tp, int iters, float* ms_fused, float* ms_layered, double* timeline_us) {
+  Engine* e = E(h);
+  RYK_CUDA(cudaSetDevice(e->device));
+  RYK_CHECK(e->precision == 1 && Tp > 0 && Tp % 128 == 0 && iters > 0, "needs FP16 mode and a padded length (multiple of 128)");
+  UNetPlan* plan = nullptr;
+  if (stage1_plan_for(e, Tp, &plan)) return -1;
+  return s1_fused_bench(e, plan, iters, ms_fused, ms_layered, timeline_us);
 }
 
 // ---- diagnostics: DIO internals of the last ryk_world_f0 / ryk_world_analyze call with this (n, fs, ...) plan

@@ -13,6 +13,7 @@
 namespace ryk {
 
 struct DioPlan;
+struct HarvestPlan;
 struct Session;
 struct Group;
 struct Reblock;
@@ -21,6 +22,7 @@ struct Engine {
   int device = 0;
   cudaStream_t stream = nullptr;
   int precision = 1;                 // 0: FP32 CUDA-core convs everywhere, 1: FP16 tcgen05 tensor-core convs where eligible
+  int f0_method = 0;                 // 0: DIO + StoneMask, 1: Harvest + StoneMask (world_harvest.cu)
   bool s1_fused = true;              // FP16 mode: stage 1 as ONE cluster kernel (s1_fused.cu) instead of 16 layer launches
   // FFT twiddles
   double2* d_twiddle = nullptr;
@@ -61,13 +63,23 @@ int engine_pinned(Engine* e, size_t bytes, void** out);
 
 // world_analysis.cu
 int analysis_kernels_init();
-int dio_plan_create(Engine* e, int n, int fs, double frame_period, double f0_floor, double f0_ceil, DioPlan** out);
+int dio_plan_create(Engine* e, int n, int fs, double frame_period, double f0_floor, double f0_ceil, DioPlan** out, int f0_method = 0);
 void dio_plan_free(DioPlan* p);
 int dio_get_plan(Engine* e, int n, int fs, double frame_period, double f0_floor, double f0_ceil, DioPlan** out);
 int dio_stonemask_run(Engine* e, DioPlan* p, const float* d_x, cudaStream_t st);
 const double* dio_plan_f0(DioPlan* p);      // refined f0 (double) after dio_stonemask_run
 double* dio_plan_f0_mut(DioPlan* p);
 int dio_plan_frames(DioPlan* p);
+HarvestPlan* dio_plan_harvest(DioPlan* p);
+const double* dio_plan_f0_raw(DioPlan* p);     // f0 contour before StoneMask
+// world_harvest.cu
+int harvest_plan_create(Engine* e, int n, int fs, double frame_period, double f0_floor, double f0_ceil, HarvestPlan** out);
+void harvest_plan_free(HarvestPlan* p);
+int harvest_run(Engine* e, HarvestPlan* p, const float* d_x, double* d_f0, cudaStream_t st);
+int harvest_plan_debug_copy(HarvestPlan* p, int* info, double* y, double* raw, double* cand, double* score, double* best, double* basic,
+                            cudaStream_t st);
+// s1_fused.cu diagnostics
+int s1_fused_bench(Engine* e, UNetPlan* p, int iters, float* ms_fused, float* ms_layered, double* timeline_us);
 int dio_plan_debug_copy(DioPlan* p, double* f0_raw, double* cand, double* score, int* counts, cudaStream_t st);
 int spectral_analysis_run(Engine* e, const float* d_x, int n, int fs, double frame_period, const double* d_f0, int n_out,
                           int fft_size, int order, float* d_sp, float* d_ap, float* d_mc, float* d_f0_out, uint8_t* d_voiced,

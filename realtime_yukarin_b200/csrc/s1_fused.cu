@@ -40,12 +40,15 @@ struct S1Params {
   const float* x; const float* w0; const float* sc0; const float* sh0; __half* enc0; int in_ch, base, act0;
   const __half* yin0; const __half* yin1; const float* w15; const float* sc15; const float* sh15; float* y; int yc0, yc1, out_ch, act15;
   int W;
+  unsigned long long* dbg;            // nullable: 31 timestamps (ns) of CTA 0 -- start, after layer 0, {tasks, barrier} x 14, end
 };
 
 __device__ __forceinline__ uint32_t cluster_size() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctaid.x;" : "=r"(r)); return r; }
 __device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
 __device__ __forceinline__ uint4 ldcg_u4(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&a)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(addr));
@@ -102,24 +105,55 @@ __device__ __forceinline__ void s1_mma_chunk(float (&acc)[2][2][4], const S1BChu
   }
 }
 
-__device__ __forceinline__ void s1_layer(const S1LayerP& L, int rank, int nc, __half* act, float* partial) {
+// this warp's first weight chunk of an upcoming (layer, task, pass): loaded ahead so that its latency hides behind the reduction /
+// epilogue of the current task or behind the cluster barrier and the staging of the next layer
+struct S1Carry { S1BChunk b; bool valid; };
+
+__device__ __forceinline__ void s1_first_of_layer(const S1LayerP& L, int rank, int nc, int warp, int lane, S1Carry& carry) {
+  const S1Geom g{L.transposed, L.Win, L.C0 + L.C1, L.Cout};
+  const S1Cut c = s1_cut(g, nc);
+  const int M = s1_M(g), KP = s1_K(g) / 32;
+  const int mslab = rank % c.MS, np = rank / c.MS;
+  const int m0 = mslab * c.slab, m1 = min(M, m0 + c.slab);
+  carry.valid = false;
+  if (m0 >= M || np >= s1_tasks(g)) return;
+  const int mg = warp / c.ks, kpart = warp - mg * c.ks;
+  const int mt_slab = (m1 - m0 + 15) / 16;
+  if (!(warp < c.ms * c.ks && mg < mt_slab)) return;
+  const uint4* wt = L.w + (size_t)np * (s1_task_halfs(g) / 8);
+  s1_load_b(carry.b, wt, kpart * (KP / c.ks), lane);
+  carry.valid = true;
+}
+
+__device__ __forceinline__ void s1_layer(const S1LayerP& L, int rank, int nc, __half* act, float* partial, S1Carry& carry) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const S1Geom g{L.transposed, L.Win, L.C0 + L.C1, L.Cout};
   const S1Cut c = s1_cut(g, nc);
   const int M = s1_M(g), K = s1_K(g), KP = K / 32, NG = g.Cout / 16;
   const int mslab = rank % c.MS, np = rank / c.MS;
   const int m0 = mslab * c.slab, m1 = min(M, m0 + c.slab);
-  if (m0 >= M) return;                                   // CTA-uniform: this slab is empty
+  if (m0 >= M) { carry.valid = false; return; }          // CTA-uniform: this slab is empty
   const int px0 = s1_px0(g, m0), RS = c.RS;
-  // ---- stage the slab's input rows (zero rows = padding), concatenating the skip tensor ----
+  // ---- stage the slab's input rows (zero rows = padding), concatenating the skip tensor; four 16-byte loads in flight per thread ----
   {
-    const int nrows = s1_rows_for(g, m1 - m0), vpr = g.Cin / 8;
-    for (int i = tid; i < nrows * vpr; i += kS1Threads) {
-      const int r = i / vpr, ch = (i - r * vpr) * 8, px = px0 + r;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (px >= 0 && px < L.Win)
-        v = ch < L.C0 ? ldcg_u4(L.in0 + (size_t)px * L.C0 + ch) : ldcg_u4(L.in1 + (size_t)px * L.C1 + (ch - L.C0));
-      *reinterpret_cast<uint4*>(act + (size_t)r * RS + ch) = v;
+    const int nrows = s1_rows_for(g, m1 - m0), vpr = g.Cin / 8, nv = nrows * vpr;
+    for (int i0 = tid; i0 < nv; i0 += 4 * kS1Threads) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kS1Threads;
+        v[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (i < nv) {
+          const int r = i / vpr, ch = (i - r * vpr) * 8, px = px0 + r;
+          if (px >= 0 && px < L.Win)
+            v[u] = ch < L.C0 ? ldcg_u4(L.in0 + (size_t)px * L.C0 + ch) : ldcg_u4(L.in1 + (size_t)px * L.C1 + (ch - L.C0));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kS1Threads;
+        if (i < nv) { const int r = i / vpr, ch = (i - r * vpr) * 8; *reinterpret_cast<uint4*>(act + (size_t)r * RS + ch) = v[u]; }
+      }
     }
   }
   __syncthreads();
@@ -130,10 +164,11 @@ __device__ __forceinline__ void s1_layer(const S1LayerP& L, int rank, int nc, __
   const int rows = m1 - m0, mt_slab = (rows + 15) / 16;
   const int npass = (mt_slab + 2 * c.ms - 1) / (2 * c.ms);
   const int ntasks = s1_tasks(g);
+  const size_t task_u4 = s1_task_halfs(g) / 8;
   const int lrow = s1_ldm_row(lane), kofs = s1_ldm_kofs(lane);
   for (int task = np; task < ntasks; task += c.NP) {
     const int cls = task / NG, ng = task - cls * NG;
-    const uint4* __restrict__ wt = L.w + (size_t)task * (s1_task_halfs(g) / 8);
+    const uint4* __restrict__ wt = L.w + (size_t)task * task_u4;
     for (int p = 0; p < npass; ++p) {
       const int tA = mg + c.ms * (2 * p), tB = tA + c.ms;
       const bool work = active && tA < mt_slab;
@@ -146,8 +181,8 @@ __device__ __forceinline__ void s1_layer(const S1LayerP& L, int rank, int nc, __
           for (int r = 0; r < 4; ++r) acc[i][nt][r] = 0.f;
       if (work) {
         const int mA = m0 + min(tA * 16 + lrow, rows - 1), mB = m0 + min(tB * 16 + lrow, rows - 1);
-        S1BChunk b0, b1;
-        s1_load_b(b0, wt, kp_lo, lane);
+        S1BChunk b0 = carry.b, b1;
+        if (!carry.valid) s1_load_b(b0, wt, kp_lo, lane);
         for (int kp = kp_lo; kp < kp_hi; kp += 4) {
           const bool more = kp + 2 < kp_hi;
           if (more) s1_load_b(b1, wt, kp + 2, lane);
@@ -158,8 +193,18 @@ __device__ __forceinline__ void s1_layer(const S1LayerP& L, int rank, int nc, __
           }
         }
       }
-      if (c.ks > 1) {                                      // CTA-uniform
-        if (work && kpart > 0) {
+      // first chunk of this warp's next (task, pass) of the layer, requested before the reduction / epilogue below
+      {
+        int ntask = task, pn = p + 1;
+        if (pn >= npass) { pn = 0; ntask = task + c.NP; }
+        carry.valid = false;
+        if (ntask < ntasks && active && mg + c.ms * (2 * pn) < mt_slab) {
+          s1_load_b(carry.b, L.w + (size_t)ntask * task_u4, kp_lo, lane);
+          carry.valid = true;
+        }
+      }
+      if (c.ks > 1) {                                      // CTA-uniform: split-K partials reduced and stored by ALL threads
+        if (work) {
 #pragma unroll
           for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -168,19 +213,24 @@ __device__ __forceinline__ void s1_layer(const S1LayerP& L, int rank, int nc, __
               for (int r = 0; r < 4; ++r) partial[((size_t)warp * 16 + (i * 2 + nt) * 4 + r) * 32 + lane] = acc[i][nt][r];
         }
         __syncthreads();
-        if (work && kpart == 0) {
-          for (int kq = 1; kq < c.ks; ++kq) {              // fixed order: deterministic sums
-            const int w2 = mg * c.ks + kq;
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
-#pragma unroll
-              for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-                for (int r = 0; r < 4; ++r) acc[i][nt][r] += partial[((size_t)w2 * 16 + (i * 2 + nt) * 4 + r) * 32 + lane];
+        for (int e = tid; e < c.ms * 256; e += kS1Threads) {
+          const int mgp = e >> 8, idx2 = (e >> 5) & 7, ln = e & 31;       // idx2 = (i * 2 + nt) * 2 + rr
+          const int i = idx2 >> 2, nt = (idx2 >> 1) & 1, rr = idx2 & 1;
+          const int tile = mgp + c.ms * (2 * p + i);
+          const int mrel = tile * 16 + s1_c_row(ln, rr * 2);
+          if (mrel < rows) {
+            const float* src = partial + ((size_t)(mgp * c.ks) * 16 + (i * 2 + nt) * 4 + rr * 2) * 32 + ln;
+            float v0 = 0.f, v1 = 0.f;
+            for (int kq = 0; kq < c.ks; ++kq) { v0 += src[(size_t)kq * 512]; v1 += src[(size_t)kq * 512 + 32]; }   // fixed order
+            const int n = ng * 16 + nt * 8 + s1_c_col(ln, 0);
+            const int opx = s1_out_px(g, cls, m0 + mrel);
+            v0 = apply_act(fmaf(v0, __ldg(L.scale + n), __ldg(L.shift + n)), L.act);
+            v1 = apply_act(fmaf(v1, __ldg(L.scale + n + 1), __ldg(L.shift + n + 1)), L.act);
+            *reinterpret_cast<__half2*>(L.out + (size_t)opx * g.Cout + n) = __floats2half2_rn(v0, v1);
           }
         }
-      }
-      if (work && kpart == 0) {
+        __syncthreads();                                   // the partial buffer is rewritten by the next pass / task
+      } else if (work) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const int tile = i ? tB : tA;
@@ -200,10 +250,12 @@ __device__ __forceinline__ void s1_layer(const S1LayerP& L, int rank, int nc, __
           }
         }
       }
-      if (c.ks > 1) __syncthreads();                       // the partial buffer is rewritten by the next pass / task
     }
   }
+  carry.valid = false;
 }
+
+__device__ __forceinline__ unsigned long long s1_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
 __global__ void __launch_bounds__(kS1Threads, 1) k_s1_fused(const __grid_constant__ S1Params P) {
   extern __shared__ __align__(128) unsigned char s1_smem[];
@@ -211,6 +263,8 @@ __global__ void __launch_bounds__(kS1Threads, 1) k_s1_fused(const __grid_constan
   float* partial = reinterpret_cast<float*>(s1_smem + kS1ActBytes);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rank = (int)cluster_rank(), nc = (int)cluster_size();
+  const bool stamp = P.dbg != nullptr && rank == 0 && tid == 0;      // diagnostics: per-phase timeline of CTA 0 (ns)
+  if (stamp) P.dbg[0] = s1_now();
   for (int l = 0; l < 3; ++l) s1_prefetch_layer(P.L[l], rank, nc);
   // ---- layer 0: conv k3 s1 p1, in_ch -> base, FP32 input, LeakyReLU, FP16 output ----
   {
@@ -227,11 +281,20 @@ __global__ void __launch_bounds__(kS1Threads, 1) k_s1_fused(const __grid_constan
       P.enc0[i] = __float2half_rn(apply_act(fmaf(a, __ldg(P.sc0 + co), __ldg(P.sh0 + co)), P.act0));
     }
   }
-  cluster_barrier();
+  S1Carry carry;
+  carry.valid = false;
+  cluster_arrive();
+  s1_first_of_layer(P.L[0], rank, nc, warp, lane, carry);           // weights do not depend on the activations being exchanged
+  cluster_wait();
+  if (stamp) P.dbg[1] = s1_now();
   for (int l = 0; l < 14; ++l) {
+    s1_layer(P.L[l], rank, nc, act, partial, carry);
+    if (stamp) P.dbg[2 + 2 * l] = s1_now();
+    cluster_arrive();
     if (l + 3 < 14) s1_prefetch_layer(P.L[l + 3], rank, nc);
-    s1_layer(P.L[l], rank, nc, act, partial);
-    cluster_barrier();
+    if (l + 1 < 14) s1_first_of_layer(P.L[l + 1], rank, nc, warp, lane, carry);
+    cluster_wait();
+    if (stamp) P.dbg[3 + 2 * l] = s1_now();
   }
   // ---- layer 15: conv k3 s1 p1 over the concatenation (yc0 + yc1 channels) -> out_ch, FP32 output; one warp per output pixel ----
   {
@@ -265,6 +328,7 @@ __global__ void __launch_bounds__(kS1Threads, 1) k_s1_fused(const __grid_constan
       if (lane < P.out_ch) P.y[(size_t)px * P.out_ch + lane] = apply_act(fmaf(mine, __ldg(P.sc15 + lane), __ldg(P.sh15 + lane)), P.act15);
     }
   }
+  if (stamp) P.dbg[30] = s1_now();
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------------------------
@@ -287,6 +351,7 @@ int s1_pack_weights(const float* d_w_chainer, int transposed, int Cin, int Cout,
 }
 
 static int g_s1_cluster = 0;     // 0: not initialised, -1: unavailable, else the cluster size
+static unsigned long long* g_s1_dbg = nullptr;      // device buffer of 32 timestamps while a diagnostic run is active
 
 static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
@@ -348,6 +413,7 @@ int s1_fused_run(Engine* e, const UNetPlan* p, cudaStream_t st) {
   P.yin0 = (const __half*)Z.in0; P.yin1 = (const __half*)Z.in1; P.w15 = Z.w_direct; P.sc15 = Z.scale; P.sh15 = Z.shift; P.y = (float*)Z.out;
   P.yc0 = Z.C0; P.yc1 = Z.C1; P.out_ch = Z.Cout; P.act15 = Z.act;
   P.W = p->W;
+  P.dbg = g_s1_dbg;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(g_s1_cluster); cfg.blockDim = dim3(kS1Threads); cfg.dynamicSmemBytes = kS1ActBytes + kS1PartialBytes; cfg.stream = st;
   cudaLaunchAttribute at[1];
@@ -359,5 +425,38 @@ int s1_fused_run(Engine* e, const UNetPlan* p, cudaStream_t st) {
 }
 
 int s1_fused_cluster_size() { return g_s1_cluster; }
+
+// Diagnostics: `iters` back-to-back forwards of the plan's 16 layers on the engine stream, fused and layered, timed with CUDA events
+// (ms per forward), plus the phase timeline of the last fused forward (31 device timestamps in ns, relative to the first).
+int s1_fused_bench(Engine* e, UNetPlan* p, int iters, float* ms_fused, float* ms_layered, double* timeline_us) {
+  RYK_CHECK(p->fused && g_s1_cluster > 0, "plan cannot run fused");
+  cudaEvent_t ev0, ev1;
+  RYK_CUDA(cudaEventCreate(&ev0)); RYK_CUDA(cudaEventCreate(&ev1));
+  const bool keep = e->s1_fused;
+  for (int mode = 0; mode < 2; ++mode) {
+    e->s1_fused = mode == 0;
+    for (int i = 0; i < 3; ++i) if (unet_forward(e, p, e->stream)) return -1;
+    RYK_CUDA(cudaEventRecord(ev0, e->stream));
+    for (int i = 0; i < iters; ++i) if (unet_forward(e, p, e->stream)) return -1;
+    RYK_CUDA(cudaEventRecord(ev1, e->stream));
+    RYK_CUDA(cudaEventSynchronize(ev1));
+    float ms = 0.f;
+    RYK_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    *(mode == 0 ? ms_fused : ms_layered) = ms / iters;
+  }
+  e->s1_fused = true;
+  RYK_CUDA(cudaMalloc(&g_s1_dbg, sizeof(unsigned long long) * 32));
+  RYK_CUDA(cudaMemsetAsync(g_s1_dbg, 0, sizeof(unsigned long long) * 32, e->stream));
+  int rc = unet_forward(e, p, e->stream);
+  unsigned long long h[32];
+  RYK_CUDA(cudaMemcpyAsync(h, g_s1_dbg, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
+  RYK_CUDA(cudaStreamSynchronize(e->stream));
+  cudaFree(g_s1_dbg); g_s1_dbg = nullptr;
+  e->s1_fused = keep;
+  cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+  if (rc) return rc;
+  for (int i = 0; i < 31; ++i) timeline_us[i] = h[i] >= h[0] ? (double)(h[i] - h[0]) * 1e-3 : -1.0;
+  return 0;
+}
 
 }  // namespace ryk

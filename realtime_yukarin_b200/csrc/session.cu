@@ -788,7 +788,7 @@ int ryk_session_create(ryk_engine* h, const ryk_session_config* cfg, int* sessio
     if (P((void**)&s->h_count[i], sizeof(int) * 2)) return -1;
   }
   for (int i = 0; i < 2; ++i) {
-    if (dio_plan_create(e, s->Lw, cfg->fs, cfg->frame_period_ms, cfg->f0_floor, cfg->f0_ceil, &s->dio[i])) return -1;
+    if (dio_plan_create(e, s->Lw, cfg->fs, cfg->frame_period_ms, cfg->f0_floor, cfg->f0_ceil, &s->dio[i], e->f0_method)) return -1;
     e->dio_plans[std::make_tuple(-(int)e->sessions.size() - 1, cfg->fs, i, 0, 0)] = s->dio[i];   // owned by the engine's plan table
   }
   if (synth_create(e, cfg->fs, cfg->frame_period_ms, cheaptrick_fft_size(cfg->fs, 71.0), cfg->vocoder_buffer_size, 4096, &s->synth)) return -1;

@@ -14,6 +14,7 @@
 #include <math.h>
 #include <vector>
 
+#include "analysis_shared.cuh"
 #include "engine.h"
 #include "fft.cuh"
 
@@ -73,79 +74,6 @@ __global__ void k_cmul_inplace(cufftDoubleComplex* __restrict__ y, const cufftDo
     cufftDoubleComplex a = y[i], b = f[i];
     y[i] = make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
   }
-}
-
-// Z[b] = Y * LP[b]
-__global__ void k_band_mul(const cufftDoubleComplex* __restrict__ y, const cufftDoubleComplex* __restrict__ lp,
-                           cufftDoubleComplex* __restrict__ z, int nbins) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int b = blockIdx.y;
-  if (i < nbins) {
-    cufftDoubleComplex a = y[i], w = lp[(size_t)b * nbins + i];
-    z[(size_t)b * nbins + i] = make_double2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
-  }
-}
-
-// Ordered extraction of the four event trains of one band. grid = (4, nbands), block = 1024.
-__device__ inline double dio_signal(const double* __restrict__ f, int type, int i) {
-  switch (type) {
-    case 0: return f[i];
-    case 1: return -f[i];
-    case 2: return (-f[i]) - (-f[i + 1]);
-    default: return -((-f[i]) - (-f[i + 1]));
-  }
-}
-
-__global__ void __launch_bounds__(1024) k_dio_zero_cross(const double* __restrict__ filtered, int fft_size, int y_length,
-                                                        const int* __restrict__ half_avg, double fs,
-                                                        int* __restrict__ edges, double* __restrict__ loc,
-                                                        double* __restrict__ itv, int* __restrict__ counts) {
-  int type = blockIdx.x, band = blockIdx.y;
-  const double* f = filtered + (size_t)band * fft_size + half_avg[band] * 2;   // delay compensation
-  int L = type < 2 ? y_length : y_length - 1;
-  size_t slot = ((size_t)band * 4 + type) * y_length;
-  int* e = edges + slot;
-  __shared__ int wsum[32];
-  __shared__ int total;
-  int per = (L - 1 + blockDim.x - 1) / blockDim.x;   // candidates i in [0, L-1)
-  int lo = threadIdx.x * per, hi = min(lo + per, L - 1);
-  int cnt = 0;
-  for (int i = lo; i < hi; ++i) {
-    double a = dio_signal(f, type, i), b = dio_signal(f, type, i + 1);
-    cnt += (0.0 < a && b <= 0.0) ? 1 : 0;
-  }
-  // block exclusive scan of cnt
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  int inc = cnt;
-  for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
-  if (lane == 31) wsum[w] = inc;
-  __syncthreads();
-  if (w == 0) {
-    int v = wsum[lane];
-    int iv = v;
-    for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += u; }
-    wsum[lane] = iv - v;
-    if (lane == 31) total = iv;
-  }
-  __syncthreads();
-  int pos = wsum[w] + inc - cnt;
-  for (int i = lo; i < hi; ++i) {
-    double a = dio_signal(f, type, i), b = dio_signal(f, type, i + 1);
-    if (0.0 < a && b <= 0.0) e[pos++] = i + 1;
-  }
-  __syncthreads();
-  int count = total;
-  if (count < 2) { if (threadIdx.x == 0) counts[band * 4 + type] = 0; return; }
-  for (int i = threadIdx.x; i < count - 1; i += blockDim.x) {
-    int e0 = e[i], e1 = e[i + 1];
-    double s0a = dio_signal(f, type, e0 - 1), s0b = dio_signal(f, type, e0);
-    double s1a = dio_signal(f, type, e1 - 1), s1b = dio_signal(f, type, e1);
-    double f0e = e0 - s0a / (s0b - s0a);
-    double f1e = e1 - s1a / (s1b - s1a);
-    itv[slot + i] = fs / (f1e - f0e);
-    loc[slot + i] = (f0e + f1e) / 2.0 / fs;
-  }
-  if (threadIdx.x == 0) counts[band * 4 + type] = count - 1;
 }
 
 __global__ void k_dio_candidates(const double* __restrict__ loc, const double* __restrict__ itv, const int* __restrict__ counts,
@@ -706,15 +634,13 @@ struct DioPlan {
   int* d_edges = nullptr; double* d_loc = nullptr; double* d_itv = nullptr; int* d_counts = nullptr;
   double* d_cand = nullptr; double* d_score = nullptr; double* d_scratch = nullptr; int* d_iscratch = nullptr;
   double* d_f0 = nullptr; double* d_f0r = nullptr;
+  HarvestPlan* harvest = nullptr;          // f0 method 1: Harvest writes d_f0 instead of DIO
 };
 
-static int cufft_ok(cufftResult r, const char* what) {
-  if (r != CUFFT_SUCCESS) { set_error(std::string("cuFFT ") + what + " failed with code " + std::to_string((int)r)); return -1; }
-  return 0;
-}
 
 void dio_plan_free(DioPlan* p) {
   if (!p) return;
+  harvest_plan_free(p->harvest);
   if (p->fwd) cufftDestroy(p->fwd);
   if (p->inv) cufftDestroy(p->inv);
   if (p->fwd_filters) cufftDestroy(p->fwd_filters);
@@ -724,8 +650,9 @@ void dio_plan_free(DioPlan* p) {
   delete p;
 }
 
-int dio_plan_create(Engine* e, int n, int fs, double frame_period, double f0_floor, double f0_ceil, DioPlan** out) {
+int dio_plan_create(Engine* e, int n, int fs, double frame_period, double f0_floor, double f0_ceil, DioPlan** out, int f0_method) {
   DioPlan* p = new DioPlan();
+  if (f0_method == 1 && harvest_plan_create(e, n, fs, frame_period, f0_floor, f0_ceil, &p->harvest)) { delete p; return -1; }
   p->n = n; p->fs = fs; p->frame_period = frame_period; p->f0_floor = f0_floor; p->f0_ceil = f0_ceil;
   p->nbands = 1 + (int)(log(f0_ceil / f0_floor) / kLog2 * 2.0);
   std::vector<double> boundary(p->nbands);
@@ -774,6 +701,13 @@ int dio_plan_create(Engine* e, int n, int fs, double frame_period, double f0_flo
 
 // DIO + StoneMask: x (device float32, n samples) -> plan->d_f0r (double, f0_length frames). Stream-ordered, no sync.
 int dio_stonemask_run(Engine* e, DioPlan* p, const float* d_x, cudaStream_t st) {
+  const size_t sm_smem = sizeof(double2) * 8192 + sizeof(double) * 2 * 2049 + 64;
+  if (p->harvest) {                                  // Harvest replaces DIO as the contour StoneMask refines
+    if (harvest_run(e, p->harvest, d_x, p->d_f0, st)) return -1;
+    k_stonemask<<<p->f0_length, 256, sm_smem, st>>>(d_x, p->n, p->fs, p->frame_period, p->d_f0, p->d_f0r, e->d_twiddle);
+    RYK_CUDA(cudaGetLastError());
+    return 0;
+  }
   int nbins = p->fft_size / 2 + 1;
   if (cufft_ok(cufftSetStream(p->fwd, st), "set stream")) return -1;
   if (cufft_ok(cufftSetStream(p->inv, st), "set stream")) return -1;
@@ -782,7 +716,7 @@ int dio_stonemask_run(Engine* e, DioPlan* p, const float* d_x, cudaStream_t st) 
   k_cmul_inplace<<<(nbins + 255) / 256, 256, 0, st>>>(p->d_Y, p->d_filt_spec, nbins);
   k_band_mul<<<dim3((nbins + 255) / 256, p->nbands), 256, 0, st>>>(p->d_Y, p->d_filt_spec + nbins, p->d_Z, nbins);
   if (cufft_ok(cufftExecZ2D(p->inv, p->d_Z, p->d_filtered), "exec Z2D")) return -1;
-  k_dio_zero_cross<<<dim3(4, p->nbands), 1024, 0, st>>>(p->d_filtered, p->fft_size, p->y_length, p->d_half_avg, (double)p->fs,
+  k_dio_zero_cross<<<dim3(4, p->nbands), 1024, 0, st>>>(p->d_filtered, p->fft_size, p->y_length, p->d_half_avg, 2, 0, (double)p->fs,
                                                       p->d_edges, p->d_loc, p->d_itv, p->d_counts);
   k_dio_candidates<<<dim3((p->f0_length + 127) / 128, p->nbands), 128, 0, st>>>(
       p->d_loc, p->d_itv, p->d_counts, p->y_length, p->f0_length, p->nbands, p->frame_period, p->f0_floor, p->f0_ceil,
@@ -806,6 +740,8 @@ int dio_plan_debug_copy(DioPlan* p, double* f0_raw, double* cand, double* score,
 }
 double* dio_plan_f0_mut(DioPlan* p) { return p->d_f0r; }
 int dio_plan_frames(DioPlan* p) { return p->f0_length; }
+HarvestPlan* dio_plan_harvest(DioPlan* p) { return p->harvest; }
+const double* dio_plan_f0_raw(DioPlan* p) { return p->d_f0; }
 
 size_t cheaptrick_smem_bytes(int fft_size, int fs) {
   int nb = fft_size / 2 + 1;

@@ -51,6 +51,7 @@ EXPORTED_SYMBOLS = [
     'ryk_world_synthesize_length', 'ryk_world_synthesize', 'ryk_output_gate', 'ryk_reblock_create', 'ryk_reblock_destroy',
     'ryk_reblock_push', 'ryk_reblock_push_device', 'ryk_reblock_collect', 'ryk_reblock_result_device', 'ryk_resample_length',
     'ryk_resample_poly', 'ryk_session_poll', 'ryk_reblock_poll', 'ryk_engine_profile_read2', 'ryk_engine_set_stage1_fused',
+    'ryk_engine_set_f0_method', 'ryk_engine_get_f0_method', 'ryk_debug_harvest', 'ryk_debug_stage1_bench',
 ]
 
 
@@ -388,6 +389,42 @@ class Engine(object):
         a, b, c = numpy.zeros(n), numpy.zeros(n), numpy.zeros(n)
         self._check(self.lib.ryk_debug_synth_timebase(self._h, sid, int(n), _dp(a), _dp(b), _dp(c)))
         return a, b, c
+
+    F0_METHODS = {'dio': 0, 'harvest': 1}
+
+    def set_f0_method(self, method: str):
+        """f0 extractor of world_f0 / world_analyze / sessions created afterwards: 'dio' (pyworld.dio + stonemask, default) or
+        'harvest' (pyworld.harvest + stonemask) -- yukarin's AcousticFeature.extract f0 hook (acoustic_feature_wrapper.py:28-33)."""
+        self._check(self.lib.ryk_engine_set_f0_method(self._h, self.F0_METHODS[method]))
+
+    @property
+    def f0_method(self) -> str:
+        return ['dio', 'harvest'][self.lib.ryk_engine_get_f0_method(self._h)]
+
+    def debug_harvest(self, n, fs, frame_period, f0_floor, f0_ceil):
+        """Intermediate arrays of the last Harvest analysis with this plan (see ryk_debug_harvest)."""
+        import math
+        ratio = int(fs / 8000.0 + 0.5)
+        channels = 1 + int(math.log((f0_ceil * 1.1) / (f0_floor * 0.9)) / 0.69314718055994529 * 40.0)
+        nf1 = int(1000.0 * n / fs) + 1
+        ylen = -(-n // ratio)
+        maxc = int(channels / 10.0 + 0.5) * 7
+        info = numpy.zeros(7, numpy.int32)
+        out = dict(y=numpy.zeros(ylen), raw=numpy.zeros((channels, nf1)), cand=numpy.zeros((nf1, maxc)), score=numpy.zeros((nf1, maxc)),
+                   best=numpy.zeros(nf1), basic=numpy.zeros(nf1), f0_raw=numpy.zeros(dio_num_frames(fs, n, frame_period)))
+        self._check(self.lib.ryk_debug_harvest(self._h, int(n), int(fs), ctypes.c_double(frame_period), ctypes.c_double(f0_floor),
+                                               ctypes.c_double(f0_ceil), info.ctypes.data_as(c_int_p), _dp(out['y']), _dp(out['raw']),
+                                               _dp(out['cand']), _dp(out['score']), _dp(out['best']), _dp(out['basic']), _dp(out['f0_raw'])))
+        assert (info[0], info[1], info[2], info[4]) == (channels, nf1, ylen, maxc), info
+        out['nc'] = int(info[6])
+        return out
+
+    def stage1_bench(self, Tp: int, iters: int = 50):
+        """(ms per stand-alone stage-1 forward fused, layered, fused-kernel phase timeline in us)."""
+        a, b = ctypes.c_float(), ctypes.c_float()
+        tl = numpy.zeros(31)
+        self._check(self.lib.ryk_debug_stage1_bench(self._h, int(Tp), int(iters), ctypes.byref(a), ctypes.byref(b), _dp(tl)))
+        return float(a.value), float(b.value), tl
 
     def debug_dio(self, n, fs, frame_period, f0_floor, f0_ceil):
         nf = dio_num_frames(fs, n, frame_period)
