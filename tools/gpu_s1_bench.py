@@ -2,6 +2,9 @@
 plus the fused kernel's phase timeline (CTA 0, device globaltimer).  Run under gpurun; prints to stdout."""
 import sys
 import tempfile
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 
 from realtime_yukarin_b200 import synthetic
 from realtime_yukarin_b200.engine import default_engine
