@@ -33,6 +33,8 @@ struct S1LayerP {
   const uint4* w;                       // fragment-packed weights (s1_w_dst)
   const float* scale; const float* shift;
   int transposed, Win, C0, C1, Cout, act;
+  int lgCin;                             // Cin = C0 + C1 is a power of two
+  S1Cut cut;                             // s1_cut(geometry, cluster size), computed on the host
 };
 struct S1Params {
   S1LayerP L[14];
@@ -66,7 +68,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // Ask L2 for the weight blocks this CTA will read in layer L (one bulk prefetch per task, issued by one thread each).
 __device__ __forceinline__ void s1_prefetch_layer(const S1LayerP& L, int rank, int nc) {
   const S1Geom g{L.transposed, L.Win, L.C0 + L.C1, L.Cout};
-  const S1Cut c = s1_cut(g, nc);
+  const S1Cut c = L.cut;
   const int np = rank / c.MS, ntasks = s1_tasks(g);
   const uint32_t bytes = (uint32_t)s1_task_halfs(g) * 2;
   const int task = np + (int)threadIdx.x * c.NP;
@@ -83,14 +85,14 @@ __device__ __forceinline__ void s1_load_b(S1BChunk& b, const uint4* __restrict__
 }
 
 // acc[tile][nt][4] += A(rows of the two m-tiles, k-tile pairs kp, kp + 1) x B chunk
-__device__ __forceinline__ void s1_mma_chunk(float (&acc)[2][2][4], const S1BChunk& b, int kp, const S1Geom& g, int cls, int RS, int px0,
+__device__ __forceinline__ void s1_mma_chunk(float (&acc)[2][2][4], const S1BChunk& b, int kp, const S1Geom& g, int lgCin, int cls, int RS, int px0,
                                              int mA, int mB, int kofs, uint32_t act_addr) {
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
 #pragma unroll
     for (int kt = 0; kt < 2; ++kt) {
       const int k0 = (kp + q) * 32 + kt * 16;
-      const int j = k0 / g.Cin, ch = k0 - j * g.Cin + kofs;
+      const int j = k0 >> lgCin, ch = (k0 & (g.Cin - 1)) + kofs;
       const int rowA = s1_in_px(g, cls, mA, j) - px0, rowB = s1_in_px(g, cls, mB, j) - px0;
       uint32_t aA[4], aB[4];
       ldmatrix_x4(aA, act_addr + (uint32_t)(rowA * RS + ch) * 2u);
@@ -111,7 +113,7 @@ struct S1Carry { S1BChunk b; bool valid; };
 
 __device__ __forceinline__ void s1_first_of_layer(const S1LayerP& L, int rank, int nc, int warp, int lane, S1Carry& carry) {
   const S1Geom g{L.transposed, L.Win, L.C0 + L.C1, L.Cout};
-  const S1Cut c = s1_cut(g, nc);
+  const S1Cut c = L.cut;
   const int M = s1_M(g), KP = s1_K(g) / 32;
   const int mslab = rank % c.MS, np = rank / c.MS;
   const int m0 = mslab * c.slab, m1 = min(M, m0 + c.slab);
@@ -128,7 +130,7 @@ __device__ __forceinline__ void s1_first_of_layer(const S1LayerP& L, int rank, i
 __device__ __forceinline__ void s1_layer(const S1LayerP& L, int rank, int nc, __half* act, float* partial, S1Carry& carry) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const S1Geom g{L.transposed, L.Win, L.C0 + L.C1, L.Cout};
-  const S1Cut c = s1_cut(g, nc);
+  const S1Cut c = L.cut;
   const int M = s1_M(g), K = s1_K(g), KP = K / 32, NG = g.Cout / 16;
   const int mslab = rank % c.MS, np = rank / c.MS;
   const int m0 = mslab * c.slab, m1 = min(M, m0 + c.slab);
@@ -136,7 +138,7 @@ __device__ __forceinline__ void s1_layer(const S1LayerP& L, int rank, int nc, __
   const int px0 = s1_px0(g, m0), RS = c.RS;
   // ---- stage the slab's input rows (zero rows = padding), concatenating the skip tensor; four 16-byte loads in flight per thread ----
   {
-    const int nrows = s1_rows_for(g, m1 - m0), vpr = g.Cin / 8, nv = nrows * vpr;
+    const int nrows = s1_rows_for(g, m1 - m0), lgv = L.lgCin - 3, nv = nrows << lgv;          // Cin / 8 16-byte vectors per row
     for (int i0 = tid; i0 < nv; i0 += 4 * kS1Threads) {
       uint4 v[4];
 #pragma unroll
@@ -144,7 +146,7 @@ __device__ __forceinline__ void s1_layer(const S1LayerP& L, int rank, int nc, __
         const int i = i0 + u * kS1Threads;
         v[u] = make_uint4(0u, 0u, 0u, 0u);
         if (i < nv) {
-          const int r = i / vpr, ch = (i - r * vpr) * 8, px = px0 + r;
+          const int r = i >> lgv, ch = (i - (r << lgv)) * 8, px = px0 + r;
           if (px >= 0 && px < L.Win)
             v[u] = ch < L.C0 ? ldcg_u4(L.in0 + (size_t)px * L.C0 + ch) : ldcg_u4(L.in1 + (size_t)px * L.C1 + (ch - L.C0));
         }
@@ -152,7 +154,7 @@ __device__ __forceinline__ void s1_layer(const S1LayerP& L, int rank, int nc, __
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int i = i0 + u * kS1Threads;
-        if (i < nv) { const int r = i / vpr, ch = (i - r * vpr) * 8; *reinterpret_cast<uint4*>(act + (size_t)r * RS + ch) = v[u]; }
+        if (i < nv) { const int r = i >> lgv, ch = (i - (r << lgv)) * 8; *reinterpret_cast<uint4*>(act + (size_t)r * RS + ch) = v[u]; }
       }
     }
   }
@@ -186,10 +188,10 @@ __device__ __forceinline__ void s1_layer(const S1LayerP& L, int rank, int nc, __
         for (int kp = kp_lo; kp < kp_hi; kp += 4) {
           const bool more = kp + 2 < kp_hi;
           if (more) s1_load_b(b1, wt, kp + 2, lane);
-          s1_mma_chunk(acc, b0, kp, g, cls, RS, px0, mA, mB, kofs, act_addr);
+          s1_mma_chunk(acc, b0, kp, g, L.lgCin, cls, RS, px0, mA, mB, kofs, act_addr);
           if (more) {
             if (kp + 4 < kp_hi) s1_load_b(b0, wt, kp + 4, lane);
-            s1_mma_chunk(acc, b1, kp + 2, g, cls, RS, px0, mA, mB, kofs, act_addr);
+            s1_mma_chunk(acc, b1, kp + 2, g, L.lgCin, cls, RS, px0, mA, mB, kofs, act_addr);
           }
         }
       }
@@ -221,6 +223,7 @@ __device__ __forceinline__ void s1_layer(const S1LayerP& L, int rank, int nc, __
           if (mrel < rows) {
             const float* src = partial + ((size_t)(mgp * c.ks) * 16 + (i * 2 + nt) * 4 + rr * 2) * 32 + ln;
             float v0 = 0.f, v1 = 0.f;
+#pragma unroll 4
             for (int kq = 0; kq < c.ks; ++kq) { v0 += src[(size_t)kq * 512]; v1 += src[(size_t)kq * 512 + 32]; }   // fixed order
             const int n = ng * 16 + nt * 8 + s1_c_col(ln, 0);
             const int opx = s1_out_px(g, cls, m0 + mrel);
@@ -266,8 +269,13 @@ __global__ void __launch_bounds__(kS1Threads, 1) k_s1_fused(const __grid_constan
   const bool stamp = P.dbg != nullptr && rank == 0 && tid == 0;      // diagnostics: per-phase timeline of CTA 0 (ns)
   if (stamp) P.dbg[0] = s1_now();
   for (int l = 0; l < 3; ++l) s1_prefetch_layer(P.L[l], rank, nc);
-  // ---- layer 0: conv k3 s1 p1, in_ch -> base, FP32 input, LeakyReLU, FP16 output ----
+  // ---- layer 0: conv k3 s1 p1, in_ch -> base, FP32 input, LeakyReLU, FP16 output (input rows and weights staged in smem) ----
   {
+    float* xs = reinterpret_cast<float*>(s1_smem);                 // [W][in_ch]
+    float* ws = xs + P.W * P.in_ch;                                // [3][in_ch][base]
+    for (int i = tid; i < P.W * P.in_ch; i += kS1Threads) xs[i] = P.x[i];
+    for (int i = tid; i < 3 * P.in_ch * P.base; i += kS1Threads) ws[i] = __ldg(P.w0 + i);
+    __syncthreads();
     const int total = P.W * P.base;
     for (int i = rank * kS1Threads + tid; i < total; i += nc * kS1Threads) {
       const int px = i / P.base, co = i - px * P.base;
@@ -276,7 +284,7 @@ __global__ void __launch_bounds__(kS1Threads, 1) k_s1_fused(const __grid_constan
       for (int t = 0; t < 3; ++t) {
         const int ix = px + t - 1;
         if (ix < 0 || ix >= P.W) continue;
-        for (int ci = 0; ci < P.in_ch; ++ci) a = fmaf(P.x[(size_t)ix * P.in_ch + ci], __ldg(P.w0 + ((size_t)t * P.in_ch + ci) * P.base + co), a);
+        for (int ci = 0; ci < P.in_ch; ++ci) a = fmaf(xs[ix * P.in_ch + ci], ws[(t * P.in_ch + ci) * P.base + co], a);
       }
       P.enc0[i] = __float2half_rn(apply_act(fmaf(a, __ldg(P.sc0 + co), __ldg(P.sh0 + co)), P.act0));
     }
@@ -296,9 +304,13 @@ __global__ void __launch_bounds__(kS1Threads, 1) k_s1_fused(const __grid_constan
     cluster_wait();
     if (stamp) P.dbg[3 + 2 * l] = s1_now();
   }
-  // ---- layer 15: conv k3 s1 p1 over the concatenation (yc0 + yc1 channels) -> out_ch, FP32 output; one warp per output pixel ----
+  // ---- layer 15: conv k3 s1 p1 over the concatenation (yc0 + yc1 channels) -> out_ch, FP32 output; one warp per output pixel,
+  //      weights staged in shared memory ----
   {
     const int Ct = P.yc0 + P.yc1;
+    float* ws = reinterpret_cast<float*>(s1_smem);                 // [3][Ct][out_ch]
+    for (int i = tid; i < 3 * Ct * P.out_ch; i += kS1Threads) ws[i] = __ldg(P.w15 + i);
+    __syncthreads();
     for (int px = rank * kS1Warps + warp; px < P.W; px += nc * kS1Warps) {
       float a[16];
 #pragma unroll
@@ -311,10 +323,10 @@ __global__ void __launch_bounds__(kS1Threads, 1) k_s1_fused(const __grid_constan
           const __half2 hv = c < P.yc0 ? __ldcg(reinterpret_cast<const __half2*>(P.yin0 + (size_t)ix * P.yc0 + c))
                                        : __ldcg(reinterpret_cast<const __half2*>(P.yin1 + (size_t)ix * P.yc1 + (c - P.yc0)));
           const float2 xv = __half22float2(hv);
-          const float* w = P.w15 + ((size_t)t * Ct + c) * P.out_ch;
+          const float* w = ws + (t * Ct + c) * P.out_ch;
 #pragma unroll
           for (int co = 0; co < 16; ++co)
-            if (co < P.out_ch) a[co] = fmaf(xv.y, __ldg(w + P.out_ch + co), fmaf(xv.x, __ldg(w + co), a[co]));
+            if (co < P.out_ch) a[co] = fmaf(xv.y, w[P.out_ch + co], fmaf(xv.x, w[co], a[co]));
         }
       }
       float mine = 0.f;
@@ -394,6 +406,8 @@ bool s1_fused_eligible(const UNet* n, const UNetPlan* p) {
     if ((size_t)s1_rows_for(g, c.slab < M ? c.slab : M) * c.RS * 2 > (size_t)kS1ActBytes) return false;
     if ((s1_K(g) / 32) % c.ks != 0 || ((s1_K(g) / 32) / c.ks) % 2 != 0 || c.MS * c.NP != g_s1_cluster) return false;
   }
+  if ((size_t)(p->W * n->in_ch + 3 * n->in_ch * n->base) * 4 > (size_t)kS1ActBytes) return false;      // layer 0 stages its input and weights
+  if ((size_t)3 * 2 * n->base * n->out_ch * 4 > (size_t)kS1ActBytes) return false;                       // layer 15 stages its weights
   return n->layers[0].k == 3 && n->layers[15].k == 3;
 }
 
@@ -406,6 +420,8 @@ int s1_fused_run(Engine* e, const UNetPlan* p, cudaStream_t st) {
     Q.in0 = (const __half*)L.in0; Q.in1 = (const __half*)L.in1; Q.out = (__half*)L.out;
     Q.w = (const uint4*)L.w_frag; Q.scale = L.scale; Q.shift = L.shift;
     Q.transposed = L.transposed; Q.Win = L.Win; Q.C0 = L.C0; Q.C1 = L.C1; Q.Cout = L.Cout; Q.act = L.act;
+    Q.lgCin = 0; while ((1 << Q.lgCin) < L.C0 + L.C1) ++Q.lgCin;
+    Q.cut = s1_cut(S1Geom{L.transposed, L.Win, L.C0 + L.C1, L.Cout}, g_s1_cluster);
   }
   const ConvLayer& A = p->layers[0];
   P.x = (const float*)A.in0; P.w0 = A.w_direct; P.sc0 = A.scale; P.sh0 = A.shift; P.enc0 = (__half*)A.out; P.in_ch = A.C0; P.base = A.Cout; P.act0 = A.act;
