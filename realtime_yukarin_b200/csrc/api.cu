@@ -173,6 +173,7 @@ int ryk_engine_destroy(ryk_engine* h) {
   cudaStreamSynchronize(e->stream);
   for (auto& kv : e->dio_plans) dio_plan_free(kv.second);
   unet_destroy(e->stage1); unet_destroy(e->stage2);
+  crepe_destroy();
   for (Synth* s : e->synths) synth_destroy(s);
   session_destroy_all(e);
   void* ptrs[] = {e->d_colmin, e->d_twiddle, e->d_jump, e->d_G, e->d_H, e->d_s1_in_mean, e->d_s1_in_std, e->d_s1_out_mean, e->d_s1_out_std, e->d_scratch};
@@ -686,6 +687,25 @@ int ryk_debug_synth_timebase(ryk_engine* h, int id, int n, double* if0, double* 
   RYK_CUDA(cudaMemcpy(ivuv, s->dev.ivuv, sizeof(double) * n, cudaMemcpyDeviceToHost));
   RYK_CUDA(cudaMemcpy(tp, s->dev.tp, sizeof(double) * n, cudaMemcpyDeviceToHost));
   return 0;
+}
+
+// ---- CREPE f0 front-end (acoustic_feature_wrapper.py:65-80): model upload and crepe.predict + predict_voicing on 16 kHz audio
+int ryk_crepe_create(ryk_engine* h, int capacity_multiplier) { RYK_CUDA(cudaSetDevice(E(h)->device)); return crepe_create(E(h), capacity_multiplier); }
+int ryk_crepe_set_conv(ryk_engine* h, int layer, const float* W, const float* bias, const float* gamma, const float* beta, const float* mean,
+                       const float* var) {
+  RYK_CUDA(cudaSetDevice(E(h)->device));
+  return crepe_set_conv(E(h), layer, W, bias, gamma, beta, mean, var);
+}
+int ryk_crepe_set_dense(ryk_engine* h, const float* W, const float* bias) { RYK_CUDA(cudaSetDevice(E(h)->device)); return crepe_set_dense(E(h), W, bias); }
+int ryk_crepe_set_decoder_tables(ryk_engine* h, const double* log_trans, double log_start, double log_emit_self, double log_emit_other) {
+  RYK_CUDA(cudaSetDevice(E(h)->device));
+  return crepe_set_tables(E(h), log_trans, log_start, log_emit_self, log_emit_other);
+}
+int ryk_crepe_num_frames(int n16, double step_ms) { return crepe_num_frames(n16, step_ms); }
+int ryk_crepe_predict(ryk_engine* h, const float* audio16k, int n, double step_ms, double* f0, float* confidence, int* voicing, float* activation,
+                      int* path) {
+  RYK_CUDA(cudaSetDevice(E(h)->device));
+  return crepe_predict(E(h), audio16k, n, step_ms, f0, confidence, voicing, activation, path);
 }
 
 // f0 extractor behind ryk_world_f0 / ryk_world_analyze / new sessions: 0 = DIO + StoneMask (default), 1 = Harvest + StoneMask.

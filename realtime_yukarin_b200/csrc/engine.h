@@ -78,6 +78,14 @@ void harvest_plan_free(HarvestPlan* p);
 int harvest_run(Engine* e, HarvestPlan* p, const float* d_x, double* d_f0, cudaStream_t st);
 int harvest_plan_debug_copy(HarvestPlan* p, int* info, double* y, double* raw, double* cand, double* score, double* best, double* basic,
                             cudaStream_t st);
+// crepe.cu: CREPE f0 front-end (acoustic_feature_wrapper.py:65-80)
+int crepe_create(Engine* e, int capacity_multiplier);
+void crepe_destroy();
+int crepe_set_conv(Engine* e, int layer, const float* W, const float* bias, const float* gamma, const float* beta, const float* mean, const float* var);
+int crepe_set_dense(Engine* e, const float* W, const float* bias);
+int crepe_set_tables(Engine* e, const double* log_trans, double log_start, double log_emit_self, double log_emit_other);
+int crepe_num_frames(int n16, double step_ms);
+int crepe_predict(Engine* e, const float* audio16k, int n, double step_ms, double* f0, float* confidence, int* voicing, float* activation, int* path_out);
 // s1_fused.cu diagnostics
 int s1_fused_bench(Engine* e, UNetPlan* p, int iters, float* ms_fused, float* ms_layered, double* timeline_us);
 int dio_plan_debug_copy(DioPlan* p, double* f0_raw, double* cand, double* score, int* counts, cudaStream_t st);

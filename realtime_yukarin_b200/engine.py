@@ -52,6 +52,7 @@ EXPORTED_SYMBOLS = [
     'ryk_reblock_push', 'ryk_reblock_push_device', 'ryk_reblock_collect', 'ryk_reblock_result_device', 'ryk_resample_length',
     'ryk_resample_poly', 'ryk_session_poll', 'ryk_reblock_poll', 'ryk_engine_profile_read2', 'ryk_engine_set_stage1_fused',
     'ryk_engine_set_f0_method', 'ryk_engine_get_f0_method', 'ryk_debug_harvest', 'ryk_debug_stage1_bench',
+    'ryk_crepe_create', 'ryk_crepe_set_conv', 'ryk_crepe_set_dense', 'ryk_crepe_set_decoder_tables', 'ryk_crepe_num_frames', 'ryk_crepe_predict',
 ]
 
 

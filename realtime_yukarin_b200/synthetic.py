@@ -108,6 +108,36 @@ def write_synthetic_models(directory, seed: int = 0, base1: int = 64, base2: int
     return paths
 
 
+def make_crepe_params(seed: int = 0, capacity: str = 'tiny') -> Dict[str, numpy.ndarray]:
+    """Seeded random weights of the CREPE architecture (He-style scales, mildly perturbed BatchNorm statistics): the trained weights
+    cannot be fetched here, so parity tests exercise the architecture and the decoders, not pitch accuracy."""
+    mult = {'tiny': 4, 'small': 8, 'medium': 16, 'large': 24, 'full': 32}[capacity]
+    rng = numpy.random.default_rng(9000 + seed)
+    filters = [n * mult for n in (32, 4, 4, 4, 8, 16)]
+    widths = [512, 64, 64, 64, 64, 64]
+    p = {}
+    cin = 1
+    for l, (f, w) in enumerate(zip(filters, widths)):
+        p[f'conv{l + 1}.W'] = (rng.standard_normal((f, cin, w)) * numpy.sqrt(2.0 / (cin * w))).astype(numpy.float32)
+        p[f'conv{l + 1}.b'] = (0.05 * rng.standard_normal(f)).astype(numpy.float32)
+        p[f'bn{l + 1}.gamma'] = (1.0 + 0.1 * rng.standard_normal(f)).astype(numpy.float32)
+        p[f'bn{l + 1}.beta'] = (0.1 * rng.standard_normal(f)).astype(numpy.float32)
+        p[f'bn{l + 1}.mean'] = (0.3 + 0.1 * rng.standard_normal(f)).astype(numpy.float32)
+        p[f'bn{l + 1}.var'] = (0.5 + 0.2 * rng.random(f)).astype(numpy.float32)
+        cin = f
+    p['dense.W'] = (rng.standard_normal((360, 4 * filters[5])) * numpy.sqrt(0.5 / (4 * filters[5]))).astype(numpy.float32)
+    p['dense.b'] = (0.5 * rng.standard_normal(360)).astype(numpy.float32)
+    return p
+
+
+def write_crepe_model(directory, seed: int = 0, capacity: str = 'tiny') -> Path:
+    d = Path(directory)
+    d.mkdir(parents=True, exist_ok=True)
+    path = d / f'crepe_{capacity}.npz'
+    numpy.savez(path, **make_crepe_params(seed, capacity))
+    return path
+
+
 def synthetic_speech(seconds: float, stream: int = 0, fs: int = 24000, silence_fraction: float = 0.2) -> numpy.ndarray:
     """Voiced harmonic source with a random-walk f0 (100-300 Hz), 20 harmonics with 1/h roll-off,
     amplitude 0.1-0.3, -40 dB white noise and ~20 % silent gaps."""

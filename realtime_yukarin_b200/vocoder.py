@@ -12,11 +12,13 @@ from .world_consts import cheaptrick_fft_size
 
 
 class CrepeAcousticFeatureWrapper(AcousticFeatureWrapper):
-    """CREPE f0 front-end (acoustic_feature_wrapper.py:65-80): out of scope for the B200 hot path (SURVEY 2a #9)."""
+    """CREPE f0 front-end (acoustic_feature_wrapper.py:65-80): crepe.predict + crepe.predict_voicing on the device (csrc/crepe.cu),
+    the rest of the analysis (CheapTrick / D4C / sp2mc) on that f0.  Needs a weight file (realtime_yukarin_b200.crepe)."""
 
     @classmethod
     def extract_f0(cls, x, fs, frame_period, f0_floor, f0_ceil):
-        raise NotImplementedError('the CREPE f0 mode is outside the accelerated path; use VocodeMode.WORLD')
+        from . import crepe
+        return crepe.extract_f0(x, fs, frame_period)
 
 
 class Vocoder(object):

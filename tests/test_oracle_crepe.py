@@ -1,0 +1,61 @@
+"""CREPE restatement (oracle/crepe.py; PARITY UNPINNED: neither the crepe package nor its weights are available here): the pieces
+that can be pinned independently are -- the Viterbi decoder against exhaustive search, TensorFlow 'same' padding arithmetic, the local
+cents average, the voicing HMM on hand-made confidences, the frame / normalisation step and the network's tensor shapes."""
+import itertools
+
+import numpy as np
+
+from oracle import crepe as oc
+from realtime_yukarin_b200 import synthetic
+
+
+def test_viterbi_equals_exhaustive_search():
+    rng = np.random.default_rng(0)
+    for n, T in ((3, 5), (4, 4), (2, 7)):
+        start = np.log(rng.dirichlet(np.ones(n)))
+        trans = np.log(rng.dirichlet(np.ones(n), size=n))
+        frame = np.log(rng.random((T, n)))
+        path = oc.viterbi(start, trans, frame)
+        best, best_p = -np.inf, None
+        for p in itertools.product(range(n), repeat=T):
+            s = start[p[0]] + frame[0, p[0]] + sum(trans[p[t - 1], p[t]] + frame[t, p[t]] for t in range(1, T))
+            if s > best + 1e-12:
+                best, best_p = s, p
+        assert tuple(path) == best_p
+
+
+def test_same_padding_is_tensorflows():
+    assert oc.same_padding(1024, 512, 4) == (256, 254, 254)
+    assert oc.same_padding(128, 64, 1) == (128, 31, 32)
+    assert oc.same_padding(8, 64, 1) == (8, 31, 32)
+
+
+def test_local_average_and_cents_mapping():
+    s = np.zeros(360, np.float32); s[100] = 1.0
+    assert abs(oc.to_local_average_cents(s) - oc.CENTS_MAPPING[100]) < 1e-9
+    s[101] = 1.0
+    assert abs(oc.to_local_average_cents(s) - 0.5 * (oc.CENTS_MAPPING[100] + oc.CENTS_MAPPING[101])) < 1e-9
+    assert abs(oc.CENTS_MAPPING[1] - oc.CENTS_MAPPING[0] - 20.0) < 1e-9          # 20-cent bins
+    assert abs(10 * 2 ** (oc.CENTS_MAPPING[0] / 1200) - 31.7) < 0.1               # C1 ~ 32.7 Hz region
+
+
+def test_voicing_hmm_keeps_state_through_short_dips():
+    conf = np.array([0.9] * 20 + [0.3] * 2 + [0.9] * 20 + [0.05] * 40)
+    v = oc.predict_voicing(conf)
+    assert np.all(v[:42] == 1)            # a two-frame dip does not leave the voiced state (self transition 0.99)
+    assert np.all(v[-30:] == 0)
+
+
+def test_frames_and_network_shapes():
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(4800).astype(np.float32)
+    fr = oc.frames_of(x, 5.0)
+    assert fr.shape == (61, 1024)
+    assert np.allclose(fr.mean(1), 0, atol=1e-6) and np.allclose(fr.std(1), 1, atol=1e-4)
+    assert np.allclose(fr[0, :512], fr[0, :512][0])          # the first frame starts in the zero padding (constant after centring)
+    w = synthetic.make_crepe_params(0, 'tiny')
+    act = oc.get_activation(x[:1600], w, 10.0)
+    assert act.shape == (11, 360) and np.all((act > 0) & (act < 1))
+    t, f0, conf, _ = oc.predict(x[:1600], w, 10.0)
+    assert np.allclose(t, np.arange(11) * 0.01) and np.all(f0 > 30) and np.all(f0 < 2100)
+    assert np.allclose(conf, act.max(1))
