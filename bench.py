@@ -54,8 +54,8 @@ def stage2_tc_flop(Tp=384, base=64):
     return fl
 
 
-DTYPE = ('f64 (WORLD analysis / synthesis, SPTK), f16 operands / f32 accumulate on tcgen05 (stage-1 and stage-2 k4 layers), '
-         'f32 CUDA cores (3x3 / k3 edge layers)')
+DTYPE = ('f64 (WORLD analysis / synthesis, SPTK), f16 operands / f32 accumulate: stage-2 k4 layers on tcgen05, stage-1 k4 layers on mma.sync '
+         'inside the one-launch cluster kernel; f32 CUDA cores (3x3 / k3 edge layers)')
 
 
 def bench_config(workload, B=1):
@@ -64,7 +64,7 @@ def bench_config(workload, B=1):
         workload=workload,
         timing='CUDA events on the engine stream (forked to / joined from the session streams) around the K pushes, max over ranks',
         pipeline='gate | analysis (2 chunks in flight) | stage 1 | stage 2 | synthesis of consecutive chunks overlap on 6 CUDA streams per audio '
-                 'stream, each stage a CUDA graph (the reference overlaps its 3 worker processes); e2e keeps 3 steps in flight',
+                 'stream, each stage a CUDA graph (the reference overlaps its 3 worker processes); e2e keeps 4 steps in flight',
         l2='per-step footprint (109 MB fp16 stage-2 weights + 54 MB stage-1 weights + ~100 MB activations) exceeds the 126 MB L2; no explicit flush',
         streams_per_gpu=B, silence_threshold_db=THRESHOLD_DB)
 
@@ -291,10 +291,11 @@ def run_gpu(args):
         Tw = round((T + 2 * EXTRA[1]) * 200)
         return Tw, Tw + (128 - Tw % 128)
 
-    def run_config(T, B, steps, warmup, with_e2e, sustain_s=0.0):
+    def run_config(T, B, steps, warmup, with_e2e, sustain_s=0.0, f0_method='dio'):
         """One workload (buffer_time T, B grouped streams per GPU) on every rank: device-resident leg, optional sustained repeat of
         the same K-step block, optional end-to-end leg with host buffers.  Returns a dict of rank-0 figures (times max over ranks)."""
         Tw, Tp = window(T)
+        eng.set_f0_method(f0_method)          # sessions take the extractor that is selected when they are created
 
         def new_streams():
             """B sessions of this rank; B > 1: grouped so that stage 2 runs once per step at batch B (BASELINE config 5)."""
@@ -393,7 +394,7 @@ def run_gpu(args):
             sids, gid = new_streams()
             host_out = [np.empty(out_cap, dtype=np.float64) for _ in range(B)]
             produced = 0
-            DEPTH = 3                                    # steps in flight (submit k, collect k - DEPTH): host buffers both ways
+            DEPTH = 4                                    # steps in flight (submit k, collect k - DEPTH; the API allows 5): host buffers both ways
 
             def submit(k):
                 return eng.session_submit(sids[0], chunks[k][0]) if gid is None else eng.group_submit(gid, chunks[k])
@@ -419,6 +420,7 @@ def run_gpu(args):
             res['t_e2e'] = max_over_ranks(t_e2e)
             res['produced'] = produced
             free_streams(sids, gid)
+        eng.set_f0_method('dio')
         return res
 
     T, B = args.buffer_time, args.streams_per_gpu
@@ -429,6 +431,8 @@ def run_gpu(args):
         # BASELINE configs 3 and 5, short device-resident legs so that the driver's N = 1..8 runs record them too
         for (Tx, Bx, sx) in ((0.1, 1, 20), (1.0, 1, 12), (1.0, 8, 6)):
             extras.append(run_config(Tx, Bx, sx, 3, with_e2e=False))
+        # the default workload with Harvest (+ StoneMask) as the f0 extractor inside the session's analysis graph (north_star: "DIO/Harvest f0")
+        harvest_leg = run_config(T, 1, 12, 3, with_e2e=False, f0_method='harvest')
 
     if world > 1:
         import torch.distributed as dist
@@ -495,6 +499,9 @@ def run_gpu(args):
             ex[f'{Bx}x{Tx:g}s'] = dict(value=v, unit='chunks/s', rtf=v * Tx, steps=sx, ms_per_step=1000.0 * r['t_dev'] / sx, streams_per_gpu=Bx,
                                        workload=workload_of(Tx, Bx, r['Tw'], r['Tp']), stage2_tflops=a,
                                        stage2_frac=(a / peaks['tflops']) if a else None)
+        vh = world * 12 / harvest_leg['t_dev']
+        ex['1x0.3s_harvest_f0'] = dict(value=vh, unit='chunks/s', rtf=vh * T, steps=12, ms_per_step=1000.0 * harvest_leg['t_dev'] / 12, streams_per_gpu=1,
+                                       workload=workload_of(T, 1, harvest_leg['Tw'], harvest_leg['Tp']) + ', f0 = Harvest + StoneMask')
         line['extra_configs'] = ex
     if 'stage_times' in main:
         line['stage_timeline'] = main['stage_times']

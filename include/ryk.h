@@ -84,13 +84,14 @@ int ryk_engine_get_f0_method(ryk_engine* e);
  * resamples to 16 kHz (ryk_resample_poly) and applies the reference's rule voiced = (voicing == 1) | (confidence > 0.1).
  * capacity_multiplier: 4 tiny, 8 small, 16 medium, 24 large, 32 full.  Conv weights W (cout, cin, k) for blocks 0..5 with widths
  * 512, 64 x 5 and filters m * {32, 4, 4, 4, 8, 16}; BatchNorm statistics per block (eps 1e-3); dense W (360, 64 m).
- * log_trans: the 360 x 360 log transition matrix of the pitch HMM and its start / emission log-probabilities, computed by the host
+ * log_trans: the 360 x 360 log transition matrix of the pitch HMM, its start / emission log-probabilities and the bin -> cents table, computed by the host
  * mirror exactly as crepe.to_viterbi_cents does (shared tables make the Viterbi sums bit-identical to the CPU restatement). */
 int ryk_crepe_create(ryk_engine* e, int capacity_multiplier);
 int ryk_crepe_set_conv(ryk_engine* e, int block, const float* W, const float* bias, const float* bn_gamma, const float* bn_beta,
                        const float* bn_mean, const float* bn_var);
 int ryk_crepe_set_dense(ryk_engine* e, const float* W, const float* bias);
-int ryk_crepe_set_decoder_tables(ryk_engine* e, const double* log_trans, double log_start, double log_emit_self, double log_emit_other);
+int ryk_crepe_set_decoder_tables(ryk_engine* e, const double* log_trans, const double* cents_mapping /* [360] */, double log_start,
+                                 double log_emit_self, double log_emit_other);
 int ryk_crepe_num_frames(int n16, double step_ms);
 /* f0 / confidence / voicing (HMM state) [frames], activation [frames][360], path [frames] (pitch-bin Viterbi path); any may be NULL */
 int ryk_crepe_predict(ryk_engine* e, const float* audio16k, int n, double step_ms, double* f0, float* confidence, int* voicing,

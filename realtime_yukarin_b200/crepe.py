@@ -59,7 +59,9 @@ def load_crepe_model(path, engine=None) -> int:
         raise ValueError(f'dense.W has shape {Wd.shape}')
     engine._check(lib.ryk_crepe_set_dense(h, fp(Wd), fp(bd)))
     ls, lt, (es, eo) = pitch_hmm_tables()
-    engine._check(lib.ryk_crepe_set_decoder_tables(h, lt.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ctypes.c_double(ls),
+    cents = numpy.ascontiguousarray(numpy.linspace(0, 7180, 360) + 1997.3794084376191)      # crepe's cents_mapping
+    engine._check(lib.ryk_crepe_set_decoder_tables(h, lt.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                                   cents.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ctypes.c_double(ls),
                                                    ctypes.c_double(es), ctypes.c_double(eo)))
     _loaded['engine'], _loaded['multiplier'] = engine, mult
     return mult

@@ -697,9 +697,10 @@ int ryk_crepe_set_conv(ryk_engine* h, int layer, const float* W, const float* bi
   return crepe_set_conv(E(h), layer, W, bias, gamma, beta, mean, var);
 }
 int ryk_crepe_set_dense(ryk_engine* h, const float* W, const float* bias) { RYK_CUDA(cudaSetDevice(E(h)->device)); return crepe_set_dense(E(h), W, bias); }
-int ryk_crepe_set_decoder_tables(ryk_engine* h, const double* log_trans, double log_start, double log_emit_self, double log_emit_other) {
+int ryk_crepe_set_decoder_tables(ryk_engine* h, const double* log_trans, const double* cents_mapping, double log_start, double log_emit_self,
+                                 double log_emit_other) {
   RYK_CUDA(cudaSetDevice(E(h)->device));
-  return crepe_set_tables(E(h), log_trans, log_start, log_emit_self, log_emit_other);
+  return crepe_set_tables(E(h), log_trans, cents_mapping, log_start, log_emit_self, log_emit_other);
 }
 int ryk_crepe_num_frames(int n16, double step_ms) { return crepe_num_frames(n16, step_ms); }
 int ryk_crepe_predict(ryk_engine* h, const float* audio16k, int n, double step_ms, double* f0, float* confidence, int* voicing, float* activation,

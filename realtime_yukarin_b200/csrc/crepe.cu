@@ -37,6 +37,7 @@ struct CrepeModel {
   float* d_dense_w = nullptr;   // [64 m][360]
   float* d_dense_b = nullptr;
   double* d_log_trans = nullptr;   // [360][360]
+  double* d_cents = nullptr;       // [360] crepe's cents_mapping (np.linspace(0, 7180, 360) + 1997.379...)
   double h_log_start = 0, h_log_emit[2] = {0, 0};
   bool tables = false;
   bool loaded[7] = {};
@@ -150,7 +151,8 @@ __device__ inline int crepe_argmax(double v, int i, int n, double* sval, int* si
 // hmmlearn _viterbi over the 360 pitch bins (one CTA of 384 threads: thread j owns state j), local average of cents around the path,
 // f0 = 10 * 2^(cents / 1200); then the 2-state Gaussian voicing HMM on the confidence (thread 0) and the reference's voicing rule.
 __global__ void __launch_bounds__(384) k_crepe_decode(const float* __restrict__ act, const float* __restrict__ conf, const int* __restrict__ obs,
-                                                     int F, const double* __restrict__ log_trans, double log_start, double log_emit_self,
+                                                     int F, const double* __restrict__ log_trans, const double* __restrict__ cents_map,
+                                                     double log_start, double log_emit_self,
                                                      double log_emit_other, double* __restrict__ lattice, int* __restrict__ path,
                                                      double* __restrict__ vlat, double* __restrict__ f0, int* __restrict__ voicing) {
   __shared__ double sval[384]; __shared__ int sidx[384];
@@ -184,13 +186,27 @@ __global__ void __launch_bounds__(384) k_crepe_decode(const float* __restrict__ 
   for (int t = j; t < F; t += blockDim.x) {
     const int center = path[t];
     const int start = center - 4 < 0 ? 0 : center - 4, end = center + 5 > kCrepeBins ? kCrepeBins : center + 5;
-    double ps = 0.0, ws = 0.0;
-    for (int i = start; i < end; ++i) {
-      const double s = (double)act[(size_t)t * kCrepeBins + i];
-      const double cents = (7180.0 * i) / 359.0 + 1997.3794084376191;     // np.linspace(0, 7180, 360)[i] + 1997.379...
-      ps += s * cents; ws += s;
+    // np.sum(salience * cents_mapping[start:end]) / np.sum(salience) with numpy's dtypes and summation order: the products are float64,
+    // the weight sum stays float32; n < 8 elements are added left to right, otherwise eight accumulators are combined pairwise and the
+    // remainder added (numpy's pairwise_sum for n <= 128).
+    const int n = end - start;
+    double p[9]; float s32[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const bool in = i < n;
+      const float s = in ? act[(size_t)t * kCrepeBins + start + i] : 0.f;
+      s32[i] = s; p[i] = in ? (double)s * cents_map[start + i] : 0.0;
     }
-    const double cents = ps / ws;
+    double ps; float ws;
+    if (n < 8) {
+      ps = 0.0; ws = 0.f;
+      for (int i = 0; i < n; ++i) { ps += p[i]; ws += s32[i]; }
+    } else {
+      ps = ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+      ws = ((s32[0] + s32[1]) + (s32[2] + s32[3])) + ((s32[4] + s32[5]) + (s32[6] + s32[7]));
+      for (int i = 8; i < n; ++i) { ps += p[i]; ws += s32[i]; }
+    }
+    const double cents = ps / (double)ws;
     double fr = 10.0 * exp2(cents / 1200.0);
     if (isnan(fr)) fr = 0.0;
     f0[t] = fr;
@@ -226,7 +242,7 @@ __global__ void __launch_bounds__(384) k_crepe_decode(const float* __restrict__ 
 static void crepe_free(CrepeModel* m) {
   if (!m) return;
   for (int l = 0; l < 6; ++l) { cudaFree(m->d_w[l]); cudaFree(m->d_bias[l]); cudaFree(m->d_bn_a[l]); cudaFree(m->d_bn_c[l]); cudaFree(m->d_conv[l]); cudaFree(m->d_in[l]); }
-  void* ptrs[] = {m->d_ones, m->d_dense_w, m->d_dense_b, m->d_log_trans, m->d_audio, m->d_im2col, m->d_flat, m->d_logit, m->d_act, m->d_conf, m->d_obs,
+  void* ptrs[] = {m->d_ones, m->d_dense_w, m->d_dense_b, m->d_log_trans, m->d_cents, m->d_audio, m->d_im2col, m->d_flat, m->d_logit, m->d_act, m->d_conf, m->d_obs,
                   m->d_lattice, m->d_path, m->d_f0, m->d_voicing, m->d_vlat};
   for (void* p : ptrs) cudaFree(p);
   delete m;
@@ -293,11 +309,13 @@ int crepe_set_dense(Engine* e, const float* W, const float* bias) {
   return 0;
 }
 
-int crepe_set_tables(Engine* e, const double* log_trans, double log_start, double log_emit_self, double log_emit_other) {
+int crepe_set_tables(Engine* e, const double* log_trans, const double* cents_mapping, double log_start, double log_emit_self, double log_emit_other) {
   CrepeModel* m = g_crepe;
   RYK_CHECK(m != nullptr, "create the CREPE model first");
   if (!m->d_log_trans) RYK_CUDA(cudaMalloc(&m->d_log_trans, sizeof(double) * kCrepeBins * kCrepeBins));
   RYK_CUDA(cudaMemcpy(m->d_log_trans, log_trans, sizeof(double) * kCrepeBins * kCrepeBins, cudaMemcpyHostToDevice));
+  if (!m->d_cents) RYK_CUDA(cudaMalloc(&m->d_cents, sizeof(double) * kCrepeBins));
+  RYK_CUDA(cudaMemcpy(m->d_cents, cents_mapping, sizeof(double) * kCrepeBins, cudaMemcpyHostToDevice));
   m->h_log_start = log_start; m->h_log_emit[0] = log_emit_self; m->h_log_emit[1] = log_emit_other;
   m->tables = true;
   return 0;
@@ -395,7 +413,7 @@ int crepe_predict(Engine* e, const float* audio16k, int n, double step_ms, doubl
     if (conv_direct_run(L, st)) return -1;
   }
   k_crepe_sigmoid<<<F, 128, 0, st>>>(m->d_logit, m->d_act, m->d_conf, m->d_obs);
-  k_crepe_decode<<<1, 384, 0, st>>>(m->d_act, m->d_conf, m->d_obs, F, m->d_log_trans, m->h_log_start, m->h_log_emit[0], m->h_log_emit[1],
+  k_crepe_decode<<<1, 384, 0, st>>>(m->d_act, m->d_conf, m->d_obs, F, m->d_log_trans, m->d_cents, m->h_log_start, m->h_log_emit[0], m->h_log_emit[1],
                                    m->d_lattice, m->d_path, m->d_vlat, m->d_f0, m->d_voicing);
   RYK_CUDA(cudaGetLastError());
   e->launches += 12;

@@ -83,7 +83,7 @@ int crepe_create(Engine* e, int capacity_multiplier);
 void crepe_destroy();
 int crepe_set_conv(Engine* e, int layer, const float* W, const float* bias, const float* gamma, const float* beta, const float* mean, const float* var);
 int crepe_set_dense(Engine* e, const float* W, const float* bias);
-int crepe_set_tables(Engine* e, const double* log_trans, double log_start, double log_emit_self, double log_emit_other);
+int crepe_set_tables(Engine* e, const double* log_trans, const double* cents_mapping, double log_start, double log_emit_self, double log_emit_other);
 int crepe_num_frames(int n16, double step_ms);
 int crepe_predict(Engine* e, const float* audio16k, int n, double step_ms, double* f0, float* confidence, int* voicing, float* activation, int* path_out);
 // s1_fused.cu diagnostics
