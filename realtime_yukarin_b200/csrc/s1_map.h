@@ -23,7 +23,7 @@ namespace ryk {
 
 constexpr int kS1Warps = 16;                 // warps per CTA
 constexpr int kS1Threads = kS1Warps * 32;
-constexpr int kS1ActBytes = 56 * 1024;       // staged input rows of one layer (one M slab)
+constexpr int kS1ActBytes = 104 * 1024;      // staged input rows of one layer (one M slab): every layer of a 384-frame window is ONE slab
 constexpr int kS1PartialBytes = kS1Warps * 16 * 32 * 4;   // split-K partial accumulators: [warp][16 regs][32 lanes] floats
 constexpr int kS1RowPad = 8;                 // halfs of padding per staged row (keeps rows 16-byte aligned, spreads banks)
 

@@ -59,3 +59,17 @@ def test_frames_and_network_shapes():
     t, f0, conf, _ = oc.predict(x[:1600], w, 10.0)
     assert np.allclose(t, np.arange(11) * 0.01) and np.all(f0 > 30) and np.all(f0 < 2100)
     assert np.allclose(conf, act.max(1))
+
+
+def test_product_decoder_tables_equal_the_oracles():
+    """The host mirror (realtime_yukarin_b200/crepe.py) builds the HMM tables it uploads to the device exactly as the restatement does:
+    the device's Viterbi sums are then bit-identical to the CPU's.  (The product module does not import the oracle; this test does.)"""
+    from realtime_yukarin_b200 import crepe as pc
+    ls, lt, (es, eo) = pc.pitch_hmm_tables()
+    ols, olt, oemit = oc.pitch_hmm_tables()
+    assert ls == ols[0] and np.all(ols == ols[0])
+    assert np.array_equal(lt, olt)
+    assert (es, eo) == (oemit[0], oemit[1])
+    assert np.array_equal(np.linspace(0, 7180, 360) + 1997.3794084376191, oc.CENTS_MAPPING)
+    # banded: transitions beyond +-11 bins are impossible
+    assert np.isneginf(lt[0, 12]) and np.isfinite(lt[0, 11]) and np.isfinite(lt[200, 189]) and np.isneginf(lt[200, 188])
