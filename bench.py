@@ -72,7 +72,7 @@ def bench_config(workload, B=1):
 def stage2_traffic():
     """DRAM bytes of one stage-2 k4 block from THIS round's ncu capture (tools/ncu_stage2_traffic.py writes the file from the
     --set full report); None when the capture is absent."""
-    f = ROOT / 'profiles' / 'r02_stage2_traffic.json'
+    f = ROOT / 'profiles' / 'r02b_stage2_traffic.json'      # this round's latest `--set full` capture (tools/gpu_r02b_final.sh)
     if not f.exists():
         return None, None
     d = json.loads(f.read_text())
@@ -296,6 +296,8 @@ def run_gpu(args):
         the same K-step block, optional end-to-end leg with host buffers.  Returns a dict of rank-0 figures (times max over ranks)."""
         Tw, Tp = window(T)
         eng.set_f0_method(f0_method)          # sessions take the extractor that is selected when they are created
+        # grouped streams: B cluster kernels of 16 SMs each would crowd the batched stage-2 forward, so groups keep the 16-layer stage 1
+        eng.set_stage1_fused(B == 1)
 
         def new_streams():
             """B sessions of this rank; B > 1: grouped so that stage 2 runs once per step at batch B (BASELINE config 5)."""
@@ -421,6 +423,7 @@ def run_gpu(args):
             res['produced'] = produced
             free_streams(sids, gid)
         eng.set_f0_method('dio')
+        eng.set_stage1_fused(True)
         return res
 
     T, B = args.buffer_time, args.streams_per_gpu

@@ -3,8 +3,8 @@
 // Selected with ryk_engine_set_f0_method(e, 1); the result feeds StoneMask exactly like DIO's does (DESIGN, DECIDE H3).
 //
 // Mapping to the hardware (FP64 throughout; FFT / scan / compare work, no tensor cores):
-//   * decimation to ~8 kHz is WORLD's zero-phase 3rd-order Chebyshev IIR -- a sequential recurrence over the chunk, run by one thread
-//     with the reversals / padding done by the whole CTA (7.5k steps for a 0.3 s chunk);
+//   * decimation to ~8 kHz is WORLD's zero-phase 3rd-order Chebyshev IIR -- a sequential recurrence, cut into per-thread segments with
+//     a warm-up prefix that the filter's pole radius makes exact to 1e-21 (hv_filter_for_decimate);
 //   * the 40-channels-per-octave band-pass bank is ONE batched cuFFT Z2D over cached filter spectra (152 channels x 4096 points),
 //     followed by the ordered zero-crossing extraction shared with DIO (analysis_shared.cuh), one CTA per (event type, channel);
 //   * candidate detection / overlap / removal are one thread per frame or per (frame, candidate);
@@ -67,13 +67,21 @@ __constant__ double c_dec_b[13][2] = {{0, 0}, {0, 0},
   {0.0026822508007164039, 0.0080467524021492123},
   {0.0021097275904708771, 0.0063291827714126309}};
 
-// FilterForDecimate: one thread, explicit rounding order (no FMA contraction: same operation sequence as the CPU restatement)
+// FilterForDecimate, all threads of the CTA: the recurrence is sequential (4 dependent FP64 operations per sample: ~1 ms for the 15 k
+// steps of a 0.3 s chunk on one thread), but the filter is stable with pole radius rho(r) <= 0.89, so thread t can start `warm` samples
+// before its own segment from a zero state -- after `warm` steps the state differs from the true one by rho^warm < 1e-21 of the signal
+// (c_dec_warm = 1.25 * 17 ln 10 / -ln rho) -- and then produces its segment with the CPU restatement's operation order (explicit
+// rounding, no FMA contraction).  Thread 0 and every thread whose warm-up reaches the start of the signal are exact.
+__constant__ int c_dec_warm[13] = {0, 0, 117, 130, 156, 186, 218, 250, 283, 317, 350, 384, 417};
 __device__ inline void hv_filter_for_decimate(const double* __restrict__ x, int n, int r, double* __restrict__ y) {
   const double a0 = c_dec_a[r][0], a1 = c_dec_a[r][1], a2 = c_dec_a[r][2], b0 = c_dec_b[r][0], b1 = c_dec_b[r][1];
+  const int seg = (n + blockDim.x - 1) / blockDim.x;
+  const int lo = threadIdx.x * seg, hi = min(n, lo + seg);
+  if (lo >= hi) return;
   double w0 = 0.0, w1 = 0.0, w2 = 0.0;
-  for (int i = 0; i < n; ++i) {
+  for (int i = max(0, lo - c_dec_warm[r]); i < hi; ++i) {
     const double wt = __dadd_rn(__dadd_rn(__dadd_rn(x[i], __dmul_rn(a0, w0)), __dmul_rn(a1, w1)), __dmul_rn(a2, w2));
-    y[i] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(b0, wt), __dmul_rn(b1, w0)), __dmul_rn(b1, w1)), __dmul_rn(b0, w2));
+    if (i >= lo) y[i] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(b0, wt), __dmul_rn(b1, w0)), __dmul_rn(b1, w1)), __dmul_rn(b0, w2));
     w2 = w1; w1 = w0; w0 = wt;
   }
 }
@@ -97,11 +105,11 @@ __global__ void __launch_bounds__(512) k_hv_decimate(const float* __restrict__ x
       t1[i] = v;
     }
     __syncthreads();
-    if (tid == 0) hv_filter_for_decimate(t1, np, ratio, t2);
+    hv_filter_for_decimate(t1, np, ratio, t2);
     __syncthreads();
     for (int i = tid; i < np; i += T) t1[i] = t2[np - i - 1];
     __syncthreads();
-    if (tid == 0) hv_filter_for_decimate(t1, np, ratio, t2);
+    hv_filter_for_decimate(t1, np, ratio, t2);
     __syncthreads();
     // tmp1[i] = t2[np - i - 1];  y_dec[count] = tmp1[nbeg + count * r + nf - 1];  y[i] = y_dec[lag / r + i]
     const int nout = (nx - 1) / ratio + 1;
