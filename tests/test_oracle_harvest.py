@@ -101,3 +101,32 @@ def test_harvest_golden_fixture():
     f0, _ = ow.harvest(x, 24000)
     assert np.array_equal(f0 != 0, g['f0'] != 0)
     assert np.allclose(f0, g['f0'], rtol=1e-9, atol=0)
+
+
+AUDIO_A = Path('/root/reference/tests/data/audioA.wav')        # the reference's own fixture; read in place when the checkout is present
+
+
+@pytest.mark.skipif(not AUDIO_A.exists(), reason='reference checkout (tests/data/audioA.wav) not present on this machine')
+def test_harvest_on_the_reference_recording():
+    """Real speech (the reference's tests/data/audioA.wav at 24 kHz, 4 s): Harvest and DIO + StoneMask -- two different published
+    extractors restated independently of each other -- agree on the pitch where both are voiced, Harvest's contour is the smoother
+    one and covers more of the voiced speech, and every value is inside [f0_floor, f0_ceil]."""
+    from realtime_yukarin_b200 import wave_io
+    data, fs = wave_io.read_wav(AUDIO_A)
+    x = data.astype(np.float64)
+    if x.ndim > 1:
+        x = x.mean(axis=1)
+    x = signal.resample_poly(x, 24000, fs)[:24000 * 4]
+    f0h, t = ow.harvest(x, 24000)
+    f0d, td = ow.dio(x, 24000)
+    f0d = ow.stonemask(x, 24000, td, f0d)
+    both = (f0h > 0) & (f0d > 0)
+    rel = np.abs(f0h[both] - f0d[both]) / f0d[both]
+    print(f'audioA: harvest voiced {int((f0h > 0).sum())}, dio voiced {int((f0d > 0).sum())}, both {int(both.sum())}; '
+          f'median |rel diff| {np.median(rel):.4f}, 90th percentile {np.percentile(rel, 90):.4f}')
+    assert both.sum() > 150
+    assert np.median(rel) < 0.01 and np.percentile(rel, 90) < 0.05
+    assert (f0h > 0).sum() >= 0.9 * (f0d > 0).sum()
+    assert np.all((f0h == 0) | ((f0h >= 71.0) & (f0h <= 800.0)))
+    d2 = lambda f: np.abs(np.diff(f[both], 2)).mean()          # roughness of the contour on the common frames
+    assert d2(f0h) <= d2(f0d)
