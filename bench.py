@@ -16,6 +16,9 @@ import argparse
 import json
 import os
 import sys
+
+# before anything creates the CUDA context: a session drives 7 streams, a group of 8 sessions 57 (see ryk_engine_create)
+os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
 import tempfile
 import threading
 import time
@@ -53,6 +56,9 @@ def stage2_tc_flop(Tp=384, base=64):
         fl += 2.0 * 16 * cin * cout * (Tp >> (7 - d)) * (512 >> (7 - d))
     return fl
 
+
+# short device-resident legs of BASELINE configs 3 and 5 plus 4 grouped streams of the headline chunk size (buffer_time, streams per GPU, steps)
+EXTRA_LEGS = ((0.1, 1, 20), (1.0, 1, 12), (1.0, 8, 8), (0.3, 4, 12))
 
 DTYPE = ('f64 (WORLD analysis / synthesis, SPTK), f16 operands / f32 accumulate: stage-2 k4 layers on tcgen05, stage-1 k4 layers on mma.sync '
          'inside the one-launch cluster kernel; f32 CUDA cores (3x3 / k3 edge layers)')
@@ -296,8 +302,6 @@ def run_gpu(args):
         the same K-step block, optional end-to-end leg with host buffers.  Returns a dict of rank-0 figures (times max over ranks)."""
         Tw, Tp = window(T)
         eng.set_f0_method(f0_method)          # sessions take the extractor that is selected when they are created
-        # grouped streams: B cluster kernels of 16 SMs each would crowd the batched stage-2 forward, so groups keep the 16-layer stage 1
-        eng.set_stage1_fused(B == 1)
 
         def new_streams():
             """B sessions of this rank; B > 1: grouped so that stage 2 runs once per step at batch B (BASELINE config 5)."""
@@ -423,7 +427,6 @@ def run_gpu(args):
             res['produced'] = produced
             free_streams(sids, gid)
         eng.set_f0_method('dio')
-        eng.set_stage1_fused(True)
         return res
 
     T, B = args.buffer_time, args.streams_per_gpu
@@ -432,7 +435,7 @@ def run_gpu(args):
     extras = []
     if default_workload and not args.no_extra:
         # BASELINE configs 3 and 5, short device-resident legs so that the driver's N = 1..8 runs record them too
-        for (Tx, Bx, sx) in ((0.1, 1, 20), (1.0, 1, 12), (1.0, 8, 6)):
+        for (Tx, Bx, sx) in EXTRA_LEGS:
             extras.append(run_config(Tx, Bx, sx, 3, with_e2e=False))
         # the default workload with Harvest (+ StoneMask) as the f0 extractor inside the session's analysis graph (north_star: "DIO/Harvest f0")
         harvest_leg = run_config(T, 1, 12, 3, with_e2e=False, f0_method='harvest')
@@ -496,7 +499,7 @@ def run_gpu(args):
                                  note='median over back-to-back K-step blocks on rank 0 x N ranks (every rank runs the same loop)')
     if extras:
         ex = {}
-        for r, (Tx, Bx, sx) in zip(extras, ((0.1, 1, 20), (1.0, 1, 12), (1.0, 8, 6))):
+        for r, (Tx, Bx, sx) in zip(extras, EXTRA_LEGS):
             v = world * Bx * sx / r['t_dev']
             a = tflops(r)
             ex[f'{Bx}x{Tx:g}s'] = dict(value=v, unit='chunks/s', rtf=v * Tx, steps=sx, ms_per_step=1000.0 * r['t_dev'] / sx, streams_per_gpu=Bx,

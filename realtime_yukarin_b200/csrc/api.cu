@@ -3,6 +3,7 @@
 // result.  The device-resident streaming session lives in session.cu.
 #include <math.h>
 #include <stddef.h>
+#include <stdlib.h>
 #include <string.h>
 #include <mutex>
 #include <algorithm>
@@ -142,6 +143,11 @@ const char* ryk_last_error(void) { return g_err.c_str(); }
 
 int ryk_engine_create(int device, ryk_engine** out) {
   RYK_CHECK(out != nullptr, "null out pointer");
+  // A session drives 7 streams and a group of 8 sessions 57: with the default 8 hardware work queues independent streams share a queue
+  // and a stream that waits on an event holds up its queue-mates (measured: the steps of a group of 8 ran strictly one after another,
+  // 1280 chunks/s; with 32 queues they overlap, 1678; profiles/r02b_max_connections_groups.txt).  Read by the driver when the CUDA
+  // context is created, so it only takes effect if nothing initialised CUDA earlier in this process; never overrides the user's value.
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
   int count = 0;
   RYK_CUDA(cudaGetDeviceCount(&count));
   RYK_CHECK(count > 0 && device < count, "no such CUDA device (libryk has no CPU fallback)");

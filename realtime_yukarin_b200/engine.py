@@ -2,6 +2,11 @@
 the CUDA hot path.  There is NO CPU fallback: if the shared object is missing, cannot be loaded, or
 no B200 is visible, every call raises.
 """
+import os as _os
+
+# must be in the environment before the CUDA context exists (see ryk_engine_create): many independent streams need their own hardware queues
+_os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
+
 import ctypes
 import os
 import threading
