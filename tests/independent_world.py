@@ -390,3 +390,128 @@ class NumpyRealtimeSynth:
         return np.concatenate(out) if out else np.zeros(0)
 
 
+
+
+# ------------------------------------------------------------------------------------ Harvest (second writing of its array stages)
+def harvest_stages_np(x, fs, f0_floor=71.0, f0_ceil=800.0):
+    """numpy / scipy writing of Harvest up to the refined, pruned candidates and of its smoothing stage (harvest.cpp: GetWaveformAndSpectrum,
+    GetRawF0Candidates, DetectOfficialF0Candidates, OverlapF0Candidates, RefineF0Candidates, RemoveUnreliableCandidates, SmoothF0Contour).
+    The sequential contour tracking (FixStep1..4) is not rewritten here.  Returns dict(y, raw, cand, score, smooth) where smooth(best)
+    maps a tracked 1 ms contour to the smoothed one."""
+    from scipy import signal
+    x = np.asarray(x, np.float64)
+    r = mround(fs / 8000.0)
+    afs = fs / r
+    lo, hi = f0_floor * 0.9, f0_ceil * 1.1
+    channels = 1 + int(np.log(hi / lo) / np.log(2.0) * 40.0)
+    boundary = lo * 2.0 ** ((np.arange(channels) + 1) / 40.0)
+    ylen = int(np.ceil(len(x) / r))
+    # decimate: pad with the edge values, reflect 9 samples, cheby1(3, 0.05 dB) forwards and backwards, every r-th sample
+    if r == 1:
+        y = x.copy()
+    else:
+        lag = int(np.ceil(140.0 / r) * r)
+        nx = np.concatenate([np.full(lag, x[0]), x, np.full(lag, x[-1])])
+        b, a = signal.cheby1(3, 0.05, 0.8 / r)
+        t = np.concatenate([2 * nx[0] - nx[9:0:-1], nx, 2 * nx[-1] - nx[-2:-11:-1]])
+        t = signal.lfilter(b, a, t)[::-1]
+        t = signal.lfilter(b, a, t)[::-1]
+        nout = (len(nx) - 1) // r + 1
+        nbeg = r - r * nout + len(nx)
+        dec = t[np.arange(nbeg, len(nx) + 9, r) + 8]
+        y = dec[lag // r: lag // r + ylen]
+    y = y - y.mean()
+    fft = 2 ** (int(np.log2(ylen + 5 + 2 * int(2.0 * afs / boundary[0]))) + 1)
+    Y = np.fft.rfft(y, fft)
+    nf = int(1000.0 * len(x) / fs) + 1
+    tpos = np.arange(nf) / 1000.0
+    raw = np.zeros((channels, nf))
+    for c, bf in enumerate(boundary):
+        h = mround(afs / bf * 2.0)
+        bp = nuttall(2 * h + 1) * np.cos(2 * np.pi * bf * np.arange(-h, h + 1) / afs)
+        f = np.fft.irfft(Y * np.fft.rfft(bp, fft), fft)[h + 1: h + 1 + ylen]
+        d = -f[:-1] + f[1:]                                     # (-f)[i] - (-f)[i + 1]
+        trains = [zc_engine(f, afs), zc_engine(-f, afs), zc_engine(d, afs), zc_engine(-d, afs)]
+        if any(len(t_[0]) <= 2 for t_ in trains):
+            continue
+        v = np.mean([interp1(loc, itv, tpos) for loc, itv in trains], axis=0)
+        v[(v > bf * 1.1) | (v < bf * 0.9) | (v > f0_ceil) | (v < f0_floor)] = 0.0
+        raw[c] = v
+    # candidates: mean over runs of >= 10 agreeing channels
+    max_cand = mround(channels / 10.0) * 7
+    cand = np.zeros((nf, max_cand))
+    ncand = 0
+    for i in range(nf):
+        vuv = (raw[:, i] > 0).astype(int); vuv[0] = vuv[-1] = 0
+        dv = np.diff(vuv)
+        st, ed = np.nonzero(dv == 1)[0] + 1, np.nonzero(dv == -1)[0] + 1
+        k = 0
+        for s_, e_ in zip(st, ed):
+            if e_ - s_ >= 10:
+                cand[i, k] = raw[s_:e_, i].sum() / (e_ - s_)
+                k += 1
+        ncand = max(ncand, k)
+    base = cand[:, :ncand].copy()
+    for i in range(1, 4):                                        # overlap +-3 frames
+        cand[i:, ncand * i: ncand * (i + 1)] = base[:-i]
+        cand[:-i, ncand * (i + 3): ncand * (i + 4)] = base[i:]
+    nc = ncand * 7
+    # refinement (GetRefinedF0) on the decimated signal
+    score = np.zeros_like(cand)
+    n = len(y)
+    for i in range(nf):
+        for j in range(nc):
+            f = cand[i, j]
+            if f <= 0:
+                cand[i, j] = 0.0
+                continue
+            half = int(1.5 * afs / f + 1.0)
+            wl = (2 * half + 1) / afs
+            fsz = 2 ** (2 + int(np.log(half * 2 + 1.0) / np.log(2.0)))
+            idx = mround((tpos[i] - half / afs) * afs + 0.001) + np.arange(2 * half + 1)
+            tm = (idx - 1.0) / afs - tpos[i]
+            mw = 0.42 + 0.5 * np.cos(2 * np.pi * tm / wl) + 0.08 * np.cos(4 * np.pi * tm / wl)
+            dw = np.empty_like(mw)
+            dw[0] = -mw[1] / 2.0; dw[1:-1] = -(mw[2:] - mw[:-2]) / 2.0; dw[-1] = mw[-2] / 2.0
+            seg = y[np.clip(idx - 1, 0, n - 1)]
+            M, D = np.fft.rfft(seg * mw, fsz), np.fft.rfft(seg * dw, fsz)
+            nh = min(int(afs / 2.0 / f), 6)
+            k = np.minimum(np.array([mround(f * fsz / afs * (q + 1)) for q in range(nh)]), fsz // 2)
+            P = np.abs(M[k]) ** 2
+            NI = M[k].real * D[k].imag - M[k].imag * D[k].real
+            inst = np.where(P == 0, 0.0, k * afs / fsz + NI / np.where(P == 0, 1, P) * afs / 2.0 / np.pi)
+            amp = np.sqrt(P)
+            rf = (amp * inst).sum() / ((amp * (np.arange(nh) + 1.0)).sum() + 1e-12)
+            sc = 1.0 / (np.abs((inst / (np.arange(nh) + 1.0) - f) / f).sum() / nh + 1e-12)
+            if rf < f0_floor or rf > f0_ceil or sc < 2.5:
+                rf, sc = 0.0, 0.0
+            cand[i, j], score[i, j] = rf, sc
+    # removal of candidates that neither neighbouring frame supports within 5 %
+    keep = cand.copy()
+    for i in range(1, nf - 1):
+        for j in range(nc):
+            ref = keep[i, j]
+            if ref == 0:
+                continue
+            e1 = min(1.0, np.abs(ref - keep[i + 1, :nc]).min() / ref)
+            e2 = min(1.0, np.abs(ref - keep[i - 1, :nc]).min() / ref)
+            if min(e1, e2) > 0.05:
+                cand[i, j] = 0.0; score[i, j] = 0.0
+
+    def smooth(best):
+        """SmoothF0Contour: per voiced section of the 300-frame padded contour, edge-extended, Butterworth(2) forwards and backwards."""
+        b = np.array([0.0078202080334971724, 0.015640416066994345, 0.0078202080334971724])
+        a = np.array([1.0, -1.7347257688092754, 0.76600660094326412])
+        pad = np.concatenate([np.zeros(300), best, np.zeros(300)])
+        v = (pad > 0).astype(int); v[0] = v[-1] = 0
+        dv = np.diff(v)
+        st, ed = np.nonzero(dv == 1)[0] + 1, np.nonzero(dv == -1)[0]
+        out = np.zeros(len(best))
+        for s_, e_ in zip(st, ed):
+            sec = pad.copy(); sec[:s_] = pad[s_]; sec[e_ + 1:] = pad[e_]
+            z = signal.lfilter(b, a, sec)[::-1]
+            z = signal.lfilter(b, a, z)[::-1]
+            out[s_ - 300: e_ + 1 - 300] = z[s_: e_ + 1]
+        return out
+
+    return dict(y=y, raw=raw, cand=cand, score=score, nc=nc, smooth=smooth)

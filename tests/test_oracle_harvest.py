@@ -130,3 +130,21 @@ def test_harvest_on_the_reference_recording():
     assert np.all((f0h == 0) | ((f0h >= 71.0) & (f0h <= 800.0)))
     d2 = lambda f: np.abs(np.diff(f[both], 2)).mean()          # roughness of the contour on the common frames
     assert d2(f0h) <= d2(f0d)
+
+
+def test_independent_numpy_writing_of_the_harvest_array_stages():
+    """A second writing of Harvest's array stages in numpy / scipy (tests/independent_world.py: scipy's cheby1 + lfilter decimation,
+    numpy FFT filter bank, vectorised zero-crossing trains, numpy rfft refinement, lfilter smoothing) against the C restatement's
+    intermediate arrays.  The sequential contour tracking is the part not covered by this cross-check."""
+    from . import independent_world as iw
+    x = synthetic.synthetic_speech(0.6, stream=4)[:7200].astype(np.float64)
+    f0, t, d = ow.harvest(x, 24000, debug=True)
+    s = iw.harvest_stages_np(x, 24000)
+    assert np.allclose(s['y'], d['y'], rtol=0, atol=1e-11)
+    assert np.array_equal(s['raw'] > 0, d['raw'] > 0)
+    assert np.allclose(s['raw'], d['raw'], rtol=1e-8, atol=0)
+    assert s['nc'] == d['nc']
+    assert np.array_equal(s['cand'] > 0, d['cand'] > 0)
+    assert np.allclose(s['cand'], d['cand'], rtol=1e-7, atol=0)
+    assert np.allclose(s['score'], d['score'], rtol=1e-5, atol=0)
+    assert np.allclose(s['smooth'](d['best']), d['basic'], rtol=1e-9, atol=1e-9)
