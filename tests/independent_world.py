@@ -515,3 +515,104 @@ def harvest_stages_np(x, fs, f0_floor=71.0, f0_ceil=800.0):
         return out
 
     return dict(y=y, raw=raw, cand=cand, score=score, nc=nc, smooth=smooth)
+
+
+def harvest_fix_contour_np(cand, score, nc):
+    """Second writing of Harvest's FixF0Contour (SearchF0Base, FixStep1..4) on the pruned candidates [frames][columns]."""
+    cand, score = cand[:, :nc], score[:, :nc]
+    nf = len(cand)
+
+    def boundaries(f0):
+        v = (f0 > 0).astype(int); v[0] = v[-1] = 0
+        ch = np.nonzero(np.diff(v) != 0)[0] + 1
+        return [(int(ch[i]), int(ch[i + 1]) - 1) for i in range(0, len(ch) - 1, 2)]      # (first, last) frame of every voiced section
+
+    def select_best(ref, row, allowed):
+        err = np.abs(ref - row) / ref
+        ok = np.nonzero(err <= allowed)[0]
+        if len(ok) == 0:
+            return 0.0
+        m = err[ok].min()
+        return float(row[ok[err[ok] == m][-1]])                   # the last candidate with the minimal error
+
+    base = np.where(score.max(axis=1) > 0, cand[np.arange(nf), score.argmax(axis=1)], 0.0)
+    # step 1: rapid changes
+    s1 = np.zeros(nf)
+    for i in range(2, nf):
+        if base[i] == 0:
+            continue
+        ref = base[i - 1] * 2 - base[i - 2]
+        with np.errstate(divide='ignore', invalid='ignore'):
+            jump = abs((base[i] - ref) / ref) > 0.008 and abs(base[i] - base[i - 1]) / base[i - 1] > 0.008
+        s1[i] = 0.0 if jump else base[i]
+    # step 2: short sections
+    s2 = s1.copy()
+    for a, b in boundaries(s1):
+        if b - a < 6:
+            s2[a:b + 1] = 0.0
+    # step 3: extension along the candidates, selection of long sections, merge
+    secs = boundaries(s2)
+    rows = []
+    for a, b in secs:
+        row = np.zeros(nf); row[a:b + 1] = s2[a:b + 1]
+        rows.append(row)
+    ext = []
+    for (a, b), row in zip(secs, rows):
+        def walk(origin, last, step):
+            cur, where, miss = row[origin], origin, 0
+            for i in range(abs(last - origin) + 1):
+                idx = origin + step * (i + 1)
+                row[idx] = select_best(cur, cand[idx], 0.18)
+                if row[idx] == 0.0:
+                    miss += 1
+                else:
+                    cur, miss, where = row[idx], 0, idx
+                if miss == 4:
+                    break
+            return where
+        e_ = walk(b, min(nf - 2, b + 100), 1)
+        s_ = walk(a, max(1, a - 100), -1)
+        ext.append((s_, e_))
+    sel, mean_f0 = [], 0.0
+    for (s_, e_), row in zip(ext, rows):
+        mean_f0 = (mean_f0 + row[s_:e_].sum()) / (e_ - s_)          # the running value carries over (published source)
+        if 2200.0 / mean_f0 < e_ - s_:
+            sel.append((s_, e_, row))
+    s3 = s2.copy()
+    if sel:
+        order = list(range(len(sel)))
+        for i in range(1, len(sel)):
+            for j in range(i - 1, -1, -1):
+                if sel[order[j]][0] > sel[order[i]][0]:
+                    order[i], order[j] = order[j], order[i]
+                else:
+                    break
+        s3 = sel[0][2].copy()
+        b0, b1 = sel[0][0], sel[0][1]
+        bounds = [[s_, e_] for s_, e_, _ in sel]
+        for q in range(1, len(sel)):
+            o = order[q]
+            st2, ed2 = (b0, b1) if o == 0 else bounds[o]
+            row = sel[o][2]
+            if st2 - b1 > 0:
+                s3[st2:ed2 + 1] = row[st2:ed2 + 1]
+                b0, b1 = st2, ed2
+            elif not (b0 <= st2 and b1 >= ed2):
+                def sc(f0v, i):
+                    hit = cand[i] == f0v
+                    return float(score[i][hit].max()) if hit.any() else 0.0
+                sc1 = sum(sc(s3[i], i) for i in range(st2, b1 + 1))
+                sc2 = sum(sc(row[i], i) for i in range(st2, b1 + 1))
+                frm = b1 if sc1 > sc2 else st2
+                s3[frm:ed2 + 1] = row[frm:ed2 + 1]
+                b1 = ed2
+    # step 4: short gaps
+    s4 = s3.copy()
+    secs = boundaries(s3)
+    for (a0, b0_), (a1, _) in zip(secs[:-1], secs[1:]):
+        dist = a1 - b0_ - 1
+        if dist >= 9:
+            continue
+        t0, t1 = s3[b0_] + 1, s3[a1] - 1
+        s4[b0_ + 1:a1] = t0 + (t1 - t0) / (dist + 1.0) * np.arange(1, dist + 1)
+    return s4

@@ -135,7 +135,7 @@ def test_harvest_on_the_reference_recording():
 def test_independent_numpy_writing_of_the_harvest_array_stages():
     """A second writing of Harvest's array stages in numpy / scipy (tests/independent_world.py: scipy's cheby1 + lfilter decimation,
     numpy FFT filter bank, vectorised zero-crossing trains, numpy rfft refinement, lfilter smoothing) against the C restatement's
-    intermediate arrays.  The sequential contour tracking is the part not covered by this cross-check."""
+    intermediate arrays (the sequential contour tracking has its own second writing below)."""
     from . import independent_world as iw
     x = synthetic.synthetic_speech(0.6, stream=4)[:7200].astype(np.float64)
     f0, t, d = ow.harvest(x, 24000, debug=True)
@@ -148,3 +148,15 @@ def test_independent_numpy_writing_of_the_harvest_array_stages():
     assert np.allclose(s['cand'], d['cand'], rtol=1e-7, atol=0)
     assert np.allclose(s['score'], d['score'], rtol=1e-5, atol=0)
     assert np.allclose(s['smooth'](d['best']), d['basic'], rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize('seconds,stream', [(0.6, 4), (2.0, 1), (1.5, 2)])
+def test_independent_writing_of_the_contour_tracking(seconds, stream):
+    """FixF0Contour (SearchF0Base, FixStep1..4) written a second time in numpy (tests/independent_world.py) on the C restatement's pruned
+    candidates: the tracked contour must come out identical (the values are copies of candidates or linear bridges)."""
+    from . import independent_world as iw
+    x = synthetic.synthetic_speech(seconds, stream=stream).astype(np.float64)
+    f0, t, d = ow.harvest(x, 24000, debug=True)
+    best = iw.harvest_fix_contour_np(d['cand'], d['score'], d['nc'])
+    assert np.array_equal(best > 0, d['best'] > 0)
+    assert np.allclose(best, d['best'], rtol=1e-12, atol=0)
