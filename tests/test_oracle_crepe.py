@@ -73,3 +73,21 @@ def test_product_decoder_tables_equal_the_oracles():
     assert np.array_equal(np.linspace(0, 7180, 360) + 1997.3794084376191, oc.CENTS_MAPPING)
     # banded: transitions beyond +-11 bins are impossible
     assert np.isneginf(lt[0, 12]) and np.isfinite(lt[0, 11]) and np.isfinite(lt[200, 189]) and np.isneginf(lt[200, 188])
+
+
+def test_product_extract_f0_applies_the_references_voicing_rule(monkeypatch):
+    """realtime_yukarin_b200.crepe.extract_f0 = acoustic_feature_wrapper.py:66-80: frames are kept where the voicing HMM says voiced OR
+    the confidence exceeds 0.1, everything else is zeroed (host logic only: the device call is replaced by canned outputs)."""
+    from realtime_yukarin_b200 import crepe as pc
+    f0 = np.array([100.0, 110.0, 120.0, 130.0])
+    conf = np.array([0.05, 0.05, 0.2, 0.9], np.float32)
+    voicing = np.array([0, 1, 0, 1], np.int32)
+
+    def fake_predict(audio, sr, step_size=10.0, engine=None, details=False):
+        t = np.arange(4) * step_size / 1000.0
+        return (t, f0.copy(), conf, np.zeros((4, 360), np.float32), voicing, np.zeros(4, np.int32))
+
+    monkeypatch.setattr(pc, 'predict', fake_predict)
+    out, t = pc.extract_f0(np.zeros(100, np.float32), 24000, 5.0)
+    assert np.array_equal(out, [0.0, 110.0, 120.0, 130.0])
+    assert np.allclose(t, np.arange(4) * 0.005)
