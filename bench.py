@@ -478,8 +478,9 @@ def run_gpu(args):
                  d2h_bytes_per_step=int(main['produced'] / max(1, args.steps)) * 8 + B * (4 + 8)),
         gpu_launches=int(main['launches']), host_enqueue_ms_per_step=1000.0 * main['t_host'] / args.steps,
         clocks=main['clocks'],
-        roofline=dict(bound='tensor', kernel='stage-2 k4 layers 1..14: k_conv_halo (c1-c3, d3-d6) + k_conv_tc / k_splitk_reduce (c4-d2)' +
-                      ('' if B == 1 else ' + the two 3x3 edge layers (group forward timed as a whole)'), achieved=ach, peak=peaks['tflops'],
+        roofline=dict(bound='tensor', kernel=('stage-2 k4 layers 1..14: k_conv_tc (tcgen05, one tile per CTA) + k_splitk_reduce for c3-d3' if B == 1 else
+                                              'stage-2 k4 layers 1..14: k_conv_halo (persistent tcgen05, c1-c3 / d3-d6) + k_conv_tc / k_splitk_reduce (c4-d2)'
+                                              ' + the two 3x3 edge layers (group forward timed as a whole)'), achieved=ach, peak=peaks['tflops'],
                       unit='TFLOP/s', frac=(ach / peaks['tflops']) if ach else None, traffic=traffic, traffic_source=traffic_src,
                       peak_source=peaks['source'], peak_burst=peaks['burst'], peak_sustained=peaks['sustained'],
                       flop_per_step=fl, ms_per_step_in_kernel=(main['s2_ms'] / main['s2_runs']) if main['s2_runs'] else None,
