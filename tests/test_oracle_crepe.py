@@ -91,3 +91,29 @@ def test_product_extract_f0_applies_the_references_voicing_rule(monkeypatch):
     out, t = pc.extract_f0(np.zeros(100, np.float32), 24000, 5.0)
     assert np.array_equal(out, [0.0, 110.0, 120.0, 130.0])
     assert np.allclose(t, np.arange(4) * 0.005)
+
+
+def test_network_forward_equals_a_plain_numpy_writing():
+    """The torch-CPU forward of the restatement against a numpy-only one (sliding windows + einsum, explicit 'same' padding, pooling by
+    reshape): pins the padding / stride / flatten conventions independently of torch's conv1d."""
+    rng = np.random.default_rng(5)
+    w = synthetic.make_crepe_params(1, 'tiny')
+    x = rng.standard_normal(1200).astype(np.float32)
+    frames = oc.frames_of(x, 10.0)[:3].astype(np.float64)
+    h = frames[:, None, :]                                           # (frames, channels, time)
+    for l in range(6):
+        W = w[f'conv{l + 1}.W'].astype(np.float64)
+        k, s = oc.WIDTHS[l], oc.STRIDES[l]
+        n_out, left, right = oc.same_padding(h.shape[2], k, s)
+        hp = np.pad(h, ((0, 0), (0, 0), (left, right)))
+        win = np.lib.stride_tricks.sliding_window_view(hp, k, axis=2)[:, :, ::s][:, :, :n_out]      # (F, Cin, n_out, k)
+        h = np.einsum('fcok,nck->fno', win, W) + w[f'conv{l + 1}.b'][None, :, None]
+        h = np.maximum(h, 0.0)
+        a = w[f'bn{l + 1}.gamma'].astype(np.float64) / np.sqrt(w[f'bn{l + 1}.var'].astype(np.float64) + oc.BN_EPS)
+        h = h * a[None, :, None] + (w[f'bn{l + 1}.beta'] - w[f'bn{l + 1}.mean'] * a)[None, :, None]
+        h = h.reshape(h.shape[0], h.shape[1], h.shape[2] // 2, 2).max(axis=3)
+    flat = h.transpose(0, 2, 1).reshape(h.shape[0], -1)
+    z = flat @ w['dense.W'].astype(np.float64).T + w['dense.b']
+    ref = 1.0 / (1.0 + np.exp(-z))
+    got = oc.get_activation(x, w, 10.0)[:3]
+    assert np.abs(got - ref).max() < 2e-5
